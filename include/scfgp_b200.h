@@ -1,0 +1,152 @@
+/*
+ * scfgp_b200 -- C ABI of the B200-native SCFGP marginal-likelihood hot path.
+ *
+ * Drop-in boundary: the reference's hot path is the triple of compiled Theano
+ * callables produced by SCFGP.build_theano_models (SCFGP/SCFGP.py:92-148) and handed
+ * around by get_compiled_funcs() / optimize(funcs=...) (SCFGP/SCFGP.py:150-151,184,
+ * 209-210):
+ *     train_func(X, y)            -> [cost, alpha, Li]          SCFGP/SCFGP.py:132-135
+ *     train_iter_func(X, y)       -> same + optimizer update    SCFGP/SCFGP.py:136-137
+ *     pred_func(Xs, alpha, Li)    -> [mu_pred, std_pred]        SCFGP/SCFGP.py:145-148
+ * The entry points below are what a ctypes/cffi binding of those callables binds
+ * (see INTEGRATION.md).  Plain pointers and sizes only; all floating point is IEEE
+ * binary64 ("double"), matrices are row-major, exactly as the NumPy arrays the
+ * reference passes.  One deliberate deviation: the hyper-parameter vector is an
+ * explicit argument (the reference captures a Theano shared variable through
+ * `givens`, SCFGP/SCFGP.py:135,137,148).
+ *
+ * Threading: one handle = one caller thread.  No hidden global state.
+ * There is no CPU fallback: every call needs a CUDA device (sm_100a).
+ */
+#ifndef SCFGP_B200_H
+#define SCFGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scfgp_handle scfgp_handle;
+
+/* status codes (the reference raises: numpy.linalg.LinAlgError from Theano's
+ * Cholesky thunk at SCFGP/SCFGP.py:106, shape errors from theano.function) */
+enum {
+  SCFGP_OK = 0,
+  SCFGP_ERR_ARG = 1,         /* bad shape / null pointer / no data set            */
+  SCFGP_ERR_CUDA = 2,        /* CUDA runtime error, text in scfgp_last_error()    */
+  SCFGP_ERR_NOT_PD = 3,      /* A = PhiT.Phi + (sig2_n+1e-6) I not positive definite;
+                                pivot index in scfgp_last_pivot()                 */
+  SCFGP_ERR_NONFINITE = 4    /* cost is NaN/Inf                                   */
+};
+
+/* fftype: the README-generation constructor argument (README.md:44-53); the snapshot
+ * source implements only the phase variant (SCFGP/SCFGP.py:83-89). */
+enum {
+  SCFGP_FF_PHASE = 0,        /* Z = X.W + (P - mean_d(F))   (SCFGP/SCFGP.py:88-89,99-100) */
+  SCFGP_FF_NOPHASE = 1       /* Z = X.W                                                */
+};
+
+/* ABI version of this header */
+int scfgp_abi_version(void);
+
+/* Create a model-shaped handle on CUDA device `device`.
+ *   D = input columns, S = sparsity/rank, M = nfeats/feature_size
+ *   (SCFGP.__init__, SCFGP/SCFGP.py:33-37; D from set_data, SCFGP/SCFGP.py:165). */
+int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out);
+int scfgp_destroy(scfgp_handle* h);
+
+/* Last error text / failing Cholesky pivot (0-based row of A), per handle. */
+const char* scfgp_last_error(const scfgp_handle* h);
+long long scfgp_last_pivot(const scfgp_handle* h);
+
+/* Number of hyper-parameters P = 3 + D*S + M*S + S + M (SCFGP.init_params,
+ * SCFGP/SCFGP.py:64-72) and of features K = 2*(M+S) (SCFGP/SCFGP.py:99-102). */
+long long scfgp_num_params(const scfgp_handle* h);
+long long scfgp_num_features(const scfgp_handle* h);
+
+/* Run all work of this handle on `cuda_stream` (a cudaStream_t; NULL = default). */
+int scfgp_set_stream(scfgp_handle* h, void* cuda_stream);
+
+/* Rows per streamed chunk (multiple of 128; default 2048).  Tuning knob only. */
+int scfgp_set_chunk_rows(scfgp_handle* h, int rows);
+
+/* Training data of train_func/train_iter_func (the X, y arguments at
+ * SCFGP/SCFGP.py:230,237,265).  X is N x D row-major, y has N entries.
+ *   _host  : copies from host memory into device buffers owned by the handle.
+ *   _device: borrows device pointers (zero-copy hand-off, e.g. torch data_ptr());
+ *            the caller keeps them alive until the next set_data/destroy.
+ * `n_global` is the row count of the whole job (sum over ranks); pass N when
+ * single-GPU.  It is the N of `cost = (nlml+penalty)/N` and `2(N-M)a`
+ * (SCFGP/SCFGP.py:126,128). */
+int scfgp_set_data_host(scfgp_handle* h, const double* X, const double* y, long long N,
+                        long long n_global);
+int scfgp_set_data_device(scfgp_handle* h, const double* dX, const double* dy, long long N,
+                          long long n_global);
+
+/* train_func(X, y) with explicit hyper-parameters, plus the gradient the reference
+ * consumes in-graph (TT.grad, SCFGP/SCFGP.py:129).
+ *   params : P doubles (host)
+ *   cost   : 1 double out
+ *   grad   : P doubles out, or NULL (then only the forward passes run)
+ *   alpha  : K doubles out, or NULL          (K x 1 in the reference)
+ *   Li     : K*K doubles out row-major, or NULL  (inverse lower Cholesky factor)
+ * Single-GPU convenience: runs every phase below in order. */
+int scfgp_eval(scfgp_handle* h, const double* params, double* cost, double* grad,
+               double* alpha, double* Li);
+
+/* pred_func(Xs, alpha, Li) -> mu_pred (T), std_pred (T)  (SCFGP/SCFGP.py:138-148).
+ * Xs is T x D row-major on the host; alpha/Li as returned by scfgp_eval, or NULL to
+ * use the factors of the last evaluation still resident on the device. */
+int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long long T,
+                  const double* alpha, const double* Li, double* mu, double* std);
+/* same with device-resident inputs/outputs (batched predict over shards) */
+int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dXs, long long T,
+                         double* dmu, double* dstd);
+
+/* ---- phase API (multi-GPU: rows are sharded over ranks, the host all-reduces the
+ * device buffer named by each phase between calls; every rank then runs the small
+ * replicated phases on identical inputs).  Order:
+ *   begin -> pass1 -> [allreduce RED1] -> factor -> pass2 -> [allreduce RED2]
+ *         -> backward -> pass3 -> [allreduce RED3] -> finish
+ * (forward only: begin -> pass1 -> factor -> pass2 -> finish with grad==NULL). */
+enum { SCFGP_RED1 = 1, SCFGP_RED2 = 2, SCFGP_RED3 = 3 };
+int scfgp_eval_begin(scfgp_handle* h, const double* params, int want_grad);
+int scfgp_eval_pass1(scfgp_handle* h);     /* G = PhiT.Phi, p = PhiT.y, yy          */
+int scfgp_eval_factor(scfgp_handle* h);    /* L, Li, beta, alpha, B = A^-1          */
+int scfgp_eval_pass2(scfgp_handle* h);     /* v, mu, E, g_tau, q, H                 */
+int scfgp_eval_backward(scfgp_handle* h);  /* Abar, pbar (small, replicated)        */
+int scfgp_eval_pass3(scfgp_handle* h);     /* dW, dphi, sbar                        */
+int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha, double* Li);
+/* Device pointer + element count (doubles) of the contiguous buffer a phase reduces. */
+int scfgp_reduce_buffer(scfgp_handle* h, int which, void** dptr, long long* count);
+
+/* Device-resident results of the last evaluation (valid until the next one). */
+int scfgp_device_factors(scfgp_handle* h, void** d_alpha, void** d_Li, long long* ld_Li);
+
+/* Counters for bench.py: kernels launched by this handle since creation, and the
+ * device time (ms, CUDA events on the handle's stream) of the three streaming passes
+ * of the last evaluation. */
+long long scfgp_launch_count(const scfgp_handle* h);
+int scfgp_last_pass_ms(const scfgp_handle* h, float* pass1, float* pass2, float* pass3,
+                       float* dense);
+
+/* ---- self-test hooks used by tests/ (each runs ONE kernel family on caller data so a
+ * failing parity test names the kernel, not the pipeline).  Host pointers, row-major. */
+/* C (m x n) = op(A).op(B)^T-style products through the DMMA mainloop.
+ *   layout 0: NT  C[i,j] = sum_k A[i,k] B[j,k]   (A m x k, B n x k)
+ *   layout 1: TN  C[i,j] = sum_r A[r,i] B[r,j]   (A k x m, B k x n)
+ *   layout 2: NN  C[i,j] = sum_k A[i,k] B[k,j]   (A m x k, B k x n) */
+int scfgp_dbg_gemm(int device, int layout, int m, int n, int k, const double* A,
+                   const double* B, double* C);
+/* lower Cholesky + inverse factor of a symmetric K x K matrix (info = pivot+1 or 0) */
+int scfgp_dbg_factor(int device, int K, const double* A, double* L, double* Li, long long* info);
+/* Phi (N x K) for given params through the feature kernel */
+int scfgp_dbg_features(scfgp_handle* h, const double* params, const double* X, long long N,
+                       double* Phi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCFGP_B200_H */

@@ -1,0 +1,541 @@
+// Kernels of the SCFGP marginal-likelihood hot path (sm_100a, FP64 DMMA).
+// Math: SURVEY.md Appendix A, restating SCFGP/SCFGP.py:92-148 of the reference.
+#pragma once
+#include "gemm_dmma.cuh"
+
+namespace scfgp {
+
+// ------------------------------------------------------------------------------------
+// tile shapes
+// ------------------------------------------------------------------------------------
+using CfgBig = TileCfg<128, 128, 64, 32, 3>;   // 8 warps, 64 accumulators / thread
+using CfgTall = TileCfg<128, 64, 32, 32, 3>;   // 8 warps, features / panels
+using CfgWide = TileCfg<64, 128, 32, 32, 3>;   // 8 warps, D x J contraction
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------
+// generic GEMM kernel:  C = beta*C + alpha * (A op B)   over a list of tiles
+//   item.x = tile row block, item.y = tile col block, item.z = reduction start,
+//   item.w = reduction length
+// ------------------------------------------------------------------------------------
+template <class Cfg, bool AK, bool BKM, int AVEC, int BVEC>
+__global__ void __launch_bounds__(Cfg::NT, 1)
+k_gemm(const double* __restrict__ A, long long lda, int a_rows,
+       const double* __restrict__ B, long long ldb, int b_rows,
+       double* C, long long ldc, double alpha, double beta,
+       const int4* __restrict__ items, int depth_arg) {
+  // C may alias A (in-place panel solve): every read of the tile's operands completes
+  // in the mainloop before the epilogue stores.
+  extern __shared__ __align__(16) double smem[];
+  const int4 it = items[blockIdx.x];
+  const int m0 = it.x * Cfg::BM, n0 = it.y * Cfg::BN;
+  const int k0 = it.z, depth = it.w >= 0 ? it.w : depth_arg - k0;
+  double acc[Cfg::MI][Cfg::NI][2];
+  zero_acc<Cfg>(acc);
+  IdentMap am{m0, a_rows}, bm{n0, b_rows};
+  const double* Ap = AK ? A + k0 : A + (long long)k0 * lda;
+  const double* Bp = BKM ? B + k0 : B + (long long)k0 * ldb;
+  gemm_mainloop<Cfg, AK, BKM, AVEC, BVEC>(acc, Ap, lda, am, Bp, ldb, bm, depth, smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i) {
+    int r = m0 + wm0 + 8 * i + g;
+    if (r >= a_rows) continue;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int c = n0 + wn0 + 8 * j + 2 * t + e;
+        if (c < b_rows) {
+          double* p = C + (long long)r * ldc + c;
+          double v = alpha * acc[i][j][e];
+          if (beta != 0.0) v += beta * (*p);
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// (a) feature map  Phi = s*[cos(X.W + phi) | sin(X.W + phi)]        SCFGP.py:98-102
+//   X chunk (rows x D, row-major), Wt (J x D row-major, ld = ldw), phi (J)
+//   Phi slab (rows x K, ld = ldp);  optional Psi = rowscale[n] * Phi
+//   grid = rowblocks(128) * featblocks(64)
+// ------------------------------------------------------------------------------------
+template <int XVEC>
+__global__ void __launch_bounds__(CfgTall::NT, 1)
+k_features(const double* __restrict__ X, long long ldx, int rows, int D,
+           const double* __restrict__ Wt, long long ldw, const double* __restrict__ phi,
+           int J, double s, double* __restrict__ Phi, long long ldp,
+           const double* __restrict__ rowscale, double* __restrict__ Psi, int nfb) {
+  using Cfg = CfgTall;
+  extern __shared__ __align__(16) double smem[];
+  const int rb = blockIdx.x / nfb, fb = blockIdx.x % nfb;
+  const int m0 = rb * Cfg::BM, n0 = fb * Cfg::BN;
+  double acc[Cfg::MI][Cfg::NI][2];
+  zero_acc<Cfg>(acc);
+  IdentMap am{m0, rows}, bm{n0, J};
+  gemm_mainloop<Cfg, true, true, XVEC, 2>(acc, X, ldx, am, Wt, ldw, bm, D, smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+#pragma unroll
+  for (int j = 0; j < Cfg::NI; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int f = n0 + wn0 + 8 * j + 2 * t + e;
+      if (f >= J) continue;
+      const double ph = phi[f];
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i) {
+        const int r = m0 + wm0 + 8 * i + g;
+        if (r >= rows) continue;
+        double sn, cs;
+        sincos(acc[i][j][e] + ph, &sn, &cs);
+        cs *= s; sn *= s;
+        double* row = Phi + (long long)r * ldp;
+        row[f] = cs;
+        row[J + f] = sn;
+        if (Psi != nullptr) {
+          const double w = rowscale[r];
+          double* prow = Psi + (long long)r * ldp;
+          prow[f] = w * cs;
+          prow[J + f] = w * sn;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// weighted column sums of a slab:  part[rs][k] += sum_{n in split rs} w[n]*S[n,k]
+//   (p = PhiT.y, q = PhiT.gmu, dphi = colsum(Zbar));  w == nullptr -> 1
+//   grid = (ceil(cols/256), nsplit)
+// ------------------------------------------------------------------------------------
+__global__ void k_colsum(const double* __restrict__ S, long long lds, int rows, int cols,
+                         const double* __restrict__ w, double* __restrict__ part, long long ldpart) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cols) return;
+  const int nsplit = gridDim.y;
+  const int per = (rows + nsplit - 1) / nsplit;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    double w0 = w ? w[r] : 1.0, w1 = w ? w[r + 1] : 1.0, w2 = w ? w[r + 2] : 1.0, w3 = w ? w[r + 3] : 1.0;
+    a0 += w0 * S[(long long)r * lds + k];
+    a1 += w1 * S[(long long)(r + 1) * lds + k];
+    a2 += w2 * S[(long long)(r + 2) * lds + k];
+    a3 += w3 * S[(long long)(r + 3) * lds + k];
+  }
+  for (; r < r1; ++r) a0 += (w ? w[r] : 1.0) * S[(long long)r * lds + k];
+  part[(long long)blockIdx.y * ldpart + k] += (a0 + a1) + (a2 + a3);
+}
+
+// out[k] (+)= sum_rs part[rs][k]
+__global__ void k_sum_parts(const double* __restrict__ part, long long ldpart, int nsplit, int cols,
+                            double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cols) return;
+  double a = 0;
+  for (int s = 0; s < nsplit; ++s) a += part[(long long)s * ldpart + k];
+  out[k] = a;
+}
+
+// sum of squares / dot products of short vectors into scalars (single block)
+//   out[0] = sum a[i]*b[i]
+__global__ void k_dot(const double* __restrict__ a, const double* __restrict__ b, long long n,
+                      double* __restrict__ out, int accumulate) {
+  __shared__ double sh[32];
+  double v = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) v += a[i] * b[i];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + v : v;
+  }
+}
+
+// yy partials over a long vector: part[blockIdx.x] += sum of squares of its slice
+__global__ void k_sumsq_part(const double* __restrict__ y, long long n, double* __restrict__ part) {
+  __shared__ double sh[32];
+  double v = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    v += y[i] * y[i];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) part[blockIdx.x] += v;
+  }
+}
+
+// out[o] = sum_i part[i*stride + o]   for o < nout   (single block, deterministic order)
+__global__ void k_reduce_slots(const double* __restrict__ part, int nslots, int stride, int nout,
+                               double* __restrict__ out) {
+  __shared__ double sh[32];
+  for (int o = 0; o < nout; ++o) {
+    double v = 0;
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) v += part[(long long)i * stride + o];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) out[o] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// (a6) T = Phi.LiT, v_n = |T_n|^2 -- only the row sums of squares leave the tile.
+//   items: (rb, kb); Li lower triangular => reduction depth min(K, (kb+1)*128)
+//   vpart[kb][n] = sum over the tile's 128 columns                    SCFGP.py:112
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CfgBig::NT, 1)
+k_tgemm_rowsq(const double* __restrict__ Phi, long long ldp, int rows, int K,
+              const double* __restrict__ Li, long long ldl,
+              double* __restrict__ vpart, long long ldv, const int4* __restrict__ items) {
+  using Cfg = CfgBig;
+  extern __shared__ __align__(16) double smem[];
+  const int4 it = items[blockIdx.x];
+  const int m0 = it.x * Cfg::BM, n0 = it.y * Cfg::BN;
+  if (m0 >= rows) return;  // short last chunk: whole CTA leaves before any barrier
+  const int depth = min(K, n0 + Cfg::BN);
+  double acc[Cfg::MI][Cfg::NI][2];
+  zero_acc<Cfg>(acc);
+  IdentMap am{m0, rows}, bm{n0, K};
+  gemm_mainloop<Cfg, true, true, 2, 2>(acc, Phi, ldp, am, Li, ldl, bm, depth, smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wmi = warp / Cfg::WARPS_N, wni = warp % Cfg::WARPS_N;
+  double* red = smem;  // [WARPS_N][BM]
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i) {
+    double sq = 0;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) sq += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    if (t == 0) red[wni * Cfg::BM + wmi * Cfg::WM + 8 * i + g] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x < Cfg::BM) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < Cfg::WARPS_N; ++w) v += red[w * Cfg::BM + threadIdx.x];
+    int r = m0 + threadIdx.x;
+    if (r < rows) vpart[(long long)it.y * ldv + r] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// per-row moments and adjoint seeds (A.2 pass 2, A.3)               SCFGP.py:111-124
+//   mu = Phi.alpha, v = sum_kb vpart, r = mu - y, d = tau (v+1)
+//   e = (r^2+v)/d + log(2 pi d)          (closed form of the 30-node Gauss-Hermite sum)
+//   k = -(r^2+v)/d^2 + 1/d ; gmu = 2r/d ; gv = 1/d + tau k ; g_tau += k (v+1)
+//   writes gmu, gv (global row arrays), Psi = gv*Phi, slot partials of E and g_tau
+//   one warp per row; grid-stride; block b owns slot b of `slots` (2 doubles)
+// ------------------------------------------------------------------------------------
+__global__ void k_seeds(const double* __restrict__ Phi, long long ldp, int rows, int K,
+                        const double* __restrict__ alpha, const double* __restrict__ vpart,
+                        long long ldv, int nkb, const double* __restrict__ y, double tau,
+                        double* __restrict__ gmu, double* __restrict__ gv,
+                        double* __restrict__ Psi, double* __restrict__ slots, int want_grad) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double Eacc = 0, Tacc = 0;
+  for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+    const double* row = Phi + (long long)r * ldp;
+    double mu = 0;
+    for (int k = lane; k < K; k += 32) mu += row[k] * alpha[k];
+    mu = warp_sum(mu);
+    double v = 0;
+    for (int b = 0; b < nkb; ++b) v += vpart[(long long)b * ldv + r];
+    const double res = mu - y[r];
+    const double d = tau * (v + 1.0);
+    const double num = res * res + v;
+    const double kk = -num / (d * d) + 1.0 / d;
+    const double gm = 2.0 * res / d;
+    const double gvv = 1.0 / d + tau * kk;
+    if (lane == 0) {
+      Eacc += num / d + log(6.283185307179586476925286766559 * d);
+      Tacc += kk * (v + 1.0);
+      gmu[r] = gm;
+      gv[r] = gvv;
+    }
+    if (want_grad) {
+      double* prow = Psi + (long long)r * ldp;
+      for (int k = lane; k < K; k += 32) prow[k] = gvv * row[k];
+    }
+  }
+  __shared__ double sh[2][32];
+  if (lane == 0) { sh[0][warp] = Eacc; sh[1][warp] = Tacc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 0, tt = 0;
+    for (int w = 0; w < nw; ++w) { e += sh[0][w]; tt += sh[1][w]; }
+    slots[2 * blockIdx.x] += e;
+    slots[2 * blockIdx.x + 1] += tt;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// (c) backward: Phibar = Phi.(2 Abar) + Psi.(2 B) + y pbarT + gmu alphaT, fused with the
+// trig derivative:  Zbar = -Phibar_c * Phi_s + Phibar_s * Phi_c ;  sbar += <Phibar, Phi>
+//   tile = 128 rows x 64 features; the 128 tile columns are ordered so that each warp's
+//   32 columns are [16 cos | 16 sin] of the same 16 features (both halves of a feature
+//   land in the same thread).
+//   items: (rb, fb).  A2/B2 are symmetric, so their rows serve as K-major B operands.
+// ------------------------------------------------------------------------------------
+struct TrigPairMap {
+  int fbase;  // first feature of this tile
+  int J;
+  __device__ __forceinline__ int operator()(int c) const {
+    const int wc = c >> 5, sub = c & 31;
+    const int f = fbase + wc * 16 + (sub & 15);
+    if (f >= J) return -1;
+    return (sub < 16) ? f : J + f;
+  }
+};
+
+__global__ void __launch_bounds__(CfgBig::NT, 1)
+k_backward(const double* __restrict__ Phi, const double* __restrict__ Psi, long long ldp,
+           int rows, int K, int J, const double* __restrict__ A2, const double* __restrict__ B2,
+           long long ldm, const double* __restrict__ y, const double* __restrict__ gmu,
+           const double* __restrict__ pbar, const double* __restrict__ alpha,
+           double* __restrict__ Zbar, long long ldz, double* __restrict__ slots,
+           const int4* __restrict__ items) {
+  using Cfg = CfgBig;
+  extern __shared__ __align__(16) double smem[];
+  const int4 it = items[blockIdx.x];
+  const int m0 = it.x * Cfg::BM;
+  const int f0 = it.y * 64;
+  double acc[Cfg::MI][Cfg::NI][2];
+  zero_acc<Cfg>(acc);
+  IdentMap am{m0, rows};
+  TrigPairMap bm{f0, J};
+  gemm_mainloop<Cfg, true, true, 2, 2>(acc, Phi, ldp, am, A2, ldm, bm, K, smem);
+  gemm_mainloop<Cfg, true, true, 2, 2>(acc, Psi, ldp, am, B2, ldm, bm, K, smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wmi = warp / Cfg::WARPS_N, wni = warp % Cfg::WARPS_N;
+  double sacc = 0;
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i) {
+    const int r = m0 + wmi * Cfg::WM + 8 * i + g;
+    if (r >= rows) continue;
+    const double yn = y[r], gm = gmu[r];
+    const double* prow = Phi + (long long)r * ldp;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int f = f0 + wni * 16 + 8 * jj + 2 * t + e;
+        if (f >= J) continue;
+        const double pc = acc[i][jj][e] + yn * pbar[f] + gm * alpha[f];
+        const double ps = acc[i][jj + 2][e] + yn * pbar[J + f] + gm * alpha[J + f];
+        const double phc = prow[f], phs = prow[J + f];
+        Zbar[(long long)r * ldz + f] = -pc * phs + ps * phc;
+        sacc += pc * phc + ps * phs;
+      }
+    }
+  }
+  sacc = warp_sum(sacc);
+  __shared__ double sh[Cfg::NWARPS];
+  if (lane == 0) sh[warp] = sacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0;
+    for (int w = 0; w < Cfg::NWARPS; ++w) v += sh[w];
+    slots[blockIdx.x] += v;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// predictive finish:  mu = Phi.alpha ; std = sqrt(tau (1 + v))          SCFGP.py:144-145
+// ------------------------------------------------------------------------------------
+__global__ void k_pred_finish(const double* __restrict__ Phi, long long ldp, int rows, int K,
+                              const double* __restrict__ alpha, const double* __restrict__ vpart,
+                              long long ldv, int nkb, double tau, double* __restrict__ mu,
+                              double* __restrict__ sd) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+    const double* row = Phi + (long long)r * ldp;
+    double m = 0;
+    for (int k = lane; k < K; k += 32) m += row[k] * alpha[k];
+    m = warp_sum(m);
+    if (lane == 0) {
+      double v = 0;
+      for (int b = 0; b < nkb; ++b) v += vpart[(long long)b * ldv + r];
+      mu[r] = m;
+      sd[r] = sqrt(tau * (1.0 + v));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// (d) small replicated dense kernels (K x K, fp64)
+// ------------------------------------------------------------------------------------
+constexpr int NB = 64;  // Cholesky block
+
+__global__ void k_add_diag(double* __restrict__ A, long long ld, int K, double val) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K) A[(long long)i * ld + i] += val;
+}
+
+// Factor the nb x nb diagonal block at (k0,k0) in place (lower), zero its strict upper
+// part, and write inv(L11) (lower) to Dinv (NB x NB, zero padded).        SCFGP.py:106-107
+constexpr size_t POTRF_SMEM = 2 * NB * (NB + 1) * sizeof(double);
+__global__ void __launch_bounds__(256, 1)
+k_potrf_diag(double* __restrict__ A, long long ld, int k0, int nb, double* __restrict__ Dinv,
+             long long* __restrict__ info) {
+  extern __shared__ __align__(16) double smem_pd[];
+  double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_pd);
+  double (*b)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_pd + NB * (NB + 1));
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    int i = e / NB, j = e % NB;
+    a[i][j] = (i < nb && j <= i) ? A[(long long)(k0 + i) * ld + k0 + j] : 0.0;
+    b[i][j] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (tid == 0) {
+      double d = a[j][j];
+      if (!(d > 0.0)) {
+        if (*info == 0) *info = (long long)(k0 + j) + 1;
+      }
+      a[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    const double dj = a[j][j];
+    for (int i = j + 1 + tid; i < nb; i += blockDim.x) a[i][j] /= dj;
+    __syncthreads();
+    const int rem = nb - j - 1;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      int i = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= i) a[i][c] -= a[i][j] * a[c][j];
+    }
+    __syncthreads();
+  }
+  // inverse by forward substitution, one column per thread
+  if (tid < nb) {
+    const int c = tid;
+    b[c][c] = 1.0 / a[c][c];
+    for (int i = c + 1; i < nb; ++i) {
+      double sacc = 0;
+      for (int m = c; m < i; ++m) sacc += a[i][m] * b[m][c];
+      b[i][c] = -sacc / a[i][i];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    int i = e / NB, j = e % NB;
+    if (i < nb && j < nb) A[(long long)(k0 + i) * ld + k0 + j] = (j <= i) ? a[i][j] : 0.0;
+    Dinv[e] = b[i][j];
+  }
+}
+
+// zero the strict upper triangle / mirror lower to upper
+__global__ void k_zero_upper(double* __restrict__ A, long long ld, int K) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)K * K) return;
+  int i = (int)(e / K), j = (int)(e % K);
+  if (j > i) A[(long long)i * ld + j] = 0.0;
+}
+__global__ void k_symmetrize(double* __restrict__ A, long long ld, int K) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  int i = bi * 32 + threadIdx.y, j = bj * 32 + threadIdx.x;
+  tile[threadIdx.y][threadIdx.x] = (i < K && j < K) ? A[(long long)i * ld + j] : 0.0;
+  __syncthreads();
+  // write transposed block into (bj, bi)
+  int ti = bj * 32 + threadIdx.y, tj = bi * 32 + threadIdx.x;
+  if (ti < K && tj < K && tj > ti) A[(long long)ti * ld + tj] = tile[threadIdx.x][threadIdx.y];
+}
+
+// copy a block (used to place inv(L_ii) on Li's diagonal)
+__global__ void k_copy_block(const double* __restrict__ src, long long lds, double* __restrict__ dst,
+                             long long ldd, int rows, int cols) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * cols) return;
+  int i = e / cols, j = e % cols;
+  dst[(long long)i * ldd + j] = src[(long long)i * lds + j];
+}
+
+// y = M x  (row-major M, one warp per row);  trans handled by k_colsum
+__global__ void k_gemv_n(const double* __restrict__ Mx, long long ld, int rows, int cols,
+                         const double* __restrict__ x, double* __restrict__ yout) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+    const double* row = Mx + (long long)r * ld;
+    double v = 0;
+    for (int k = lane; k < cols; k += 32) v += row[k] * x[k];
+    v = warp_sum(v);
+    if (lane == 0) yout[r] = v;
+  }
+}
+
+// scalars of the factor phase: out[0] = sum log L_ii, out[1] = beta.beta, out[2] = p.alpha
+__global__ void k_factor_scalars(const double* __restrict__ L, long long ld, int K,
+                                 const double* __restrict__ beta, const double* __restrict__ p,
+                                 const double* __restrict__ alpha, double* __restrict__ out) {
+  __shared__ double sh[3][32];
+  double a = 0, b = 0, c = 0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    a += log(L[(long long)i * ld + i]);
+    b += beta[i] * beta[i];
+    c += p[i] * alpha[i];
+  }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; sh[2][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = b = c = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; c += sh[2][w]; }
+    out[0] = a; out[1] = b; out[2] = c;
+  }
+}
+
+// A2 = 2*(B - BHB - 0.5 (t aT + a tT) + a aT / sig2n),  B2 = 2 B,  pbar = t - 2 a / sig2n,
+// trace slots: tr[blockIdx.x] = partial trace of Abar.                         (A.4)
+__global__ void k_abar(const double* __restrict__ Bm, const double* __restrict__ BHB, long long ld, int K,
+                       const double* __restrict__ tvec, const double* __restrict__ alpha, double sig2n,
+                       double* __restrict__ A2, double* __restrict__ B2, double* __restrict__ pbar,
+                       double* __restrict__ trslots) {
+  const int i = blockIdx.x;
+  if (i >= K) return;
+  const double ti = tvec[i], ai = alpha[i];
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    const long long o = (long long)i * ld + j;
+    const double bij = Bm[o];
+    const double ab = bij - BHB[o] - 0.5 * (ti * alpha[j] + ai * tvec[j]) + ai * alpha[j] / sig2n;
+    A2[o] = 2.0 * ab;
+    B2[o] = 2.0 * bij;
+    if (j == i) trslots[i] = ab;
+  }
+  if (threadIdx.x == 0) pbar[i] = ti - 2.0 * ai / sig2n;
+}
+
+}  // namespace scfgp

@@ -1,0 +1,988 @@
+// C ABI + host orchestration of the SCFGP hot path on one B200 (sm_100a).
+// Interface: include/scfgp_b200.h.  Math: SURVEY.md Appendix A (SCFGP/SCFGP.py:74-148).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include <cuda_runtime.h>
+
+#include "../../include/scfgp_b200.h"
+#include "kernels.cuh"
+
+using namespace scfgp;
+
+namespace {
+
+constexpr double kEps = 1e-6;  // jitter, SCFGP/SCFGP.py:93
+constexpr int kColSplit = 8;   // row splits of the column-sum kernels
+constexpr int kSeedBlocks = 296;
+
+struct ItemList {
+  int4* d = nullptr;
+  int count = 0;
+};
+
+}  // namespace
+
+struct scfgp_handle {
+  int D = 0, S = 0, M = 0, J = 0, K = 0, fftype = 0, device = 0;
+  long long P = 0;
+  cudaStream_t stream = nullptr;
+  long long N = 0, Nglobal = 0;
+  const double* dX = nullptr;
+  const double* dy = nullptr;
+  double* ownX = nullptr;
+  double* owny = nullptr;
+  int R = 2048;  // rows per chunk
+  int xvec = 2;
+  long long ldk = 0;  // leading dimension of K x K matrices and slabs
+  long long ldj = 0;  // leading dimension of D x J / Zbar
+  long long ldw = 0;
+
+  // device buffers
+  double *Wt = nullptr, *phi = nullptr;
+  double *PhiS = nullptr, *PsiS = nullptr, *Zbar = nullptr, *vpart = nullptr;
+  double *red1 = nullptr, *red2 = nullptr, *red3 = nullptr;
+  double *L = nullptr, *Li = nullptr, *Bm = nullptr, *BH = nullptr, *BHB = nullptr, *A2 = nullptr,
+         *B2 = nullptr, *Dinv = nullptr, *tmpS = nullptr;
+  double *alpha = nullptr, *beta = nullptr, *tvec = nullptr, *pbar = nullptr, *scal = nullptr;
+  double *gmu = nullptr, *gv = nullptr;
+  long long row_cap = 0;
+  double *colpart = nullptr, *slots = nullptr, *trslots = nullptr;
+  long long* info = nullptr;
+  int nrb_cap = 0;
+
+  // work lists
+  ItemList lowerK, fullK, tgemm, bwd, dw;
+  std::vector<ItemList> potrf_panel, potrf_trail, trtri_s, trtri_x;
+  std::vector<int4*> to_free;
+
+  // host state of the evaluation in flight
+  std::vector<double> params, lF, rF, F, W, phi_h;
+  double a = 0, b = 0, c = 0, sig2n = 0, sigf = 0, tau = 0, s = 0;
+  int want_grad = 0;
+  bool have_factors = false;
+
+  std::string err;
+  long long pivot = -1;
+  long long launches = 0;
+  cudaEvent_t ev[8] = {};
+  float ms_pass[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return SCFGP_ERR_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+#define CKL()                                                                           \
+  do {                                                                                  \
+    h->launches++;                                                                      \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess) {                                                            \
+      h->err = std::string("kernel launch: ") + cudaGetErrorString(e_) + " at line " +  \
+               std::to_string(__LINE__);                                                \
+      return SCFGP_ERR_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <class T>
+int dalloc(scfgp_handle* h, T** p, size_t n) {
+  CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  CK(cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  return SCFGP_OK;
+}
+
+int upload_items(scfgp_handle* h, const std::vector<int4>& v, ItemList* out) {
+  out->count = (int)v.size();
+  out->d = nullptr;
+  if (v.empty()) return SCFGP_OK;
+  CK(cudaMalloc((void**)&out->d, v.size() * sizeof(int4)));
+  CK(cudaMemcpy(out->d, v.data(), v.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  h->to_free.push_back(out->d);
+  return SCFGP_OK;
+}
+
+// lower-triangular tile list of an m x m output with square tiles `bs`
+std::vector<int4> lower_tiles(int m, int bs, int k0, int depth) {
+  std::vector<int4> v;
+  int nb = cdiv(m, bs);
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j <= i; ++j) v.push_back(make_int4(i, j, k0, depth));
+  return v;
+}
+
+template <class Cfg, bool AK, bool BKM, int AVEC, int BVEC>
+int launch_gemm(scfgp_handle* h, const double* A, long long lda, int a_rows, const double* B,
+                long long ldb, int b_rows, double* C, long long ldc, double alpha, double beta,
+                const ItemList& items, int depth_arg) {
+  if (items.count == 0) return SCFGP_OK;
+  constexpr size_t smem = SmemSize<Cfg, AK, BKM>::BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(k_gemm<Cfg, AK, BKM, AVEC, BVEC>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_gemm<Cfg, AK, BKM, AVEC, BVEC><<<items.count, Cfg::NT, smem, h->stream>>>(
+      A, lda, a_rows, B, ldb, b_rows, C, ldc, alpha, beta, items.d, depth_arg);
+  CKL();
+  return SCFGP_OK;
+}
+
+int set_kernel_attrs(scfgp_handle* h) {
+  CK(cudaFuncSetAttribute(k_features<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgTall, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(k_features<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgTall, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(k_tgemm_rowsq, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgBig, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgBig, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+  return SCFGP_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// host-side unpack of the flat parameter vector            SCFGP/SCFGP.py:74-90, A.1
+// ---------------------------------------------------------------------------------
+int unpack_and_upload(scfgp_handle* h, const double* params) {
+  const int D = h->D, S = h->S, M = h->M, J = h->J;
+  h->params.assign(params, params + h->P);
+  const double* p = h->params.data();
+  h->a = p[0]; h->b = p[1]; h->c = p[2];
+  const double* lf = p + 3;
+  const double* rf = lf + (size_t)D * S;
+  const double* lp = rf + (size_t)M * S;
+  const double* pp = lp + S;
+  h->lF.assign(lf, lf + (size_t)D * S);
+  h->rF.assign(rf, rf + (size_t)M * S);
+  h->F.assign((size_t)D * M, 0.0);
+  for (int d = 0; d < D; ++d)
+    for (int m = 0; m < M; ++m) {
+      double acc = 0;
+      for (int s2 = 0; s2 < S; ++s2) acc += lf[(size_t)d * S + s2] * rf[(size_t)m * S + s2];
+      h->F[(size_t)d * M + m] = acc;
+    }
+  h->phi_h.assign(J, 0.0);
+  if (h->fftype == SCFGP_FF_PHASE) {
+    for (int s2 = 0; s2 < S; ++s2) {
+      double mean = 0;
+      for (int d = 0; d < D; ++d) mean += lf[(size_t)d * S + s2];
+      h->phi_h[s2] = lp[s2] - mean / D;
+    }
+    for (int m = 0; m < M; ++m) {
+      double mean = 0;
+      for (int d = 0; d < D; ++d) mean += h->F[(size_t)d * M + m];
+      h->phi_h[S + m] = pp[m] - mean / D;
+    }
+  }
+  // Wt (J x ldw): row j = column j of W = [l_F | F]
+  std::vector<double> wt((size_t)J * h->ldw, 0.0);
+  for (int d = 0; d < D; ++d) {
+    for (int s2 = 0; s2 < S; ++s2) wt[(size_t)s2 * h->ldw + d] = lf[(size_t)d * S + s2];
+    for (int m = 0; m < M; ++m) wt[(size_t)(S + m) * h->ldw + d] = h->F[(size_t)d * M + m];
+  }
+  h->sig2n = std::exp(2 * h->a);
+  h->sigf = std::exp(h->b);
+  h->tau = std::log(1 + std::exp(h->c));
+  h->s = h->sigf * std::sqrt(2.0 / M);
+  CK(cudaMemcpyAsync(h->Wt, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->phi, h->phi_h.data(), (size_t)J * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // wt is a stack-lifetime staging buffer
+  return SCFGP_OK;
+}
+
+int ensure_row_arrays(scfgp_handle* h, long long n) {
+  if (n <= h->row_cap) return SCFGP_OK;
+  if (h->gmu) cudaFree(h->gmu);
+  if (h->gv) cudaFree(h->gv);
+  h->gmu = h->gv = nullptr;
+  int rc;
+  if ((rc = dalloc(h, &h->gmu, (size_t)n))) return rc;
+  if ((rc = dalloc(h, &h->gv, (size_t)n))) return rc;
+  h->row_cap = n;
+  return SCFGP_OK;
+}
+
+// (re)allocate everything that depends on the chunk size R
+int alloc_chunk_buffers(scfgp_handle* h) {
+  for (double** p : {&h->PhiS, &h->PsiS, &h->Zbar, &h->vpart}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  const int K = h->K, R = h->R;
+  int rc;
+  if ((rc = dalloc(h, &h->PhiS, (size_t)R * h->ldk))) return rc;
+  if ((rc = dalloc(h, &h->PsiS, (size_t)R * h->ldk))) return rc;
+  if ((rc = dalloc(h, &h->Zbar, (size_t)R * h->ldj))) return rc;
+  const int nkb = cdiv(K, 128);
+  if ((rc = dalloc(h, &h->vpart, (size_t)nkb * R))) return rc;
+  // work lists that depend on R
+  const int nrb = R / 128;
+  std::vector<int4> tg, bw;
+  for (int kb = nkb - 1; kb >= 0; --kb)  // deepest reductions first
+    for (int rb = 0; rb < nrb; ++rb) tg.push_back(make_int4(rb, kb, 0, 0));
+  const int nfb = cdiv(h->J, 64);
+  for (int rb = 0; rb < nrb; ++rb)
+    for (int fb = 0; fb < nfb; ++fb) bw.push_back(make_int4(rb, fb, 0, 0));
+  if ((rc = upload_items(h, tg, &h->tgemm))) return rc;
+  if ((rc = upload_items(h, bw, &h->bwd))) return rc;
+  if (h->slots) cudaFree(h->slots);
+  h->slots = nullptr;
+  if ((rc = dalloc(h, &h->slots, (size_t)std::max(2 * kSeedBlocks, (int)bw.size()) + 1024))) return rc;
+  return SCFGP_OK;
+}
+
+int run_features(scfgp_handle* h, const double* Xc, int rows, const double* rowscale, double* Psi) {
+  const int nfb = cdiv(h->J, 64);
+  const int nrb = cdiv(rows, 128);
+  const size_t smem = SmemSize<CfgTall, true, true>::BYTES;
+  if (h->xvec == 2)
+    k_features<2><<<nrb * nfb, CfgTall::NT, smem, h->stream>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi,
+                                                               h->J, h->s, h->PhiS, h->ldk, rowscale, Psi, nfb);
+  else
+    k_features<1><<<nrb * nfb, CfgTall::NT, smem, h->stream>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi,
+                                                               h->J, h->s, h->PhiS, h->ldk, rowscale, Psi, nfb);
+  CKL();
+  return SCFGP_OK;
+}
+
+// count of T-GEMM items that touch valid rows (items are ordered kb-major, rb-minor over
+// the full chunk; for a short last chunk launch a re-filtered prefix is not possible, so
+// short chunks simply run all items -- invalid row blocks are zero-filled and skipped in
+// the epilogue).
+int run_tgemm(scfgp_handle* h, int rows) {
+  const size_t smem = SmemSize<CfgBig, true, true>::BYTES;
+  k_tgemm_rowsq<<<h->tgemm.count, CfgBig::NT, smem, h->stream>>>(h->PhiS, h->ldk, rows, h->K, h->Li, h->ldk,
+                                                                h->vpart, h->R, h->tgemm.d);
+  CKL();
+  return SCFGP_OK;
+}
+
+// lower Cholesky of h->L in place + Li = inv(L)                SCFGP/SCFGP.py:106-107
+int factor_device(scfgp_handle* h, double* L, double* Li, int K, long long ld) {
+  int rc;
+  const int nblk = cdiv(K, NB);
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int k0 = bi * NB, nb = std::min(NB, K - k0);
+    double* Dk = h->Dinv + (size_t)bi * NB * NB;
+    k_potrf_diag<<<1, 256, POTRF_SMEM, h->stream>>>(L, ld, k0, nb, Dk, h->info);
+    CKL();
+    const int m = K - k0 - nb;
+    if (m > 0) {
+      double* panel = L + (size_t)(k0 + nb) * ld + k0;
+      // L21 = A21 . inv(L11)^T
+      if ((rc = launch_gemm<CfgTall, true, true, 2, 2>(h, panel, ld, m, Dk, NB, nb, panel, ld, 1.0, 0.0,
+                                                       h->potrf_panel[bi], nb)))
+        return rc;
+      // A22 -= L21 . L21^T (lower tiles)
+      double* trail = L + (size_t)(k0 + nb) * ld + (k0 + nb);
+      if ((rc = launch_gemm<CfgBig, true, true, 2, 2>(h, panel, ld, m, panel, ld, m, trail, ld, -1.0, 1.0,
+                                                      h->potrf_trail[bi], nb)))
+        return rc;
+    }
+  }
+  // Li by block-row forward substitution:  Li[i,:i0] = -inv(L_ii) . (L[i,:i0] . Li[:i0,:i0])
+  CK(cudaMemsetAsync(Li, 0, (size_t)K * ld * sizeof(double), h->stream));
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int i0 = bi * NB, nb = std::min(NB, K - i0);
+    double* Dk = h->Dinv + (size_t)bi * NB * NB;
+    if (i0 > 0) {
+      // S (nb x i0) = L[i0:, 0:i0] . Li[0:i0, 0:i0]       (NN; column block c needs k >= c)
+      if ((rc = launch_gemm<CfgWide, true, false, 2, 2>(h, L + (size_t)i0 * ld, ld, nb, Li, ld, i0, h->tmpS,
+                                                        ld, 1.0, 0.0, h->trtri_s[bi], i0)))
+        return rc;
+      // Li[i0:, 0:i0] = -Dinv . S
+      if ((rc = launch_gemm<CfgWide, true, false, 2, 2>(h, Dk, NB, nb, h->tmpS, ld, i0, Li + (size_t)i0 * ld,
+                                                        ld, -1.0, 0.0, h->trtri_x[bi], nb)))
+        return rc;
+    }
+    k_copy_block<<<cdiv(nb * nb, 256), 256, 0, h->stream>>>(Dk, NB, Li + (size_t)i0 * ld + i0, ld, nb, nb);
+    CKL();
+  }
+  return SCFGP_OK;
+}
+
+int build_static_lists(scfgp_handle* h) {
+  const int K = h->K;
+  int rc;
+  if ((rc = upload_items(h, lower_tiles(K, 128, 0, -1), &h->lowerK))) return rc;
+  {
+    std::vector<int4> v;
+    int nb = cdiv(K, 128);
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j < nb; ++j) v.push_back(make_int4(i, j, 0, -1));
+    if ((rc = upload_items(h, v, &h->fullK))) return rc;
+  }
+  {
+    std::vector<int4> v;
+    for (int mb = 0; mb < cdiv(h->D, 64); ++mb)
+      for (int nb = 0; nb < cdiv(h->J, 128); ++nb) v.push_back(make_int4(mb, nb, 0, -1));
+    if ((rc = upload_items(h, v, &h->dw))) return rc;
+  }
+  const int nblk = cdiv(K, NB);
+  h->potrf_panel.resize(nblk);
+  h->potrf_trail.resize(nblk);
+  h->trtri_s.resize(nblk);
+  h->trtri_x.resize(nblk);
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int k0 = bi * NB, nb = std::min(NB, K - k0);
+    const int m = K - k0 - nb;
+    std::vector<int4> pv;
+    for (int i = 0; i < cdiv(m, 128); ++i) pv.push_back(make_int4(i, 0, 0, -1));
+    if ((rc = upload_items(h, pv, &h->potrf_panel[bi]))) return rc;
+    if ((rc = upload_items(h, lower_tiles(m, 128, 0, -1), &h->potrf_trail[bi]))) return rc;
+    std::vector<int4> sv, xv;
+    for (int j = 0; j < cdiv(k0, 128); ++j) {
+      sv.push_back(make_int4(0, j, j * 128, -1));  // skip the zero upper part of Li
+      xv.push_back(make_int4(0, j, 0, -1));
+    }
+    if ((rc = upload_items(h, sv, &h->trtri_s[bi]))) return rc;
+    if ((rc = upload_items(h, xv, &h->trtri_x[bi]))) return rc;
+  }
+  return SCFGP_OK;
+}
+
+void free_all(scfgp_handle* h) {
+  for (double* p : {h->Wt, h->phi, h->PhiS, h->PsiS, h->Zbar, h->vpart, h->red1, h->red2, h->red3, h->L,
+                    h->Li, h->Bm, h->BH, h->BHB, h->A2, h->B2, h->Dinv, h->tmpS, h->alpha, h->beta, h->tvec,
+                    h->pbar, h->scal, h->gmu, h->gv, h->colpart, h->slots, h->trslots, h->ownX, h->owny})
+    if (p) cudaFree(p);
+  if (h->info) cudaFree(h->info);
+  for (int4* p : h->to_free) cudaFree(p);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+}
+
+// penalty of SCFGP/SCFGP.py:94,114-117,127 and its adjoints (A.6), host
+double penalty_and_grad(const scfgp_handle* h, std::vector<double>& dlF, std::vector<double>& dF) {
+  const int D = h->D, S = h->S, M = h->M;
+  auto stats = [&](const std::vector<double>& Q, int n, std::vector<double>& mean, std::vector<double>& sd,
+                   double& mu, double& sig) {
+    mean.assign(D, 0.0); sd.assign(D, 0.0); mu = 0; sig = 0;
+    for (int d = 0; d < D; ++d) {
+      double m = 0;
+      for (int j = 0; j < n; ++j) m += Q[(size_t)d * n + j];
+      m /= n;
+      double v = 0;
+      for (int j = 0; j < n; ++j) { double t = Q[(size_t)d * n + j] - m; v += t * t; }
+      mean[d] = m; sd[d] = std::sqrt(v / n);
+      mu += m; sig += sd[d];
+    }
+  };
+  std::vector<double> ml, sl, mw, sw;
+  double mu_l, sig_l, mu_w, sig_w;
+  stats(h->lF, S, ml, sl, mu_l, sig_l);
+  stats(h->F, M, mw, sw, mu_w, sig_w);
+  auto kl = [](double mu, double sig) { return sig + mu * mu - std::log(sig); };
+  const double pen = (kl(mu_w, sig_w) * M + kl(mu_l, sig_l) * S) / (S + M);
+  auto adj = [&](const std::vector<double>& Q, int n, const std::vector<double>& mean,
+                 const std::vector<double>& sd, double mu, double sig, double weight, std::vector<double>& out) {
+    out.assign((size_t)D * n, 0.0);
+    for (int d = 0; d < D; ++d)
+      for (int j = 0; j < n; ++j)
+        out[(size_t)d * n + j] =
+            weight * (2 * mu / n + (1 - 1 / sig) * (Q[(size_t)d * n + j] - mean[d]) / (n * sd[d]));
+  };
+  adj(h->lF, S, ml, sl, mu_l, sig_l, (double)S / (S + M), dlF);
+  adj(h->F, M, mw, sw, mu_w, sig_w, (double)M / (S + M), dF);
+  return pen;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int scfgp_abi_version(void) { return 1; }
+
+int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out) {
+  if (!out) return SCFGP_ERR_ARG;
+  *out = nullptr;
+  if (D <= 0 || S <= 0 || M <= 0 || (fftype != SCFGP_FF_PHASE && fftype != SCFGP_FF_NOPHASE))
+    return SCFGP_ERR_ARG;
+  scfgp_handle* h = new scfgp_handle();
+  *out = h;
+  h->D = D; h->S = S; h->M = M; h->J = S + M; h->K = 2 * (S + M); h->fftype = fftype; h->device = device;
+  h->P = 3 + (long long)D * S + (long long)M * S + S + M;
+  h->ldk = h->K;                       // K = 2J is even: 16-byte row alignment holds
+  h->ldj = (h->J + 1) / 2 * 2;
+  h->ldw = (D + 1) / 2 * 2;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { h->err = "no such CUDA device"; return SCFGP_ERR_CUDA; }
+  CK(cudaSetDevice(device));
+  int rc;
+  if ((rc = set_kernel_attrs(h))) return rc;
+  const size_t K = h->K, KK = K * h->ldk;
+  if ((rc = dalloc(h, &h->Wt, (size_t)h->J * h->ldw))) return rc;
+  if ((rc = dalloc(h, &h->phi, h->J))) return rc;
+  if ((rc = dalloc(h, &h->red1, KK + K + 1))) return rc;
+  if ((rc = dalloc(h, &h->red2, KK + K + 2))) return rc;
+  if ((rc = dalloc(h, &h->red3, (size_t)D * h->ldj + h->ldj + 1))) return rc;
+  for (double** p : {&h->L, &h->Li, &h->Bm, &h->BH, &h->BHB, &h->A2, &h->B2})
+    if ((rc = dalloc(h, p, KK))) return rc;
+  if ((rc = dalloc(h, &h->tmpS, (size_t)NB * h->ldk))) return rc;
+  if ((rc = dalloc(h, &h->Dinv, (size_t)cdiv(K, NB) * NB * NB))) return rc;
+  for (double** p : {&h->alpha, &h->beta, &h->tvec, &h->pbar})
+    if ((rc = dalloc(h, p, K))) return rc;
+  if ((rc = dalloc(h, &h->scal, 64))) return rc;
+  if ((rc = dalloc(h, &h->colpart, (size_t)kColSplit * K))) return rc;
+  if ((rc = dalloc(h, &h->trslots, K))) return rc;
+  if ((rc = dalloc(h, &h->info, 1))) return rc;
+  if ((rc = build_static_lists(h))) return rc;
+  if ((rc = alloc_chunk_buffers(h))) return rc;
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  CK(cudaStreamSynchronize(h->stream));
+  return SCFGP_OK;
+}
+
+int scfgp_destroy(scfgp_handle* h) {
+  if (!h) return SCFGP_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_all(h);
+  delete h;
+  return SCFGP_OK;
+}
+
+const char* scfgp_last_error(const scfgp_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long scfgp_last_pivot(const scfgp_handle* h) { return h ? h->pivot : -1; }
+long long scfgp_num_params(const scfgp_handle* h) { return h ? h->P : 0; }
+long long scfgp_num_features(const scfgp_handle* h) { return h ? h->K : 0; }
+long long scfgp_launch_count(const scfgp_handle* h) { return h ? h->launches : 0; }
+
+int scfgp_set_stream(scfgp_handle* h, void* cuda_stream) {
+  if (!h) return SCFGP_ERR_ARG;
+  h->stream = (cudaStream_t)cuda_stream;
+  return SCFGP_OK;
+}
+
+int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
+  if (!h || rows < 128 || rows % 128 != 0) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->R = rows;
+  return alloc_chunk_buffers(h);
+}
+
+static int set_data_common(scfgp_handle* h, long long N, long long n_global) {
+  h->N = N;
+  h->Nglobal = n_global > 0 ? n_global : N;
+  h->have_factors = false;
+  h->xvec = (((uintptr_t)h->dX % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
+  return ensure_row_arrays(h, N);
+}
+
+int scfgp_set_data_host(scfgp_handle* h, const double* X, const double* y, long long N, long long n_global) {
+  if (!h || !X || !y || N <= 0) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  if (h->ownX) cudaFree(h->ownX);
+  if (h->owny) cudaFree(h->owny);
+  h->ownX = h->owny = nullptr;
+  CK(cudaMalloc((void**)&h->ownX, (size_t)N * h->D * sizeof(double)));
+  CK(cudaMalloc((void**)&h->owny, (size_t)N * sizeof(double)));
+  CK(cudaMemcpyAsync(h->ownX, X, (size_t)N * h->D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->owny, y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->dX = h->ownX;
+  h->dy = h->owny;
+  return set_data_common(h, N, n_global);
+}
+
+int scfgp_set_data_device(scfgp_handle* h, const double* dX, const double* dy, long long N, long long n_global) {
+  if (!h || !dX || !dy || N <= 0) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  h->dX = dX;
+  h->dy = dy;
+  return set_data_common(h, N, n_global);
+}
+
+// ---------------------------------------------------------------------------------
+int scfgp_eval_begin(scfgp_handle* h, const double* params, int want_grad) {
+  if (!h || !params) return SCFGP_ERR_ARG;
+  if (!h->dX || h->N <= 0) { h->err = "no training data set"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  h->want_grad = want_grad;
+  h->have_factors = false;
+  h->pivot = -1;
+  return unpack_and_upload(h, params);
+}
+
+int scfgp_eval_pass1(scfgp_handle* h) {
+  if (!h) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  const int K = h->K;
+  const size_t KK = (size_t)K * h->ldk;
+  int rc;
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  CK(cudaMemsetAsync(h->red1, 0, (KK + K + 1) * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->colpart, 0, (size_t)kColSplit * K * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->slots, 0, 1024 * sizeof(double), h->stream));
+  double* G = h->red1;
+  double* p = h->red1 + KK;
+  double* yy = p + K;
+  for (long long r0 = 0; r0 < h->N; r0 += h->R) {
+    const int rows = (int)std::min<long long>(h->R, h->N - r0);
+    if ((rc = run_features(h, h->dX + r0 * h->D, rows, nullptr, nullptr))) return rc;
+    if ((rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PhiS, h->ldk, K, h->PhiS, h->ldk, K, G, h->ldk,
+                                                      1.0, 1.0, h->lowerK, rows)))
+      return rc;
+    k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->dy + r0,
+                                                                    h->colpart, K);
+    CKL();
+  }
+  k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart, K, kColSplit, K, p);
+  CKL();
+  k_sumsq_part<<<256, 256, 0, h->stream>>>(h->dy, h->N, h->slots);
+  CKL();
+  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots, 256, 1, 1, yy);
+  CKL();
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  return SCFGP_OK;
+}
+
+int scfgp_eval_factor(scfgp_handle* h) {
+  if (!h) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  const int K = h->K;
+  const size_t KK = (size_t)K * h->ldk;
+  int rc;
+  CK(cudaEventRecord(h->ev[6], h->stream));
+  double* G = h->red1;
+  double* p = h->red1 + KK;
+  CK(cudaMemsetAsync(h->info, 0, sizeof(long long), h->stream));
+  CK(cudaMemcpyAsync(h->L, G, KK * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  k_add_diag<<<cdiv(K, 256), 256, 0, h->stream>>>(h->L, h->ldk, K, h->sig2n + kEps);
+  CKL();
+  if ((rc = factor_device(h, h->L, h->Li, K, h->ldk))) return rc;
+  // beta = Li p ; alpha = LiT beta                           SCFGP/SCFGP.py:108-110
+  k_gemv_n<<<cdiv(K, 8), 256, 0, h->stream>>>(h->Li, h->ldk, K, K, p, h->beta);
+  CKL();
+  CK(cudaMemsetAsync(h->colpart, 0, (size_t)kColSplit * K * sizeof(double), h->stream));
+  k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, h->stream>>>(h->Li, h->ldk, K, K, h->beta, h->colpart, K);
+  CKL();
+  k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart, K, kColSplit, K, h->alpha);
+  CKL();
+  k_factor_scalars<<<1, 256, 0, h->stream>>>(h->L, h->ldk, K, h->beta, p, h->alpha, h->scal);
+  CKL();
+  if (h->want_grad) {
+    // B = LiT Li = A^-1 (lower tiles; rows r < m0 of Li[:, m-block] are zero), then mirror
+    if ((rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->Li, h->ldk, K, h->Li, h->ldk, K, h->Bm, h->ldk,
+                                                      1.0, 0.0, h->lowerK, K)))
+      return rc;
+    k_symmetrize<<<dim3(cdiv(K, 32), cdiv(K, 32)), dim3(32, 32), 0, h->stream>>>(h->Bm, h->ldk, K);
+    CKL();
+  }
+  long long info = 0;
+  CK(cudaMemcpyAsync(&info, h->info, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->ev[7], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (info != 0) {
+    h->pivot = info - 1;
+    h->err = "matrix is not positive definite (leading minor " + std::to_string(info) + ")";
+    return SCFGP_ERR_NOT_PD;
+  }
+  h->have_factors = true;
+  return SCFGP_OK;
+}
+
+int scfgp_eval_pass2(scfgp_handle* h) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (!h->have_factors) { h->err = "pass2 before factor"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  const int K = h->K;
+  const size_t KK = (size_t)K * h->ldk;
+  int rc;
+  CK(cudaEventRecord(h->ev[2], h->stream));
+  CK(cudaMemsetAsync(h->red2, 0, (KK + K + 2) * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->colpart, 0, (size_t)kColSplit * K * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->slots, 0, 2 * kSeedBlocks * sizeof(double), h->stream));
+  double* H = h->red2;
+  double* q = h->red2 + KK;
+  double* Eg = q + K;
+  const int nkb = cdiv(K, 128);
+  for (long long r0 = 0; r0 < h->N; r0 += h->R) {
+    const int rows = (int)std::min<long long>(h->R, h->N - r0);
+    if ((rc = run_features(h, h->dX + r0 * h->D, rows, nullptr, nullptr))) return rc;
+    if ((rc = run_tgemm(h, rows))) return rc;
+    k_seeds<<<kSeedBlocks, 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->alpha, h->vpart, h->R, nkb,
+                                               h->dy + r0, h->tau, h->gmu + r0, h->gv + r0, h->PsiS, h->slots,
+                                               h->want_grad);
+    CKL();
+    if (h->want_grad) {
+      if ((rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PsiS, h->ldk, K, h->PhiS, h->ldk, K, H, h->ldk,
+                                                        1.0, 1.0, h->lowerK, rows)))
+        return rc;
+      k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->gmu + r0,
+                                                                      h->colpart, K);
+      CKL();
+    }
+  }
+  if (h->want_grad) {
+    k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart, K, kColSplit, K, q);
+    CKL();
+  }
+  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots, kSeedBlocks, 2, 2, Eg);
+  CKL();
+  CK(cudaEventRecord(h->ev[3], h->stream));
+  return SCFGP_OK;
+}
+
+int scfgp_eval_backward(scfgp_handle* h) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (!h->have_factors || !h->want_grad) { h->err = "backward without factors/grad"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  const int K = h->K;
+  const size_t KK = (size_t)K * h->ldk;
+  int rc;
+  double* H = h->red2;
+  double* q = h->red2 + KK;
+  k_symmetrize<<<dim3(cdiv(K, 32), cdiv(K, 32)), dim3(32, 32), 0, h->stream>>>(H, h->ldk, K);
+  CKL();
+  k_gemv_n<<<cdiv(K, 8), 256, 0, h->stream>>>(h->Bm, h->ldk, K, K, q, h->tvec);
+  CKL();
+  // BH = B.H ; BHB = BH.B  (H, B symmetric -> NT)
+  if ((rc = launch_gemm<CfgBig, true, true, 2, 2>(h, h->Bm, h->ldk, K, H, h->ldk, K, h->BH, h->ldk, 1.0, 0.0,
+                                                  h->fullK, K)))
+    return rc;
+  if ((rc = launch_gemm<CfgBig, true, true, 2, 2>(h, h->BH, h->ldk, K, h->Bm, h->ldk, K, h->BHB, h->ldk, 1.0,
+                                                  0.0, h->fullK, K)))
+    return rc;
+  k_abar<<<K, 256, 0, h->stream>>>(h->Bm, h->BHB, h->ldk, K, h->tvec, h->alpha, h->sig2n, h->A2, h->B2,
+                                   h->pbar, h->trslots);
+  CKL();
+  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->trslots, K, 1, 1, h->scal + 3);
+  CKL();
+  return SCFGP_OK;
+}
+
+int scfgp_eval_pass3(scfgp_handle* h) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (!h->have_factors || !h->want_grad) { h->err = "pass3 without factors/grad"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  const int K = h->K, J = h->J, D = h->D;
+  int rc;
+  CK(cudaEventRecord(h->ev[4], h->stream));
+  const size_t n3 = (size_t)D * h->ldj + h->ldj + 1;
+  CK(cudaMemsetAsync(h->red3, 0, n3 * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->colpart, 0, (size_t)kColSplit * K * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->slots, 0, (size_t)(h->bwd.count + 1) * sizeof(double), h->stream));
+  double* dW = h->red3;
+  double* dphi = dW + (size_t)D * h->ldj;
+  double* sbar = dphi + h->ldj;
+  const size_t smem = SmemSize<CfgBig, true, true>::BYTES;
+  const int nfb = cdiv(J, 64);
+  for (long long r0 = 0; r0 < h->N; r0 += h->R) {
+    const int rows = (int)std::min<long long>(h->R, h->N - r0);
+    const double* Xc = h->dX + r0 * D;
+    if ((rc = run_features(h, Xc, rows, h->gv + r0, h->PsiS))) return rc;
+    const int nitems = cdiv(rows, 128) * nfb;  // items are rb-major
+    k_backward<<<nitems, CfgBig::NT, smem, h->stream>>>(h->PhiS, h->PsiS, h->ldk, rows, K, J, h->A2, h->B2,
+                                                        h->ldk, h->dy + r0, h->gmu + r0, h->pbar, h->alpha,
+                                                        h->Zbar, h->ldj, h->slots, h->bwd.d);
+    CKL();
+    // dW += XcT . Zbar
+    if (h->xvec == 2)
+      rc = launch_gemm<CfgWide, false, false, 2, 2>(h, Xc, D, D, h->Zbar, h->ldj, J, dW, h->ldj, 1.0, 1.0,
+                                                    h->dw, rows);
+    else
+      rc = launch_gemm<CfgWide, false, false, 1, 2>(h, Xc, D, D, h->Zbar, h->ldj, J, dW, h->ldj, 1.0, 1.0,
+                                                    h->dw, rows);
+    if (rc) return rc;
+    k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, h->stream>>>(h->Zbar, h->ldj, rows, J, nullptr,
+                                                                    h->colpart, K);
+    CKL();
+  }
+  k_sum_parts<<<cdiv(J, 256), 256, 0, h->stream>>>(h->colpart, K, kColSplit, J, dphi);
+  CKL();
+  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots, h->bwd.count, 1, 1, sbar);
+  CKL();
+  CK(cudaEventRecord(h->ev[5], h->stream));
+  return SCFGP_OK;
+}
+
+int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha, double* Li) {
+  if (!h || !cost) return SCFGP_ERR_ARG;
+  if (!h->have_factors) { h->err = "finish before factor"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  const int K = h->K, J = h->J, D = h->D, S = h->S, M = h->M;
+  const size_t KK = (size_t)K * h->ldk;
+  double sc[8] = {0};       // logdetL, beta.beta, p.alpha, tr(Abar)
+  double r1[1], r2[2];
+  CK(cudaMemcpyAsync(sc, h->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(r1, h->red1 + KK + K, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(r2, h->red2 + KK + K, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> g3;
+  if (grad) {
+    if (!h->want_grad) { h->err = "gradient requested but eval_begin had want_grad=0"; return SCFGP_ERR_ARG; }
+    g3.resize((size_t)D * h->ldj + h->ldj + 1);
+    CK(cudaMemcpyAsync(g3.data(), h->red3, g3.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (alpha) CK(cudaMemcpyAsync(alpha, h->alpha, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (Li) CK(cudaMemcpy2DAsync(Li, (size_t)K * sizeof(double), h->Li, h->ldk * sizeof(double),
+                               (size_t)K * sizeof(double), K, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 3; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]) == cudaSuccess) h->ms_pass[i] = ms;
+    else { h->ms_pass[i] = 0; (void)cudaGetLastError(); }
+  }
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->ms_pass[3] = ms;
+    else { h->ms_pass[3] = 0; (void)cudaGetLastError(); }
+  }
+  const double Ng = (double)h->Nglobal;
+  const double logdetL = sc[0], bb = sc[1], pa = sc[2], trA = sc[3];
+  const double yy = r1[0], E = r2[0], gtau = r2[1];
+  std::vector<double> pen_dlF, pen_dF;
+  const double pen = penalty_and_grad(h, pen_dlF, pen_dF);
+  // nlml: SCFGP/SCFGP.py:125-126 ; cost: :128
+  const double nlml = 2 * logdetL + E + (yy - bb) / h->sig2n + 2 * (Ng - M) * h->a;
+  *cost = (nlml + pen) / Ng;
+  if (!std::isfinite(*cost)) { h->err = "cost is not finite"; return SCFGP_ERR_NONFINITE; }
+  if (grad) {
+    const double* dW = g3.data();
+    const double* dphi = dW + (size_t)D * h->ldj;
+    const double sbar_s = dphi[h->ldj];  // = sum(Phibar * Phi) = d nlml / d b
+    const double d_a = 2 * h->sig2n * (trA - (yy - pa) / (h->sig2n * h->sig2n)) + 2 * (Ng - M);
+    const double d_b = sbar_s;
+    const double d_c = gtau / (1 + std::exp(-h->c));
+    // A.6: centering + penalty + chain through F = l_F r_F^T
+    std::vector<double> Wl((size_t)D * S), WF((size_t)D * M);
+    const bool phase = h->fftype == SCFGP_FF_PHASE;
+    for (int d = 0; d < D; ++d) {
+      for (int s2 = 0; s2 < S; ++s2)
+        Wl[(size_t)d * S + s2] = dW[(size_t)d * h->ldj + s2] - (phase ? dphi[s2] / D : 0.0) + pen_dlF[(size_t)d * S + s2];
+      for (int m = 0; m < M; ++m)
+        WF[(size_t)d * M + m] = dW[(size_t)d * h->ldj + S + m] - (phase ? dphi[S + m] / D : 0.0) + pen_dF[(size_t)d * M + m];
+    }
+    double* g = grad;
+    g[0] = d_a / Ng; g[1] = d_b / Ng; g[2] = d_c / Ng;
+    double* g_lf = g + 3;
+    double* g_rf = g_lf + (size_t)D * S;
+    double* g_lp = g_rf + (size_t)M * S;
+    double* g_p = g_lp + S;
+    for (int d = 0; d < D; ++d)
+      for (int s2 = 0; s2 < S; ++s2) {
+        double acc = Wl[(size_t)d * S + s2];
+        for (int m = 0; m < M; ++m) acc += WF[(size_t)d * M + m] * h->rF[(size_t)m * S + s2];
+        g_lf[(size_t)d * S + s2] = acc / Ng;
+      }
+    for (int m = 0; m < M; ++m)
+      for (int s2 = 0; s2 < S; ++s2) {
+        double acc = 0;
+        for (int d = 0; d < D; ++d) acc += WF[(size_t)d * M + m] * h->lF[(size_t)d * S + s2];
+        g_rf[(size_t)m * S + s2] = acc / Ng;
+      }
+    for (int s2 = 0; s2 < S; ++s2) g_lp[s2] = phase ? dphi[s2] / Ng : 0.0;
+    for (int m = 0; m < M; ++m) g_p[m] = phase ? dphi[S + m] / Ng : 0.0;
+  }
+  return SCFGP_OK;
+}
+
+int scfgp_eval(scfgp_handle* h, const double* params, double* cost, double* grad, double* alpha, double* Li) {
+  int rc;
+  if ((rc = scfgp_eval_begin(h, params, grad != nullptr))) return rc;
+  if ((rc = scfgp_eval_pass1(h))) return rc;
+  if ((rc = scfgp_eval_factor(h))) return rc;
+  if ((rc = scfgp_eval_pass2(h))) return rc;
+  if (grad) {
+    if ((rc = scfgp_eval_backward(h))) return rc;
+    if ((rc = scfgp_eval_pass3(h))) return rc;
+  }
+  return scfgp_eval_finish(h, cost, grad, alpha, Li);
+}
+
+int scfgp_reduce_buffer(scfgp_handle* h, int which, void** dptr, long long* count) {
+  if (!h || !dptr || !count) return SCFGP_ERR_ARG;
+  const long long K = h->K, KK = K * h->ldk;
+  switch (which) {
+    case SCFGP_RED1: *dptr = h->red1; *count = KK + K + 1; break;
+    case SCFGP_RED2: *dptr = h->red2; *count = KK + K + 2; break;
+    case SCFGP_RED3: *dptr = h->red3; *count = (long long)h->D * h->ldj + h->ldj + 1; break;
+    default: return SCFGP_ERR_ARG;
+  }
+  return SCFGP_OK;
+}
+
+int scfgp_device_factors(scfgp_handle* h, void** d_alpha, void** d_Li, long long* ld_Li) {
+  if (!h || !h->have_factors) return SCFGP_ERR_ARG;
+  if (d_alpha) *d_alpha = h->alpha;
+  if (d_Li) *d_Li = h->Li;
+  if (ld_Li) *ld_Li = h->ldk;
+  return SCFGP_OK;
+}
+
+int scfgp_last_pass_ms(const scfgp_handle* h, float* p1, float* p2, float* p3, float* dense) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (p1) *p1 = h->ms_pass[0];
+  if (p2) *p2 = h->ms_pass[1];
+  if (p3) *p3 = h->ms_pass[2];
+  if (dense) *dense = h->ms_pass[3];
+  return SCFGP_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// prediction                                                 SCFGP/SCFGP.py:138-148
+// ---------------------------------------------------------------------------------
+int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dXs, long long T, double* dmu,
+                         double* dstd) {
+  if (!h || !params || !dXs || !dmu || !dstd || T <= 0) return SCFGP_ERR_ARG;
+  if (!h->have_factors) { h->err = "predict needs alpha/Li (evaluate first or pass them)"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = unpack_and_upload(h, params))) return rc;
+  const int K = h->K;
+  const int nkb = cdiv(K, 128);
+  const int save_xvec = h->xvec;
+  h->xvec = (((uintptr_t)dXs % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
+  for (long long r0 = 0; r0 < T; r0 += h->R) {
+    const int rows = (int)std::min<long long>(h->R, T - r0);
+    if ((rc = run_features(h, dXs + r0 * h->D, rows, nullptr, nullptr))) { h->xvec = save_xvec; return rc; }
+    if ((rc = run_tgemm(h, rows))) { h->xvec = save_xvec; return rc; }
+    k_pred_finish<<<kSeedBlocks, 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->alpha, h->vpart, h->R, nkb,
+                                                     h->tau, dmu + r0, dstd + r0);
+    h->launches++;
+  }
+  h->xvec = save_xvec;
+  CK(cudaGetLastError());
+  return SCFGP_OK;
+}
+
+int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long long T, const double* alpha,
+                  const double* Li, double* mu, double* sd) {
+  if (!h || !params || !Xs || !mu || !sd || T <= 0) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  const int K = h->K;
+  if ((alpha == nullptr) != (Li == nullptr)) { h->err = "pass both alpha and Li or neither"; return SCFGP_ERR_ARG; }
+  if (alpha) {
+    CK(cudaMemcpyAsync(h->alpha, alpha, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(h->Li, h->ldk * sizeof(double), Li, (size_t)K * sizeof(double),
+                         (size_t)K * sizeof(double), K, cudaMemcpyHostToDevice, h->stream));
+    h->have_factors = true;
+  }
+  double *dXs = nullptr, *dout = nullptr;
+  CK(cudaMalloc((void**)&dXs, (size_t)T * h->D * sizeof(double)));
+  if (cudaMalloc((void**)&dout, (size_t)2 * T * sizeof(double)) != cudaSuccess) {
+    cudaFree(dXs); h->err = "cudaMalloc(pred out)"; return SCFGP_ERR_CUDA;
+  }
+  int rc = SCFGP_OK;
+  cudaError_t e = cudaMemcpyAsync(dXs, Xs, (size_t)T * h->D * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) rc = scfgp_predict_device(h, params, dXs, T, dout, dout + T);
+  if (e == cudaSuccess && rc == SCFGP_OK) e = cudaMemcpyAsync(mu, dout, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && rc == SCFGP_OK) e = cudaMemcpyAsync(sd, dout + T, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(dXs);
+  cudaFree(dout);
+  if (e != cudaSuccess) { h->err = std::string("predict: ") + cudaGetErrorString(e); return SCFGP_ERR_CUDA; }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// self-test hooks
+// ---------------------------------------------------------------------------------
+int scfgp_dbg_gemm(int device, int layout, int m, int n, int k, const double* A, const double* B, double* C) {
+  if (m <= 0 || n <= 0 || k <= 0 || !A || !B || !C || layout < 0 || layout > 2) return SCFGP_ERR_ARG;
+  scfgp_handle tmp;
+  scfgp_handle* h = &tmp;
+  h->device = device;
+  CK(cudaSetDevice(device));
+  // pad leading dimensions to even so the 16-byte path applies
+  const long long lda = layout == 1 ? (m + 1) / 2 * 2 : (k + 1) / 2 * 2;
+  const long long ldb = layout == 0 ? (k + 1) / 2 * 2 : (n + 1) / 2 * 2;
+  const long long ldc = n;
+  const int arows_store = layout == 1 ? k : m, acols = layout == 1 ? m : k;
+  const int brows_store = layout == 0 ? n : k, bcols = layout == 0 ? k : n;
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  CK(cudaMalloc((void**)&dA, (size_t)arows_store * lda * sizeof(double)));
+  CK(cudaMalloc((void**)&dB, (size_t)brows_store * ldb * sizeof(double)));
+  CK(cudaMalloc((void**)&dC, (size_t)m * ldc * sizeof(double)));
+  CK(cudaMemset(dA, 0, (size_t)arows_store * lda * sizeof(double)));
+  CK(cudaMemset(dB, 0, (size_t)brows_store * ldb * sizeof(double)));
+  CK(cudaMemcpy2D(dA, lda * sizeof(double), A, (size_t)acols * sizeof(double), (size_t)acols * sizeof(double),
+                  arows_store, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy2D(dB, ldb * sizeof(double), B, (size_t)bcols * sizeof(double), (size_t)bcols * sizeof(double),
+                  brows_store, cudaMemcpyHostToDevice));
+  std::vector<int4> v;
+  for (int i = 0; i < cdiv(m, 128); ++i)
+    for (int j = 0; j < cdiv(n, 128); ++j) v.push_back(make_int4(i, j, 0, -1));
+  ItemList il;
+  int rc = upload_items(h, v, &il);
+  if (!rc) {
+    if (layout == 0) rc = launch_gemm<CfgBig, true, true, 2, 2>(h, dA, lda, m, dB, ldb, n, dC, ldc, 1.0, 0.0, il, k);
+    else if (layout == 1) rc = launch_gemm<CfgBig, false, false, 2, 2>(h, dA, lda, m, dB, ldb, n, dC, ldc, 1.0, 0.0, il, k);
+    else rc = launch_gemm<CfgBig, true, false, 2, 2>(h, dA, lda, m, dB, ldb, n, dC, ldc, 1.0, 0.0, il, k);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(C, dC, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  for (int4* p : h->to_free) cudaFree(p);
+  h->to_free.clear();
+  if (rc) return rc;
+  return e == cudaSuccess ? SCFGP_OK : SCFGP_ERR_CUDA;
+}
+
+int scfgp_dbg_factor(int device, int K, const double* A, double* L, double* Li, long long* info) {
+  if (K <= 0 || K % 2 != 0 || !A || !L || !Li || !info) return SCFGP_ERR_ARG;
+  // borrow a handle of matching K (D=1, S=1, M=K/2-1) for its work lists and buffers
+  if (K < 4) return SCFGP_ERR_ARG;
+  scfgp_handle* h = nullptr;
+  int rc = scfgp_create(1, 1, K / 2 - 1, SCFGP_FF_PHASE, device, &h);
+  if (rc) { if (h) scfgp_destroy(h); return rc; }
+  const size_t KK = (size_t)K * h->ldk;
+  cudaError_t e = cudaMemcpy(h->L, A, KK * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->info, 0, sizeof(long long));
+  if (e == cudaSuccess) rc = factor_device(h, h->L, h->Li, K, h->ldk);
+  if (e == cudaSuccess && !rc) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && !rc) e = cudaMemcpy(L, h->L, KK * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && !rc) e = cudaMemcpy(Li, h->Li, KK * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && !rc) e = cudaMemcpy(info, h->info, sizeof(long long), cudaMemcpyDeviceToHost);
+  scfgp_destroy(h);
+  if (rc) return rc;
+  return e == cudaSuccess ? SCFGP_OK : SCFGP_ERR_CUDA;
+}
+
+int scfgp_dbg_features(scfgp_handle* h, const double* params, const double* X, long long N, double* Phi) {
+  if (!h || !params || !X || !Phi || N <= 0) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = unpack_and_upload(h, params))) return rc;
+  double* dXs = nullptr;
+  CK(cudaMalloc((void**)&dXs, (size_t)N * h->D * sizeof(double)));
+  CK(cudaMemcpy(dXs, X, (size_t)N * h->D * sizeof(double), cudaMemcpyHostToDevice));
+  const int save_xvec = h->xvec;
+  h->xvec = (h->D % 2 == 0) ? 2 : 1;
+  for (long long r0 = 0; r0 < N && !rc; r0 += h->R) {
+    const int rows = (int)std::min<long long>(h->R, N - r0);
+    rc = run_features(h, dXs + r0 * h->D, rows, nullptr, nullptr);
+    if (!rc) {
+      cudaError_t e = cudaMemcpy2DAsync(Phi + r0 * h->K, (size_t)h->K * sizeof(double), h->PhiS,
+                                        h->ldk * sizeof(double), (size_t)h->K * sizeof(double), rows,
+                                        cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = SCFGP_ERR_CUDA; }
+    }
+  }
+  h->xvec = save_xvec;
+  cudaFree(dXs);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+"""Host wrapper around the C ABI: one ``Engine`` = one ``scfgp_handle`` on one GPU.
+
+Multi-GPU: one process per GPU (torchrun); training rows are sharded over ranks, each
+pass's partial sums are combined with ``torch.distributed.all_reduce`` (NCCL over
+NVLink) on the device buffer the phase API exposes, and the small dense phases are
+replicated on every rank (identical inputs -> identical factors, no broadcast).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class ScfgpError(RuntimeError):
+    pass
+
+
+class _DevBuf:
+    """Expose a raw device pointer to torch via __cuda_array_interface__ (tensor hand-off)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {
+            "shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+            "strides": None,
+        }
+
+
+class Engine:
+    def __init__(self, D: int, S: int, M: int, fftype: int = _lib.FF_PHASE, device: int = 0,
+                 chunk_rows: int | None = None):
+        self.lib = _lib.load()
+        self.D, self.S, self.M = int(D), int(S), int(M)
+        self.J = self.S + self.M
+        self.K = 2 * self.J
+        self.P = 3 + self.D * self.S + self.M * self.S + self.S + self.M
+        self.device = int(device)
+        self._h = C.c_void_p()
+        rc = self.lib.scfgp_create(self.D, self.S, self.M, int(fftype), self.device, C.byref(self._h))
+        if rc != _lib.OK:
+            msg = self._err()
+            if self._h:
+                self.lib.scfgp_destroy(self._h)
+                self._h = C.c_void_p()
+            raise ScfgpError(f"scfgp_create failed ({rc}): {msg}")
+        if chunk_rows:
+            self._check(self.lib.scfgp_set_chunk_rows(self._h, int(chunk_rows)))
+        self.N = 0
+        self._keep = None   # keeps borrowed torch tensors alive
+        self._red = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _err(self) -> str:
+        if not self._h:
+            return "no handle"
+        return (self.lib.scfgp_last_error(self._h) or b"").decode()
+
+    def _check(self, rc: int):
+        if rc == _lib.OK:
+            return
+        msg = self._err()
+        if rc == _lib.ERR_NOT_PD:
+            # what Theano's Cholesky thunk raises at SCFGP/SCFGP.py:106
+            raise np.linalg.LinAlgError(msg)
+        if rc == _lib.ERR_ARG:
+            raise ValueError(msg or "bad argument")
+        if rc == _lib.ERR_NONFINITE:
+            raise FloatingPointError(msg)
+        raise ScfgpError(f"CUDA error: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.scfgp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.scfgp_launch_count(self._h))
+
+    def pass_ms(self):
+        f = [C.c_float() for _ in range(4)]
+        self.lib.scfgp_last_pass_ms(self._h, *[C.byref(x) for x in f])
+        return tuple(float(x.value) for x in f)
+
+    def set_stream(self, stream_ptr: int):
+        self._check(self.lib.scfgp_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    # ------------------------------------------------------------------ data
+    def set_data(self, X, y, n_global: int | None = None):
+        """X (N,D), y (N,) or (N,1) host arrays -> device copies owned by the handle."""
+        X = _lib.as_f64(X)
+        y = _lib.as_f64(np.asarray(y).reshape(-1))
+        if X.ndim != 2 or X.shape[1] != self.D or y.shape[0] != X.shape[0]:
+            raise ValueError(f"shape mismatch: X {X.shape}, y {y.shape}, D={self.D}")
+        self.N = X.shape[0]
+        self._keep = None
+        self._check(self.lib.scfgp_set_data_host(self._h, _lib.dptr(X), _lib.dptr(y), self.N,
+                                                 int(n_global or self.N)))
+
+    def set_data_device(self, X_t, y_t, n_global: int | None = None):
+        """Borrow float64 CUDA torch tensors (zero-copy)."""
+        import torch
+        assert X_t.is_cuda and y_t.is_cuda and X_t.dtype == torch.float64 and y_t.dtype == torch.float64
+        X_t = X_t.contiguous()
+        y_t = y_t.contiguous().reshape(-1)
+        if X_t.ndim != 2 or X_t.shape[1] != self.D or y_t.shape[0] != X_t.shape[0]:
+            raise ValueError("shape mismatch")
+        self.N = int(X_t.shape[0])
+        self._keep = (X_t, y_t)
+        self._check(self.lib.scfgp_set_data_device(self._h, C.c_void_p(X_t.data_ptr()),
+                                                   C.c_void_p(y_t.data_ptr()), self.N, int(n_global or self.N)))
+
+    # ------------------------------------------------------------------ evaluation
+    def _reduce_tensor(self, which: int):
+        import torch
+        if which not in self._red:
+            p, n = C.c_void_p(), C.c_longlong()
+            self._check(self.lib.scfgp_reduce_buffer(self._h, which, C.byref(p), C.byref(n)))
+            self._red[which] = torch.as_tensor(_DevBuf(p.value, n.value), device=f"cuda:{self.device}")
+        return self._red[which]
+
+    def eval(self, params, want_grad: bool = True, want_factors: bool = True, group=None):
+        """cost, grad (P,) or None, alpha (K,1) or None, Li (K,K) or None.
+
+        If ``torch.distributed`` is initialised with world_size > 1 the three partial
+        reductions are all-reduced between phases."""
+        params = _lib.as_f64(params).reshape(-1)
+        if params.shape[0] != self.P:
+            raise ValueError(f"params has {params.shape[0]} entries, expected {self.P}")
+        dist = None
+        try:
+            import torch.distributed as td
+            if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
+                dist = td
+        except ImportError:
+            pass
+        cost = np.zeros(1)
+        grad = np.zeros(self.P) if want_grad else None
+        alpha = np.zeros(self.K) if want_factors else None
+        Li = np.zeros((self.K, self.K)) if want_factors else None
+        nul = C.POINTER(C.c_double)()
+        gp = _lib.dptr(grad) if want_grad else nul
+        ap = _lib.dptr(alpha) if want_factors else nul
+        lp = _lib.dptr(Li) if want_factors else nul
+        if dist is None:
+            self._check(self.lib.scfgp_eval(self._h, _lib.dptr(params), _lib.dptr(cost), gp, ap, lp))
+        else:
+            import torch
+            lib, h = self.lib, self._h
+            self._check(lib.scfgp_eval_begin(h, _lib.dptr(params), int(want_grad)))
+            self._check(lib.scfgp_eval_pass1(h))
+            dist.all_reduce(self._reduce_tensor(_lib.RED1), group=group)
+            torch.cuda.current_stream().synchronize()
+            self._check(lib.scfgp_eval_factor(h))
+            self._check(lib.scfgp_eval_pass2(h))
+            dist.all_reduce(self._reduce_tensor(_lib.RED2), group=group)
+            torch.cuda.current_stream().synchronize()
+            if want_grad:
+                self._check(lib.scfgp_eval_backward(h))
+                self._check(lib.scfgp_eval_pass3(h))
+                dist.all_reduce(self._reduce_tensor(_lib.RED3), group=group)
+                torch.cuda.current_stream().synchronize()
+            self._check(lib.scfgp_eval_finish(h, _lib.dptr(cost), gp, ap, lp))
+        return (float(cost[0]), grad, alpha.reshape(-1, 1) if want_factors else None, Li)
+
+    def predict(self, params, Xs, alpha=None, Li=None):
+        """mu_pred (T,1), std_pred (T,)  -- the shapes pred_func returns (SCFGP.py:145-148)."""
+        params = _lib.as_f64(params).reshape(-1)
+        Xs = _lib.as_f64(Xs)
+        if Xs.ndim != 2 or Xs.shape[1] != self.D:
+            raise ValueError(f"Xs has shape {Xs.shape}, expected (T,{self.D})")
+        T = Xs.shape[0]
+        mu, sd = np.zeros(T), np.zeros(T)
+        nul = C.POINTER(C.c_double)()
+        if alpha is not None:
+            a = _lib.as_f64(alpha).reshape(-1)
+            L = _lib.as_f64(Li)
+            if a.shape[0] != self.K or L.shape != (self.K, self.K):
+                raise ValueError("alpha/Li shape mismatch")
+            ap, lp = _lib.dptr(a), _lib.dptr(L)
+        else:
+            ap, lp = nul, nul
+        self._check(self.lib.scfgp_predict(self._h, _lib.dptr(params), _lib.dptr(Xs), T, ap, lp,
+                                           _lib.dptr(mu), _lib.dptr(sd)))
+        return mu.reshape(-1, 1), sd
+
+    def predict_device(self, params, Xs_t):
+        """Device-resident batched predict: returns (mu, std) CUDA tensors of length T."""
+        import torch
+        params = _lib.as_f64(params).reshape(-1)
+        Xs_t = Xs_t.contiguous()
+        T = int(Xs_t.shape[0])
+        mu = torch.empty(T, dtype=torch.float64, device=Xs_t.device)
+        sd = torch.empty(T, dtype=torch.float64, device=Xs_t.device)
+        self._check(self.lib.scfgp_predict_device(self._h, _lib.dptr(params), C.c_void_p(Xs_t.data_ptr()), T,
+                                                  C.c_void_p(mu.data_ptr()), C.c_void_p(sd.data_ptr())))
+        return mu, sd
+
+    def features(self, params, X):
+        """Debug hook: materialise Phi (N,K) through the feature kernel."""
+        params = _lib.as_f64(params).reshape(-1)
+        X = _lib.as_f64(X)
+        Phi = np.zeros((X.shape[0], self.K))
+        self._check(self.lib.scfgp_dbg_features(self._h, _lib.dptr(params), _lib.dptr(X), X.shape[0],
+                                                _lib.dptr(Phi)))
+        return Phi
+
+
+def dbg_gemm(layout: int, A, B, device: int = 0):
+    lib = _lib.load()
+    A, B = _lib.as_f64(A), _lib.as_f64(B)
+    if layout == 0:
+        m, k = A.shape; n = B.shape[0]
+    elif layout == 1:
+        k, m = A.shape; n = B.shape[1]
+    else:
+        m, k = A.shape; n = B.shape[1]
+    Cm = np.zeros((m, n))
+    rc = lib.scfgp_dbg_gemm(device, layout, m, n, k, _lib.dptr(A), _lib.dptr(B), _lib.dptr(Cm))
+    if rc:
+        raise ScfgpError(f"scfgp_dbg_gemm rc={rc}")
+    return Cm
+
+
+def dbg_factor(A, device: int = 0):
+    lib = _lib.load()
+    A = _lib.as_f64(A)
+    K = A.shape[0]
+    L, Li = np.zeros((K, K)), np.zeros((K, K))
+    info = C.c_longlong(0)
+    rc = lib.scfgp_dbg_factor(device, K, _lib.dptr(A), _lib.dptr(L), _lib.dptr(Li), C.byref(info))
+    if rc:
+        raise ScfgpError(f"scfgp_dbg_factor rc={rc}")
+    return L, Li, int(info.value)
