@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the SCFGP hot path: one "step" = one NLML + gradient evaluation
+(cost, full gradient, alpha, Li) over the whole synthetic training set.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
+N = 10M rows total, D = 64, rank S = 16, feature_size M = 1024 (K = 2080), float64.
+Rows are sharded over the N GPUs (strong scaling: the total is fixed), each pass's
+partial sums are all-reduced over NCCL.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 3 --warmup 3
+    python bench.py --impl reference --steps 2 --warmup 1     # CPU restatement of the reference
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="cfg4: synthetic N=10M, D=64, rank=16, feature_size=1024", N=10_000_000, D=64, S=16, M=1024)
+
+
+def flops_per_row(D, S, M):
+    """Algorithmic flops of one evaluation per training row:
+    F_eval = 7 N K^2 + 8 N D J."""
+    J = S + M
+    K = 2 * J
+    return 7.0 * K * K + 8.0 * D * J
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic data on the device (torch used for data generation only)
+# ---------------------------------------------------------------------------------------
+def make_device_problem(n_local, D, S, M, seed, device, dist=None):
+    import torch
+    from scfgp_b200 import synth
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    X = torch.rand((n_local, D), dtype=torch.float64, device=device, generator=g)
+    rng = np.random.default_rng(0)          # teacher and evaluation point are shared by all ranks
+    teacher = synth.draw_params(D, S, M, rng, lf_scale=0.3)
+    w = torch.as_tensor(rng.standard_normal(2 * (S + M)), device=device)
+    params0 = synth.draw_params(D, S, M, rng, lf_scale=0.3)
+    t = 3
+    l_F = teacher[t:t + D * S].reshape(D, S); t += D * S
+    r_F = teacher[t:t + M * S].reshape(M, S); t += M * S
+    F = l_F @ r_F.T
+    l_p = teacher[t:t + S]; t += S
+    p = teacher[t:t + M]
+    W = torch.as_tensor(np.concatenate([l_F, F], 1), device=device)
+    phi = torch.as_tensor(np.concatenate([l_p - l_F.mean(0), p - F.mean(0)]), device=device)
+    sc = float(np.exp(teacher[1]) * np.sqrt(2.0 / M))
+    y = torch.empty(n_local, dtype=torch.float64, device=device)
+    step = 262144
+    for i in range(0, n_local, step):
+        Z = X[i:i + step] @ W + phi
+        y[i:i + step] = sc * (torch.cos(Z) @ w[:S + M] + torch.sin(Z) @ w[S + M:])
+        del Z
+    y += 0.05 * y.std() * torch.randn(n_local, dtype=torch.float64, device=device, generator=g)
+    # standardise globally so that sum(y^2) = N like the auto-normal scaler (Scaler.py:73-79)
+    stats = torch.stack([y.sum(), (y * y).sum(), torch.tensor(float(n_local), dtype=torch.float64, device=device)])
+    if dist is not None:
+        dist.all_reduce(stats)
+    mean = stats[0] / stats[2]
+    std = torch.sqrt(stats[1] / stats[2] - mean * mean)
+    y = (y - mean) / std
+    return X, y, params0
+
+
+# ---------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle's reference-shaped evaluation on host cores
+# ---------------------------------------------------------------------------------------
+def cpu_reference_run(D, S, M, steps, warmup, target_seconds=12.0):
+    """Times the literal float64 restatement of the reference's Theano graph (materialised
+    Phi, Gauss-Hermite term, LAPACK Cholesky + inverse, reverse-mode gradient) with all host
+    threads on a bounded row sample of the workload.  Returns (rows/s, info dict)."""
+    import torch
+    from oracle import scfgp_oracle as O
+    from scfgp_b200 import synth
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    # size the sample: probe at 2000 rows, then scale to ~target_seconds per step (cap by memory)
+    n_probe = 2000
+    X, y, h = synth.make_problem(n_probe, D, S, M, seed=1)
+    t0 = time.perf_counter(); O.cpu_eval_reference_shaped(h, X, y, S, M, threads=cores); t_probe = time.perf_counter() - t0
+    n = int(min(60000, max(n_probe, n_probe * target_seconds / max(t_probe, 1e-3))))
+    n = max(2000, (n // 1000) * 1000)
+    X, y, h = synth.make_problem(n, D, S, M, seed=1)
+    for _ in range(warmup):
+        O.cpu_eval_reference_shaped(h, X, y, S, M, threads=cores)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.cpu_eval_reference_shaped(h, X, y, S, M, threads=cores)
+        ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    info = {"cores": cores, "kind": "port",
+            "sample": f"{n} rows of the cfg4 geometry (D={D}, S={S}, M={M}; K={2 * (S + M)}); literal float64 "
+                      f"restatement of SCFGP.py:92-129 (materialised Phi + autograd), torch-CPU {cores} threads; "
+                      f"{sec:.2f} s/eval; dense K^3 work is not amortised at this N, so rows/s at N=1e7 would be higher "
+                      f"by at most the K^3 share"}
+    return n / sec, sec, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=WORKLOAD["N"], help="total training rows (default: the cfg4 workload)")
+    ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    D, S, M = WORKLOAD["D"], WORKLOAD["S"], WORKLOAD["M"]
+    N = args.rows
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    fpr = flops_per_row(D, S, M)
+    config = {"workload": WORKLOAD["name"] if N == WORKLOAD["N"] else f"cfg4 geometry at N={N}",
+              "N": N, "D": D, "rank": S, "feature_size": M, "K": 2 * (S + M),
+              "parallelism": f"rows sharded over {args.gpus} GPU(s), 3 all-reduces/eval",
+              "l2": "inputs (X = N*D*8 bytes per pass) far exceed the 126 MB L2; no explicit flush"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rows_s, sec, info = cpu_reference_run(D, S, M, max(1, args.steps), args.warmup)
+        line = {"impl": "reference", "metric": "nlml_grad_rows_per_sec", "value": rows_s, "unit": "rows/s",
+                "evals_per_sec_at_N": rows_s / N, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": dict(info, value=rows_s, unit="rows/s"),
+                "e2e": {"value": rows_s, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    from scfgp_b200 import Engine, shard_bounds, _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+    lo, hi = shard_bounds(N, rank, world)
+    n_local = hi - lo
+
+    Xd, yd, params0 = make_device_problem(n_local, D, S, M, seed=1000 + rank, device=device, dist=dist)
+    eng = Engine(D, S, M, device=local_rank, chunk_rows=args.chunk_rows or None)
+    eng.set_data_device(Xd, yd, n_global=N)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.eval(params0)
+    # ---- timed region: K evaluations, inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.set_profiling(_lib.FAM_BACKWARD)
+    launches0 = eng.launches
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pass_ms = []
+    for _ in range(args.steps):
+        cost, grad, alpha, Li = eng.eval(params0)
+        pass_ms.append(eng.pass_ms())
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launches - launches0
+    bw_ms, bw_launches = eng.get_profile()
+    eng.set_profiling(_lib.FAM_NONE)
+    t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=device)
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total = float(tmax[0]); launches = int(tsum[1])
+    ms_step = ms_total / args.steps
+    rows_per_s = N / (ms_step * 1e-3)
+
+    # ---- end to end through the public call with HOST buffers (train_func(X, y) semantics):
+    #      pinned host X/y -> device inside the timed region, results read back to host
+    e2e = None
+    if not args.no_e2e:
+        Xh = torch.empty((n_local, D), dtype=torch.float64, pin_memory=True); Xh.copy_(Xd)
+        yh = torch.empty((n_local,), dtype=torch.float64, pin_memory=True); yh.copy_(yd)
+        Xn, yn = Xh.numpy(), yh.numpy()
+        eng.set_data(Xn, yn, n_global=N)
+        nrep = max(1, min(2, args.steps))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            eng.set_data(Xn, yn, n_global=N)          # H2D of this step's inputs
+            c2, g2, a2, L2 = eng.eval(params0)        # D2H of cost, grad, alpha, Li
+        barrier()
+        sec = (time.perf_counter() - t0) / nrep
+        tt = torch.tensor([sec], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt[0])
+        K = eng.K
+        e2e = {"value": N / sec, "unit": "rows/s", "ms_per_step": sec * 1e3,
+               "h2d_bytes_per_step": int(n_local * D * 8 + n_local * 8 + eng.P * 8) * world,
+               "d2h_bytes_per_step": int(8 * (1 + eng.P + K + K * K)) * world,
+               "api": "Engine.set_data(X_host, y_host) + Engine.eval(params) == scfgp_set_data_host + scfgp_eval"}
+        assert abs(c2 - cost) <= 1e-9 * abs(cost)
+        eng.set_data_device(Xd, yd, n_global=N)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_backward: 4 N K^2 of the 7 N K^2 flops)
+    K = eng.K
+    peak_burst = peak_sus = None
+    try:
+        n = 8192
+        a = torch.randn(n, n, dtype=torch.float64, device=device); b = torch.randn(n, n, dtype=torch.float64, device=device)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(4):
+            s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+            s0.record(); a @ b; s1.record(); torch.cuda.synchronize()
+            best = min(best, s0.elapsed_time(s1))
+        peak_burst = 2.0 * n ** 3 / best * 1e-9
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(60):
+            a @ b
+        s1.record(); torch.cuda.synchronize()
+        peak_sus = 2.0 * n ** 3 * 60 / s0.elapsed_time(s1) * 1e-9
+        del a, b
+    except Exception as ex:  # pragma: no cover
+        peak_burst = None
+    rows_per_launch = n_local * args.steps / max(bw_launches, 1)
+    flops_per_launch = 4.0 * K * K * rows_per_launch            # Phi.(2Abar) + Psi.(2B): 2 GEMMs x 2 N K^2
+    avg_ms = bw_ms / max(bw_launches, 1)
+    achieved = flops_per_launch / (avg_ms * 1e-3) * 1e-12 if avg_ms > 0 else None
+    peak = peak_sus or 35.4
+    roofline = {"bound": "tensor", "kernel": "k_backward (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "avg_launch_ms": avg_ms, "launches": bw_launches, "algorithmic_flops_per_launch": flops_per_launch,
+                "peak_source": "cublasDgemm 8192^3 sustained, measured in this run (MEASURED_PEAKS.json holds no "
+                               "fp64 entry; register-resident DMMA.8x8x4 issue peak measured 37.0 TFLOP/s)",
+                "peak_dgemm_burst": peak_burst, "peak_dgemm_sustained": peak_sus,
+                "whole_eval_tflops": fpr * N / (ms_step * 1e-3) * 1e-12 / max(world, 1),
+                "whole_eval_frac_of_peak": fpr * N / (ms_step * 1e-3) * 1e-12 / max(world, 1) / peak,
+                "pass_ms_last": dict(zip(["pass1", "pass2", "pass3", "dense"], pass_ms[-1]))}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        rs, sec, info = cpu_reference_run(D, S, M, steps=1, warmup=0)
+        cpu_baseline = dict(info, value=rs, unit="rows/s")
+
+    line = {"metric": "nlml_grad_rows_per_sec", "value": rows_per_s, "unit": "rows/s",
+            "evals_per_sec": 1e3 / ms_step, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "cost": cost, "grad_norm": float(np.linalg.norm(grad))}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -132,6 +132,19 @@ long long scfgp_launch_count(const scfgp_handle* h);
 int scfgp_last_pass_ms(const scfgp_handle* h, float* pass1, float* pass2, float* pass3,
                        float* dense);
 
+/* Optional kernel-family timing for the roofline report: CUDA events (on the handle's
+ * stream) around every launch of ONE family; totals accumulate until the next
+ * scfgp_set_profiling call and are collected at scfgp_eval_finish. */
+enum {
+  SCFGP_FAM_NONE = 0,
+  SCFGP_FAM_FEATURES = 1,   /* X.W GEMM + sincos epilogue                      */
+  SCFGP_FAM_TGEMM = 2,      /* Phi.LiT with row-sum-of-squares epilogue         */
+  SCFGP_FAM_BACKWARD = 3,   /* Phi.(2Abar) + Psi.(2B) with trig-derivative epilogue */
+  SCFGP_FAM_SYRK = 4        /* PhiT.Phi / PsiT.Phi Gram accumulation            */
+};
+int scfgp_set_profiling(scfgp_handle* h, int family);
+int scfgp_get_profile(const scfgp_handle* h, double* total_ms, long long* launches);
+
 /* ---- self-test hooks used by tests/ (each runs ONE kernel family on caller data so a
  * failing parity test names the kernel, not the pipeline).  Host pointers, row-major. */
 /* C (m x n) = op(A).op(B)^T-style products through the DMMA mainloop.

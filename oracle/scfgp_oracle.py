@@ -328,3 +328,123 @@ def cpu_eval_reference_shaped(h, X, y, S, M, threads=None):
     """One NLML+gradient evaluation the way the reference executes it (dense float64
     ops on a materialised Phi, reverse-mode gradient): used for CPU timing only."""
     return literal_cost_grad(h, X, y, S, M, hermite=True, threads=threads)
+
+
+# --------------------------------------------------------------------------------------
+# phase-split streaming oracle (same phase API as include/scfgp_b200.h) -- lets the CPU
+# tests drive the multi-rank reduction protocol with gloo, one row shard per rank
+# --------------------------------------------------------------------------------------
+class PhaseOracle:
+    """NumPy counterpart of the scfgp_eval_* phase API over one row shard.  Buffers returned
+    by ``reduce_buffer`` are flat float64 arrays laid out like the CUDA library's:
+    RED1 = [G | p | yy], RED2 = [H | q | E | g_tau], RED3 = [dW | dphi | dnlml/db]."""
+
+    def __init__(self, X, y, S, M, n_global=None, chunk=1024):
+        self.X = np.asarray(X, dtype=np.float64)
+        self.y = np.asarray(y, dtype=np.float64).reshape(-1)
+        self.N, self.D = self.X.shape
+        self.S, self.M = S, M
+        self.J = S + M
+        self.K = 2 * self.J
+        self.Ng = n_global or self.N
+        self.chunk = chunk
+
+    def _chunks(self):
+        for i in range(0, self.N, self.chunk):
+            yield i, self.X[i:i + self.chunk], self.y[i:i + self.chunk]
+
+    def begin(self, h):
+        a, b, c, l_F, r_F, F, l_FC, FC = unpack_params(h, self.D, self.S, self.M)
+        self.a, self.b, self.c, self.l_F, self.r_F, self.F = a, b, c, l_F, r_F, F
+        self.W = np.concatenate((l_F, F), 1)
+        self.phi = np.concatenate((l_FC.ravel(), FC.ravel()))
+        self.sig2n = np.exp(2 * a)
+        self.tau = np.log(1 + np.exp(c))
+        self.s = np.exp(b) * np.sqrt(2. / self.M)
+        K = self.K
+        self.red = {1: np.zeros(K * K + K + 1), 2: np.zeros(K * K + K + 2),
+                    3: np.zeros(self.D * self.J + self.J + 1)}
+
+    def reduce_buffer(self, which):
+        return self.red[which]
+
+    def pass1(self):
+        K = self.K
+        G = np.zeros((K, K)); p = np.zeros(K); yy = 0.0
+        for _, Xc, yc in self._chunks():
+            Ph = _features(Xc, self.W, self.phi, self.s)
+            G += Ph.T.dot(Ph); p += Ph.T.dot(yc); yy += yc.dot(yc)
+        self.red[1][:] = np.concatenate((G.ravel(), p, [yy]))
+
+    def factor(self):
+        K = self.K
+        G = self.red[1][:K * K].reshape(K, K)
+        self.p = self.red[1][K * K:K * K + K].copy()
+        self.yy = self.red[1][-1]
+        A = G + (self.sig2n + EPSILON) * np.eye(K)
+        self.L = np.linalg.cholesky(A)
+        self.Li = np.linalg.inv(self.L)
+        self.beta = self.Li.dot(self.p)
+        self.alpha = self.Li.T.dot(self.beta)
+        self.Bm = self.Li.T.dot(self.Li)
+
+    def pass2(self):
+        K = self.K
+        E = 0.0; gt = 0.0; q = np.zeros(K); H = np.zeros((K, K))
+        self.gmu = np.empty(self.N); self.gv = np.empty(self.N)
+        for i, Xc, yc in self._chunks():
+            Ph = _features(Xc, self.W, self.phi, self.s)
+            v = (Ph.dot(self.Li.T) ** 2).sum(1)
+            r = Ph.dot(self.alpha) - yc
+            d = self.tau * (v + 1)
+            E += ((r ** 2 + v) / d + np.log(2 * np.pi * d)).sum()
+            k = -(r ** 2 + v) / d ** 2 + 1 / d
+            gm = 2 * r / d; gvv = 1 / d + self.tau * k
+            gt += (k * (v + 1)).sum()
+            self.gmu[i:i + len(yc)] = gm; self.gv[i:i + len(yc)] = gvv
+            q += Ph.T.dot(gm); H += Ph.T.dot(gvv[:, None] * Ph)
+        self.red[2][:] = np.concatenate((H.ravel(), q, [E, gt]))
+
+    def backward(self):
+        K = self.K
+        H = self.red[2][:K * K].reshape(K, K)
+        q = self.red[2][K * K:K * K + K]
+        t = self.Bm.dot(q)
+        al = self.alpha
+        self.Abar = self.Bm - self.Bm.dot(H).dot(self.Bm) - 0.5 * (np.outer(t, al) + np.outer(al, t)) \
+            + np.outer(al, al) / self.sig2n
+        self.pbar = t - 2 * al / self.sig2n
+
+    def pass3(self):
+        J = self.J
+        Wbar = np.zeros((self.D, J)); phibar = np.zeros(J); db = 0.0
+        for i, Xc, yc in self._chunks():
+            Ph = _features(Xc, self.W, self.phi, self.s)
+            n = len(yc)
+            Phbar = Ph.dot(2 * self.Abar) + (2 * self.gv[i:i + n])[:, None] * Ph.dot(self.Bm) \
+                + np.outer(yc, self.pbar) + np.outer(self.gmu[i:i + n], self.alpha)
+            db += (Phbar * Ph).sum()
+            Zbar = -Phbar[:, :J] * Ph[:, J:] + Phbar[:, J:] * Ph[:, :J]
+            Wbar += Xc.T.dot(Zbar); phibar += Zbar.sum(0)
+        self.red[3][:] = np.concatenate((Wbar.ravel(), phibar, [db]))
+
+    def finish(self, want_grad=True):
+        K, J, D, S, M, Ng = self.K, self.J, self.D, self.S, self.M, self.Ng
+        E, gt = self.red[2][-2], self.red[2][-1]
+        nlml = 2 * np.log(np.diagonal(self.L)).sum() + E + (self.yy - self.beta.dot(self.beta)) / self.sig2n \
+            + 2 * (Ng - M) * self.a
+        pen, pen_dlF, pen_dF = penalty_and_grad(self.l_F, self.F, S, M)
+        cost = (nlml + pen) / Ng
+        if not want_grad:
+            return float(cost), None, self.alpha[:, None], self.Li
+        Wbar = self.red[3][:D * J].reshape(D, J)
+        phibar = self.red[3][D * J:D * J + J]
+        d_b = self.red[3][-1]
+        d_a = 2 * self.sig2n * (np.trace(self.Abar) - (self.yy - self.p.dot(self.alpha)) / self.sig2n ** 2) \
+            + 2 * (Ng - M)
+        d_c = gt / (1 + np.exp(-self.c))
+        Wl = Wbar[:, :S] - phibar[None, :S] / D + pen_dlF
+        WF = Wbar[:, S:] - phibar[None, S:] / D + pen_dF
+        grad = np.concatenate(([d_a, d_b, d_c], (Wl + WF.dot(self.r_F)).ravel(), WF.T.dot(self.l_F).ravel(),
+                               phibar[:S], phibar[S:])) / Ng
+        return float(cost), grad, self.alpha[:, None], self.Li

@@ -72,6 +72,13 @@ struct scfgp_handle {
   long long launches = 0;
   cudaEvent_t ev[8] = {};
   float ms_pass[4] = {0, 0, 0, 0};
+
+  // optional per-kernel-family timing (CUDA events around every launch of one family)
+  int prof_family = SCFGP_FAM_NONE;
+  std::vector<cudaEvent_t> prof_ev;   // pairs
+  size_t prof_used = 0;
+  double prof_ms = 0;
+  long long prof_launches = 0;
 };
 
 namespace {
@@ -97,6 +104,31 @@ namespace {
   } while (0)
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// profiling brackets: record an event pair around launches of the selected family
+inline void prof_begin(scfgp_handle* h, int fam) {
+  if (h->prof_family != fam) return;
+  if (h->prof_used + 2 > h->prof_ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    h->prof_ev.push_back(a); h->prof_ev.push_back(b);
+  }
+  cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+}
+inline void prof_end(scfgp_handle* h, int fam) {
+  if (h->prof_family != fam) return;
+  cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+  h->prof_used += 2;
+}
+inline void prof_collect(scfgp_handle* h) {
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) {
+      h->prof_ms += ms; h->prof_launches++;
+    } else (void)cudaGetLastError();
+  }
+  h->prof_used = 0;
+}
 
 template <class T>
 int dalloc(scfgp_handle* h, T** p, size_t n) {
@@ -250,12 +282,14 @@ int run_features(scfgp_handle* h, const double* Xc, int rows, const double* rows
   const int nfb = cdiv(h->J, 64);
   const int nrb = cdiv(rows, 128);
   const size_t smem = SmemSize<CfgTall, true, true>::BYTES;
+  prof_begin(h, SCFGP_FAM_FEATURES);
   if (h->xvec == 2)
     k_features<2><<<nrb * nfb, CfgTall::NT, smem, h->stream>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi,
                                                                h->J, h->s, h->PhiS, h->ldk, rowscale, Psi, nfb);
   else
     k_features<1><<<nrb * nfb, CfgTall::NT, smem, h->stream>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi,
                                                                h->J, h->s, h->PhiS, h->ldk, rowscale, Psi, nfb);
+  prof_end(h, SCFGP_FAM_FEATURES);
   CKL();
   return SCFGP_OK;
 }
@@ -266,8 +300,10 @@ int run_features(scfgp_handle* h, const double* Xc, int rows, const double* rows
 // the epilogue).
 int run_tgemm(scfgp_handle* h, int rows) {
   const size_t smem = SmemSize<CfgBig, true, true>::BYTES;
+  prof_begin(h, SCFGP_FAM_TGEMM);
   k_tgemm_rowsq<<<h->tgemm.count, CfgBig::NT, smem, h->stream>>>(h->PhiS, h->ldk, rows, h->K, h->Li, h->ldk,
                                                                 h->vpart, h->R, h->tgemm.d);
+  prof_end(h, SCFGP_FAM_TGEMM);
   CKL();
   return SCFGP_OK;
 }
@@ -365,6 +401,7 @@ void free_all(scfgp_handle* h) {
   for (int4* p : h->to_free) cudaFree(p);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->prof_ev) cudaEventDestroy(e);
 }
 
 // penalty of SCFGP/SCFGP.py:94,114-117,127 and its adjoints (A.6), host
@@ -540,9 +577,11 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   for (long long r0 = 0; r0 < h->N; r0 += h->R) {
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
     if ((rc = run_features(h, h->dX + r0 * h->D, rows, nullptr, nullptr))) return rc;
-    if ((rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PhiS, h->ldk, K, h->PhiS, h->ldk, K, G, h->ldk,
-                                                      1.0, 1.0, h->lowerK, rows)))
-      return rc;
+    prof_begin(h, SCFGP_FAM_SYRK);
+    rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PhiS, h->ldk, K, h->PhiS, h->ldk, K, G, h->ldk, 1.0, 1.0,
+                                                 h->lowerK, rows);
+    prof_end(h, SCFGP_FAM_SYRK);
+    if (rc) return rc;
     k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->dy + r0,
                                                                     h->colpart, K);
     CKL();
@@ -626,9 +665,11 @@ int scfgp_eval_pass2(scfgp_handle* h) {
                                                h->want_grad);
     CKL();
     if (h->want_grad) {
-      if ((rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PsiS, h->ldk, K, h->PhiS, h->ldk, K, H, h->ldk,
-                                                        1.0, 1.0, h->lowerK, rows)))
-        return rc;
+      prof_begin(h, SCFGP_FAM_SYRK);
+      rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PsiS, h->ldk, K, h->PhiS, h->ldk, K, H, h->ldk, 1.0, 1.0,
+                                                   h->lowerK, rows);
+      prof_end(h, SCFGP_FAM_SYRK);
+      if (rc) return rc;
       k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->gmu + r0,
                                                                       h->colpart, K);
       CKL();
@@ -693,9 +734,11 @@ int scfgp_eval_pass3(scfgp_handle* h) {
     const double* Xc = h->dX + r0 * D;
     if ((rc = run_features(h, Xc, rows, h->gv + r0, h->PsiS))) return rc;
     const int nitems = cdiv(rows, 128) * nfb;  // items are rb-major
+    prof_begin(h, SCFGP_FAM_BACKWARD);
     k_backward<<<nitems, CfgBig::NT, smem, h->stream>>>(h->PhiS, h->PsiS, h->ldk, rows, K, J, h->A2, h->B2,
                                                         h->ldk, h->dy + r0, h->gmu + r0, h->pbar, h->alpha,
                                                         h->Zbar, h->ldj, h->slots, h->bwd.d);
+    prof_end(h, SCFGP_FAM_BACKWARD);
     CKL();
     // dW += XcT . Zbar
     if (h->xvec == 2)
@@ -738,6 +781,7 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
   if (Li) CK(cudaMemcpy2DAsync(Li, (size_t)K * sizeof(double), h->Li, h->ldk * sizeof(double),
                                (size_t)K * sizeof(double), K, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  prof_collect(h);
   for (int i = 0; i < 3; ++i) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]) == cudaSuccess) h->ms_pass[i] = ms;
@@ -827,6 +871,20 @@ int scfgp_device_factors(scfgp_handle* h, void** d_alpha, void** d_Li, long long
   if (d_alpha) *d_alpha = h->alpha;
   if (d_Li) *d_Li = h->Li;
   if (ld_Li) *ld_Li = h->ldk;
+  return SCFGP_OK;
+}
+
+int scfgp_set_profiling(scfgp_handle* h, int family) {
+  if (!h || family < SCFGP_FAM_NONE || family > SCFGP_FAM_SYRK) return SCFGP_ERR_ARG;
+  h->prof_family = family;
+  h->prof_ms = 0; h->prof_launches = 0; h->prof_used = 0;
+  return SCFGP_OK;
+}
+
+int scfgp_get_profile(const scfgp_handle* h, double* total_ms, long long* launches) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (total_ms) *total_ms = h->prof_ms;
+  if (launches) *launches = h->prof_launches;
   return SCFGP_OK;
 }
 

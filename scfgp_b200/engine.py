@@ -90,6 +90,15 @@ class Engine:
         self.lib.scfgp_last_pass_ms(self._h, *[C.byref(x) for x in f])
         return tuple(float(x.value) for x in f)
 
+    def set_profiling(self, family: int):
+        self._check(self.lib.scfgp_set_profiling(self._h, int(family)))
+
+    def get_profile(self):
+        """(total ms, launches) of the profiled kernel family since set_profiling."""
+        ms, n = C.c_double(), C.c_longlong()
+        self.lib.scfgp_get_profile(self._h, C.byref(ms), C.byref(n))
+        return float(ms.value), int(n.value)
+
     def set_stream(self, stream_ptr: int):
         self._check(self.lib.scfgp_set_stream(self._h, C.c_void_p(stream_ptr)))
 
@@ -154,20 +163,23 @@ class Engine:
             self._check(self.lib.scfgp_eval(self._h, _lib.dptr(params), _lib.dptr(cost), gp, ap, lp))
         else:
             import torch
-            lib, h = self.lib, self._h
-            self._check(lib.scfgp_eval_begin(h, _lib.dptr(params), int(want_grad)))
-            self._check(lib.scfgp_eval_pass1(h))
-            dist.all_reduce(self._reduce_tensor(_lib.RED1), group=group)
-            torch.cuda.current_stream().synchronize()
-            self._check(lib.scfgp_eval_factor(h))
-            self._check(lib.scfgp_eval_pass2(h))
-            dist.all_reduce(self._reduce_tensor(_lib.RED2), group=group)
-            torch.cuda.current_stream().synchronize()
-            if want_grad:
-                self._check(lib.scfgp_eval_backward(h))
-                self._check(lib.scfgp_eval_pass3(h))
-                dist.all_reduce(self._reduce_tensor(_lib.RED3), group=group)
+            from .sharding import run_eval_phases
+            lib, h, eng = self.lib, self._h, self
+
+            class _Api:
+                def pass1(s): eng._check(lib.scfgp_eval_pass1(h))
+                def factor(s): eng._check(lib.scfgp_eval_factor(h))
+                def pass2(s): eng._check(lib.scfgp_eval_pass2(h))
+                def backward(s): eng._check(lib.scfgp_eval_backward(h))
+                def pass3(s): eng._check(lib.scfgp_eval_pass3(h))
+                def reduce_buffer(s, which): return eng._reduce_tensor(which)
+
+            def _allreduce(buf):
+                dist.all_reduce(buf, group=group)
                 torch.cuda.current_stream().synchronize()
+
+            self._check(lib.scfgp_eval_begin(h, _lib.dptr(params), int(want_grad)))
+            run_eval_phases(_Api(), _allreduce, want_grad)
             self._check(lib.scfgp_eval_finish(h, _lib.dptr(cost), gp, ap, lp))
         return (float(cost[0]), grad, alpha.reshape(-1, 1) if want_factors else None, Li)
 

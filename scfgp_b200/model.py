@@ -1,0 +1,355 @@
+"""``SCFGP`` -- the reference's model facade over the B200 hot path.
+
+Mirrors ``SCFGP/SCFGP.py:21-317`` (constructor, ``set_data``, ``optimize``, ``predict``,
+``get_compiled_funcs``, ``save``/``load``) and the README-generation spelling
+``SCFGP(rank, feature_size, fftype, msg).fit/predict`` (README.md:44-53,
+experiments/kin8nm/kin8nm.py:53-74).  The three "compiled functions" are closures over a
+``scfgp_b200.engine.Engine`` (C ABI -> sm_100a kernels); the optimiser and the scalers
+stay on the host.  No CPU fallback exists: constructing the functions without the CUDA
+library raises.
+"""
+from __future__ import annotations
+
+import string
+import sys
+import time
+
+import numpy as np
+import numpy.random as npr
+
+from . import _lib
+from .engine import Engine
+from .optimizer import Optimizer as OPT
+from .scaler import Scaler
+
+_PHASE_NAMES = {None: _lib.FF_PHASE, True: _lib.FF_PHASE, "phase": _lib.FF_PHASE, "ph": _lib.FF_PHASE,
+                False: _lib.FF_NOPHASE, "non-phase": _lib.FF_NOPHASE, "nonphase": _lib.FF_NOPHASE,
+                "no-phase": _lib.FF_NOPHASE, "f": _lib.FF_NOPHASE}
+
+
+def _new_evals():
+    return {
+        "SCORE": ["Model Selection Score", []],
+        "COST": ["Hyperparameter Selection Cost", []],
+        "MAE": ["Mean Absolute Error", []],
+        "NMAE": ["Normalized Mean Absolute Error", []],
+        "MSE": ["Mean Square Error", []],
+        "NMSE": ["Normalized Mean Square Error", []],
+        "MNLP": ["Mean Negative Log Probability", []],
+        "TIME(s)": ["Training Time", []],
+    }
+
+
+class CompiledFuncs(tuple):
+    """(train_func, train_iter_func, pred_func) -- what ``get_compiled_funcs`` returns
+    (SCFGP/SCFGP.py:150-151).  Carries the engine so another model of the same shape can
+    reuse the handle (``optimize(funcs=...)``, SCFGP/SCFGP.py:209-210)."""
+    engine = None
+
+
+class SCFGP(object):
+    """Sparsely Correlated Fourier Features Based Gaussian Process (B200-native hot path)."""
+
+    def __init__(self, rank=None, feature_size=None, fftype=None, msg=None, *, sparsity=None, nfeats=None,
+                 evals=None, X_scaling_method='auto-inv-normal', y_scaling_method='auto-normal',
+                 verbose=None, device=0, chunk_rows=None):
+        # G2 spelling: SCFGP(sparsity=20, nfeats=18, ...) (SCFGP.py:33-35);
+        # G1 spelling: SCFGP(rank, feature_size, fftype, msg) (README.md:47-50).
+        S = sparsity if sparsity is not None else (rank if rank is not None else 20)
+        M = nfeats if nfeats is not None else (feature_size if feature_size is not None else 18)
+        self.S_requested = int(S)      # rank <= 0 ("-1" in the G1 scripts): resolved to D in set_data
+        self.S = int(S)
+        self.M = int(M)
+        key = fftype.lower() if isinstance(fftype, str) else fftype
+        if key not in _PHASE_NAMES:
+            raise ValueError(f"unknown fftype {fftype!r}; use 'phase' or 'non-phase'")
+        self.fftype = _PHASE_NAMES[key]
+        self.verbose = bool(verbose if verbose is not None else (msg if msg is not None else False))
+        self.X_scaler = Scaler(X_scaling_method)
+        self.y_scaler = Scaler(y_scaling_method)
+        self.evals = _new_evals() if evals is None else evals
+        self.device = device
+        self.chunk_rows = chunk_rows
+        self.N = self.D = -1
+        self.X = self.y = self.params = self.alpha = self.Li = None
+        self.train_func = self.train_iter_func = self.pred_func = None
+        self._engine = None
+        self._engine_data_id = None
+        self._rule = None
+        self.min_obj_ind = 0
+        self.generate_ID()
+
+    # ------------------------------------------------------------------ misc (SCFGP.py:53-62)
+    def message(self, *arg):
+        if self.verbose:
+            print(" ".join(map(str, arg)))
+            sys.stdout.flush()
+
+    def generate_ID(self):
+        chars = string.ascii_uppercase + string.digits
+        self.ID = ''.join(chars[i] for i in npr.randint(0, len(chars), 5))
+        self.NAME = "SCFGP (Sparsity=%d, Fourier Features=%d)" % (self.S, self.M)
+
+    # ------------------------------------------------------------------ parameters (SCFGP.py:64-72)
+    def init_params(self, rng=None):
+        r = npr if rng is None else rng
+        randn = (lambda n: r.randn(n)) if rng is None else (lambda n: r.standard_normal(n))
+        rand = (lambda n: r.rand(n)) if rng is None else (lambda n: r.random(n))
+        a, b, c = randn(1), randn(1), randn(1)
+        l_f = randn(self.D * self.S)
+        r_f = rand(self.M * self.S)
+        l_p = 2 * np.pi * rand(self.S)
+        p = 2 * np.pi * rand(self.M)
+        self.params = np.concatenate([a, b, c, l_f, r_f, l_p, p])
+
+    # ------------------------------------------------------------------ compiled functions
+    def _ensure_engine(self, engine=None):
+        if engine is not None:
+            if (engine.D, engine.S, engine.M) != (self.D, self.S, self.M):
+                raise ValueError("injected funcs were built for a different (D, S, M)")
+            self._engine = engine
+        if self._engine is None:
+            self._engine = Engine(self.D, self.S, self.M, self.fftype, self.device, self.chunk_rows)
+        return self._engine
+
+    def _upload(self, X, y):
+        key = (id(X), id(y), X.shape)
+        if self._engine_data_id != key:
+            self._engine.set_data(X, y)
+            self._engine_data_id = key
+
+    def build_models(self, algo='adam', algo_params=None, engine=None):
+        """Counterpart of ``build_theano_models`` (SCFGP.py:92-148): binds the three callables."""
+        eng = self._ensure_engine(engine)
+        self._engine_data_id = None
+        self._rule = OPT.build(algo, algo_params, nesterov=0.9)
+
+        def train_func(X, y):
+            self._upload(X, y)
+            cost, _, alpha, Li = eng.eval(self.params, want_grad=False)
+            return [np.float64(cost), alpha, Li]
+
+        def train_iter_func(X, y):
+            self._upload(X, y)
+            cost, grad, alpha, Li = eng.eval(self.params, want_grad=True)
+            self.last_grad = grad
+            self.params = self._rule.step(self.params, grad)
+            return [np.float64(cost), alpha, Li]
+
+        def pred_func(Xs, alpha, Li):
+            mu, sd = eng.predict(self.params, Xs, alpha, Li)
+            return [mu, sd]
+
+        self.train_func, self.train_iter_func, self.pred_func = train_func, train_iter_func, pred_func
+
+    def get_compiled_funcs(self):
+        f = CompiledFuncs((self.train_func, self.train_iter_func, self.pred_func))
+        f.engine = self._engine
+        return f
+
+    # ------------------------------------------------------------------ data (SCFGP.py:153-170)
+    def set_data(self, X, y):
+        self.message("-" * 60, "\nNormalizing SCFGP training data...")
+        X = np.asarray(X, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None]
+        self.X_scaler.fit(X)
+        self.y_scaler.fit(y)
+        self.X = np.ascontiguousarray(self.X_scaler.forward_transform(X))
+        self.y = np.ascontiguousarray(self.y_scaler.forward_transform(y))
+        self.message("done.")
+        self.N, self.D = self.X.shape
+        if self.S_requested <= 0:
+            self.S = self.D
+            self.NAME = "SCFGP (Sparsity=%d, Fourier Features=%d)" % (self.S, self.M)
+        if self.train_func is None:
+            self.message("-" * 60, "\nInitializing SCFGP hyperparameters...")
+            if self.params is None or len(self.params) != 3 + self.D * self.S + self.M * self.S + self.S + self.M:
+                self.init_params()
+            self.message("done.")
+        else:
+            cost, self.alpha, self.Li = self.train_func(self.X, self.y)
+
+    def minibatches(self, X, y, batchsize, shuffle=True):
+        assert len(X) == len(y)
+        if shuffle:
+            inds = np.arange(len(X))
+            np.random.shuffle(inds)
+        for start_ind in range(0, len(X) - batchsize + 1, batchsize):
+            batch = inds[start_ind:start_ind + batchsize] if shuffle else slice(start_ind, start_ind + batchsize)
+            yield np.ascontiguousarray(X[batch]), np.ascontiguousarray(y[batch])
+
+    # ------------------------------------------------------------------ training loop (SCFGP.py:184-276)
+    def optimize(self, Xv=None, yv=None, funcs=None, visualizer=None, **args):
+        obj = args.get('obj', 'COST').upper()
+        obj = obj if obj in self.evals else 'COST'
+        algo = args.get('algo', {'algo': None})
+        nbatches = args.get('nbatches', 1)
+        batchsize = args.get('batchsize', 150)
+        cvrg_tol = args.get('cvrg_tol', 1e-4)
+        max_cvrg = args.get('max_cvrg', 18)
+        max_iter = args.get('max_iter', 500)
+        restore_best = args.get('restore_best', False)  # the reference's restore is a no-op
+        if not isinstance(algo, dict) or algo.get('algo') not in OPT.algos:
+            algo = {'algo': 'adam',
+                    'algo_params': {'learning_rate': 0.01, 'beta1': 0.9, 'beta2': 0.999, 'epsilon': 1e-8}}
+        for metric in self.evals:
+            self.evals[metric][1] = []
+        if funcs is None:
+            self.message("-" * 50, "\nBinding SCFGP B200 kernels...")
+            self.build_models(algo['algo'], algo.get('algo_params'))
+            self.message("done.")
+        else:
+            # Reuse the injected engine; unlike the reference the functions act on
+            # *this* model's parameters, not on the first model's captured shared variable.
+            self.build_models(algo['algo'], algo.get('algo_params'), engine=getattr(funcs, "engine", None))
+        if visualizer is not None:
+            raise NotImplementedError("Visualizer (matplotlib live plots) is out of scope of the hot path")
+        if Xv is None or yv is None:
+            obj = 'COST'
+            for m in ('MAE', 'NMAE', 'MSE', 'NMSE', 'MNLP', 'SCORE'):
+                self.evals[m][1].append(0)
+        self.min_obj_ind = 0
+        train_start_time = time.time()
+        min_obj_val, argmin_params, cvrg_iter = np.inf, self.params.copy(), 0
+        report_every = max(1, max_iter // 10)
+        for it in range(max_iter):
+            if nbatches > 1:
+                cost_sum, params_list, batch_count = 0, [], 0
+                for Xb, yb in self.minibatches(self.X, self.y, batchsize):
+                    params_list.append(self.params.copy())
+                    cost, self.alpha, self.Li = self.train_iter_func(Xb, yb)
+                    cost_sum += cost
+                    batch_count += 1
+                    if batch_count == nbatches:
+                        break
+                self.evals['COST'][1].append(np.double(cost_sum / batch_count))
+            else:
+                cost, self.alpha, self.Li = self.train_iter_func(self.X, self.y)
+                self.evals['COST'][1].append(cost)
+            self.evals['TIME(s)'][1].append(time.time() - train_start_time)
+            if Xv is not None and yv is not None:
+                self.predict(Xv, yv)
+            if it % report_every == 1:
+                self.message("-" * 17, "VALIDATION ITERATION", it, "-" * 17)
+                self._print_current_evals()
+            obj_val = self.evals[obj][1][-1]
+            if obj_val < min_obj_val:
+                cvrg_iter = cvrg_iter + 1 if min_obj_val - obj_val < cvrg_tol else 0
+                min_obj_val = obj_val
+                self.min_obj_ind = len(self.evals['COST'][1]) - 1
+                argmin_params = self.params.copy()
+            else:
+                cvrg_iter += 1
+            if it > 30 and cvrg_iter > max_cvrg:
+                break
+        if restore_best:
+            self.params = argmin_params.copy()
+        cost, self.alpha, self.Li = self.train_func(self.X, self.y)
+        self.evals['COST'][1].append(np.double(cost))
+        self.evals['TIME(s)'][1].append(time.time() - train_start_time)
+        if Xv is not None and yv is not None:
+            self.predict(Xv, yv)
+        self.min_obj_ind = len(self.evals['COST'][1]) - 1
+        disp, self.verbose = self.verbose, True if args.get('print_result', self.verbose) else False
+        self.message("-" * 19, "OPTIMIZATION RESULT", "-" * 20)
+        self._print_current_evals()
+        self.message("-" * 60)
+        self.verbose = disp
+
+    # ------------------------------------------------------------------ prediction (SCFGP.py:278-294)
+    def predict(self, Xs, ys=None):
+        self.Xs = np.ascontiguousarray(self.X_scaler.forward_transform(np.asarray(Xs, dtype=np.float64)))
+        if self.pred_func is None:
+            self.build_models()
+        mu_f, std_f = self.pred_func(self.Xs, self.alpha, self.Li)
+        mu_y = self.y_scaler.backward_transform(mu_f)
+        up_bnd_y = self.y_scaler.backward_transform(mu_f + std_f[:, None])
+        dn_bnd_y = self.y_scaler.backward_transform(mu_f - std_f[:, None])
+        std_y = 0.5 * (up_bnd_y - dn_bnd_y)
+        if ys is not None:
+            ys = np.asarray(ys, dtype=np.float64)
+            if ys.ndim == 1:
+                ys = ys[:, None]
+            ev = self.evals
+            ev['MAE'][1].append(np.mean(np.abs(mu_y - ys)))
+            ev['NMAE'][1].append(ev['MAE'][1][-1] / np.std(ys))
+            ev['MSE'][1].append(np.mean((mu_y - ys) ** 2.))
+            ev['NMSE'][1].append(ev['MSE'][1][-1] / np.var(ys))
+            ev['MNLP'][1].append(0.5 * np.mean(((ys - mu_y) / std_y) ** 2 + np.log(2 * np.pi * std_y ** 2)))
+            ev['SCORE'][1].append(ev['NMSE'][1][-1] / (1 + np.exp(-ev['MNLP'][1][-1])))
+            # README-generation result attributes (experiments/kin8nm/kin8nm.py:67-74)
+            self.TsMAE, self.TsMSE = ev['MAE'][1][-1], ev['MSE'][1][-1]
+            self.TsRMSE = float(np.sqrt(self.TsMSE))
+            self.TsNMSE, self.TsMNLP, self.SCORE = ev['NMSE'][1][-1], ev['MNLP'][1][-1], ev['SCORE'][1][-1]
+        return mu_y, std_y
+
+    # ------------------------------------------------------------------ README-generation API
+    def fit(self, X_train, y_train, X_test=None, y_test=None, funcs=None, plot=False, plot_training=False,
+            **opt):
+        """``model.fit(X_train, y_train, {X_test}, {y_test})`` (README.md:51).  ``plot*`` are
+        accepted and ignored (matplotlib visualisation is out of scope)."""
+        self.set_data(X_train, y_train)
+        t0 = time.time()
+        self.optimize(X_test, y_test, funcs, None, **opt)
+        self.TrTime = time.time() - t0
+        self.COST = self.evals['COST'][1][-1]
+        return self
+
+    # ------------------------------------------------------------------ checkpoint (SCFGP.py:296-310)
+    def save(self, path):
+        """``.npz`` checkpoint: unlike the reference's pickle it also stores S, D and the optimiser
+        slots and does not contain compiled functions."""
+        out = dict(ID=self.ID, M=self.M, S=self.S, D=self.D, fftype=self.fftype, params=self.params,
+                   alpha=self.alpha, Li=self.Li)
+        for k, v in self.X_scaler.state_dict().items():
+            out["xs_" + k] = v
+        for k, v in self.y_scaler.state_dict().items():
+            out["ys_" + k] = v
+        for k, v in self.evals.items():
+            out["evals_" + k] = np.asarray(v[1], dtype=np.float64)
+        if self._rule is not None:
+            for k, v in self._rule.state_dict().items():
+                out["opt_" + k] = v
+        with open(path, "wb") as f:
+            np.savez_compressed(f, **out)
+
+    def load(self, path):
+        with np.load(path, allow_pickle=False) as z:
+            d = {k: z[k] for k in z.files}
+        self.ID = str(d["ID"])
+        self.M, self.S, self.D = int(d["M"]), int(d["S"]), int(d["D"])
+        self.S_requested = self.S
+        self.fftype = int(d.get("fftype", _lib.FF_PHASE))
+        self.params, self.alpha, self.Li = d["params"], d["alpha"], d["Li"]
+        self.X_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("xs_")})
+        self.y_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("ys_")})
+        for k in self.evals:
+            if "evals_" + k in d:
+                self.evals[k][1] = list(d["evals_" + k])
+        self._engine = None
+        self.train_func = self.train_iter_func = self.pred_func = None
+        self.NAME = "SCFGP (Sparsity=%d, Fourier Features=%d)" % (self.S, self.M)
+        return self
+
+    def load_reference_golden(self, npz_path):
+        """Load the arrays extracted from the reference's shipped pickle
+        (tests/golden/make_golden.py) so the shipped Boston model can predict."""
+        with np.load(npz_path, allow_pickle=False) as z:
+            d = {k: z[k] for k in z.files}
+        self.M, self.S, self.D = int(d["M"]), int(d["S"]), int(d["D"])
+        self.S_requested = self.S
+        self.params, self.alpha, self.Li = d["params"], d["alpha"], d["Li"]
+        self.X_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("xs_")})
+        self.y_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("ys_")})
+        self._engine = None
+        self.train_func = self.train_iter_func = self.pred_func = None
+        return self
+
+    def _print_current_evals(self):
+        for metric in sorted(self.evals.keys()):
+            if len(self.evals[metric][1]) < len(self.evals['COST'][1]):
+                continue
+            best_perform_eval = self.evals[metric][1][self.min_obj_ind]
+            self.message(self.NAME, "%7s = %.4e" % (metric, best_perform_eval))

@@ -1,0 +1,34 @@
+"""Row sharding and the phase sequence of one multi-GPU likelihood evaluation.
+
+Training rows shard over ranks (every O(N) quantity of the path is a sum over rows,
+SURVEY.md section 8e); X never moves.  ``run_eval_phases`` is the one place that knows
+the order of phases and reductions; ``Engine.eval`` drives the CUDA phase API with it
+(NCCL), and the CPU tests drive a NumPy phase implementation with it (gloo).
+"""
+from __future__ import annotations
+
+
+def shard_bounds(n_rows: int, rank: int, world: int):
+    """Contiguous, balanced row range [lo, hi) of `rank`; the first n_rows % world ranks
+    get one extra row."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(int(n_rows), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def run_eval_phases(api, allreduce, want_grad: bool):
+    """Sequence: pass1 -> allreduce(RED1) -> factor -> pass2 -> allreduce(RED2)
+    [-> backward -> pass3 -> allreduce(RED3)].  `api` exposes pass1/factor/pass2/backward/
+    pass3 and reduce_buffer(which); `allreduce(buf)` sums `buf` in place over ranks."""
+    api.pass1()
+    allreduce(api.reduce_buffer(1))
+    api.factor()
+    api.pass2()
+    allreduce(api.reduce_buffer(2))
+    if want_grad:
+        api.backward()
+        api.pass3()
+        allreduce(api.reduce_buffer(3))

@@ -1,0 +1,62 @@
+"""N>1 protocol on CPU: two gloo ranks, rows sharded with shard_bounds, each rank runs the
+phase API (NumPy PhaseOracle standing in for the CUDA phases) through the SAME
+run_eval_phases driver Engine.eval uses; the all-reduced result must equal the
+single-process evaluation."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, shape, out):
+    sys.path.insert(0, ROOT)
+    from oracle import scfgp_oracle as O
+    from scfgp_b200 import synth, shard_bounds, run_eval_phases
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, D, S, M = shape
+    X, y, h = synth.make_problem(N, D, S, M, seed=11)
+    lo, hi = shard_bounds(N, rank, world)
+    po = O.PhaseOracle(X[lo:hi], y[lo:hi], S, M, n_global=N, chunk=64)
+    po.begin(h)
+
+    def allreduce(buf):
+        t = torch.from_numpy(buf)       # shares memory: in-place sum like the NCCL path
+        dist.all_reduce(t)
+
+    run_eval_phases(po, allreduce, want_grad=True)
+    cost, grad, alpha, Li = po.finish()
+    if rank == 0:
+        np.savez(out, cost=cost, grad=grad, alpha=alpha, Li=Li)
+    # every rank must hold identical replicated results
+    t = torch.tensor([cost], dtype=torch.float64); lst = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(lst, t)
+    assert all(float(x) == float(lst[0]) for x in lst)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(301, 6, 3, 20)])
+def test_two_rank_gloo_matches_single(tmp_path, shape):
+    from oracle import scfgp_oracle as O
+    from scfgp_b200 import synth
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), shape, out), nprocs=2, join=True)
+    N, D, S, M = shape
+    X, y, h = synth.make_problem(N, D, S, M, seed=11)
+    c0, g0, a0, L0 = O.streaming_eval(h, X, y, S, M)
+    z = np.load(out)
+    assert abs(float(z["cost"]) - c0) <= 1e-12 * abs(c0)
+    np.testing.assert_allclose(z["grad"], g0, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(z["alpha"], a0, rtol=1e-8, atol=1e-10)
