@@ -12,6 +12,7 @@
 
 #include "../../include/scfgp_b200.h"
 #include "kernels.cuh"
+#include "kernels_tma.cuh"
 
 using namespace scfgp;
 
@@ -24,6 +25,18 @@ constexpr int kSeedBlocks = 296;
 struct ItemList {
   int4* d = nullptr;
   int count = 0;
+};
+
+constexpr int kMaxStreams = 4;
+struct Ctx {
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  double *Phi = nullptr, *Psi = nullptr, *Zbar = nullptr, *vpart = nullptr;  // slabs
+  double *acc = nullptr;      // K x ldk partial of G / H
+  double *dW = nullptr;       // D x ldj partial
+  double *colpart = nullptr;  // kColSplit x K
+  double *slots = nullptr;    // slot_stride scalars
+  CUtensorMap mapPhi, mapPsi; // 16x16-box TMA views of the slabs
 };
 
 }  // namespace
@@ -45,14 +58,23 @@ struct scfgp_handle {
 
   // device buffers
   double *Wt = nullptr, *phi = nullptr;
-  double *PhiS = nullptr, *PsiS = nullptr, *Zbar = nullptr, *vpart = nullptr;
+  // per-stream chunk contexts: consecutive row chunks run on different streams so the tail
+  // of one chunk's kernels overlaps the head of the next; each context owns its slabs and
+  // partial accumulators (deterministic: chunk c always lands in context c % ns)
+  Ctx ctx[kMaxStreams];
+  int ns = 3;
+  cudaEvent_t ev_fork = nullptr;
+  double *acc_all = nullptr, *dW_all = nullptr, *colpart_all = nullptr, *slots_all = nullptr;
+  long long slot_stride = 0;
+  int use_tma = 1;
+  CUtensorMap mapLi, mapA2, mapB2;
   double *red1 = nullptr, *red2 = nullptr, *red3 = nullptr;
   double *L = nullptr, *Li = nullptr, *Bm = nullptr, *BH = nullptr, *BHB = nullptr, *A2 = nullptr,
          *B2 = nullptr, *Dinv = nullptr, *tmpS = nullptr;
   double *alpha = nullptr, *beta = nullptr, *tvec = nullptr, *pbar = nullptr, *scal = nullptr;
   double *gmu = nullptr, *gv = nullptr;
   long long row_cap = 0;
-  double *colpart = nullptr, *slots = nullptr, *trslots = nullptr;
+  double *colpart = nullptr, *slots = nullptr, *trslots = nullptr;   // main-stream scratch
   long long* info = nullptr;
   int nrb_cap = 0;
 
@@ -105,19 +127,48 @@ namespace {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// 2-D row-major float64 view with 16 x 16 boxes, 128-byte swizzle, zero fill out of bounds
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+int make_tmap(scfgp_handle* h, CUtensorMap* out, const double* base, long long cols, long long rows, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { h->err = "cuTensorMapEncodeTiled not available"; return SCFGP_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  cuuint32_t box[2] = {16, 16};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return SCFGP_ERR_CUDA; }
+  return SCFGP_OK;
+}
+
 // profiling brackets: record an event pair around launches of the selected family
-inline void prof_begin(scfgp_handle* h, int fam) {
+inline void prof_begin(scfgp_handle* h, int fam, cudaStream_t st) {
   if (h->prof_family != fam) return;
   if (h->prof_used + 2 > h->prof_ev.size()) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     h->prof_ev.push_back(a); h->prof_ev.push_back(b);
   }
-  cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+  cudaEventRecord(h->prof_ev[h->prof_used], st);
 }
-inline void prof_end(scfgp_handle* h, int fam) {
+inline void prof_end(scfgp_handle* h, int fam, cudaStream_t st) {
   if (h->prof_family != fam) return;
-  cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+  cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
   h->prof_used += 2;
 }
 inline void prof_collect(scfgp_handle* h) {
@@ -159,8 +210,9 @@ std::vector<int4> lower_tiles(int m, int bs, int k0, int depth) {
 template <class Cfg, bool AK, bool BKM, int AVEC, int BVEC>
 int launch_gemm(scfgp_handle* h, const double* A, long long lda, int a_rows, const double* B,
                 long long ldb, int b_rows, double* C, long long ldc, double alpha, double beta,
-                const ItemList& items, int depth_arg) {
+                const ItemList& items, int depth_arg, cudaStream_t st = nullptr, bool use_st = false) {
   if (items.count == 0) return SCFGP_OK;
+  if (!use_st) st = h->stream;
   constexpr size_t smem = SmemSize<Cfg, AK, BKM>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
@@ -168,7 +220,7 @@ int launch_gemm(scfgp_handle* h, const double* A, long long lda, int a_rows, con
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_gemm<Cfg, AK, BKM, AVEC, BVEC><<<items.count, Cfg::NT, smem, h->stream>>>(
+  k_gemm<Cfg, AK, BKM, AVEC, BVEC><<<items.count, Cfg::NT, smem, st>>>(
       A, lda, a_rows, B, ldb, b_rows, C, ldc, alpha, beta, items.d, depth_arg);
   CKL();
   return SCFGP_OK;
@@ -184,6 +236,9 @@ int set_kernel_attrs(scfgp_handle* h) {
   CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SmemSize<CfgBig, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+  CK(cudaFuncSetAttribute(k_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_tgemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_backward_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
   return SCFGP_OK;
 }
 
@@ -249,19 +304,22 @@ int ensure_row_arrays(scfgp_handle* h, long long n) {
   return SCFGP_OK;
 }
 
-// (re)allocate everything that depends on the chunk size R
+// (re)allocate everything that depends on the chunk size R / number of streams
 int alloc_chunk_buffers(scfgp_handle* h) {
-  for (double** p : {&h->PhiS, &h->PsiS, &h->Zbar, &h->vpart}) {
+  for (int i = 0; i < kMaxStreams; ++i) {
+    Ctx& c = h->ctx[i];
+    for (double** p : {&c.Phi, &c.Psi, &c.Zbar, &c.vpart}) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+  }
+  for (double** p : {&h->acc_all, &h->dW_all, &h->colpart_all, &h->slots_all}) {
     if (*p) cudaFree(*p);
     *p = nullptr;
   }
   const int K = h->K, R = h->R;
-  int rc;
-  if ((rc = dalloc(h, &h->PhiS, (size_t)R * h->ldk))) return rc;
-  if ((rc = dalloc(h, &h->PsiS, (size_t)R * h->ldk))) return rc;
-  if ((rc = dalloc(h, &h->Zbar, (size_t)R * h->ldj))) return rc;
   const int nkb = cdiv(K, 128);
-  if ((rc = dalloc(h, &h->vpart, (size_t)nkb * R))) return rc;
+  int rc;
   // work lists that depend on R
   const int nrb = R / 128;
   std::vector<int4> tg, bw;
@@ -272,38 +330,100 @@ int alloc_chunk_buffers(scfgp_handle* h) {
     for (int fb = 0; fb < nfb; ++fb) bw.push_back(make_int4(rb, fb, 0, 0));
   if ((rc = upload_items(h, tg, &h->tgemm))) return rc;
   if ((rc = upload_items(h, bw, &h->bwd))) return rc;
-  if (h->slots) cudaFree(h->slots);
-  h->slots = nullptr;
-  if ((rc = dalloc(h, &h->slots, (size_t)std::max(2 * kSeedBlocks, (int)bw.size()) + 1024))) return rc;
+  h->slot_stride = (std::max<long long>(std::max(2 * kSeedBlocks, (int)bw.size()), 256) + 1) / 2 * 2;
+  const size_t KK = (size_t)K * h->ldk, DJ = (size_t)h->D * h->ldj;
+  if ((rc = dalloc(h, &h->acc_all, KK * h->ns))) return rc;
+  if ((rc = dalloc(h, &h->dW_all, DJ * h->ns))) return rc;
+  if ((rc = dalloc(h, &h->colpart_all, (size_t)kColSplit * K * h->ns))) return rc;
+  if ((rc = dalloc(h, &h->slots_all, (size_t)h->slot_stride * h->ns))) return rc;
+  for (int i = 0; i < h->ns; ++i) {
+    Ctx& c = h->ctx[i];
+    if ((rc = dalloc(h, &c.Phi, (size_t)R * h->ldk))) return rc;
+    if ((rc = dalloc(h, &c.Psi, (size_t)R * h->ldk))) return rc;
+    if ((rc = dalloc(h, &c.Zbar, (size_t)R * h->ldj))) return rc;
+    if ((rc = dalloc(h, &c.vpart, (size_t)nkb * R))) return rc;
+    c.acc = h->acc_all + KK * i;
+    c.dW = h->dW_all + DJ * i;
+    c.colpart = h->colpart_all + (size_t)kColSplit * K * i;
+    c.slots = h->slots_all + (size_t)h->slot_stride * i;
+    if (h->use_tma) {
+      if ((rc = make_tmap(h, &c.mapPhi, c.Phi, K, R, h->ldk))) return rc;
+      if ((rc = make_tmap(h, &c.mapPsi, c.Psi, K, R, h->ldk))) return rc;
+    }
+  }
   return SCFGP_OK;
 }
 
-int run_features(scfgp_handle* h, const double* Xc, int rows, const double* rowscale, double* Psi) {
+// fork: the chunk streams start after everything queued on the main stream so far
+int fork_streams(scfgp_handle* h) {
+  CK(cudaEventRecord(h->ev_fork, h->stream));
+  for (int i = 0; i < h->ns; ++i) CK(cudaStreamWaitEvent(h->ctx[i].st, h->ev_fork, 0));
+  return SCFGP_OK;
+}
+// join: the main stream continues after every chunk stream has drained
+int join_streams(scfgp_handle* h) {
+  for (int i = 0; i < h->ns; ++i) {
+    CK(cudaEventRecord(h->ctx[i].done, h->ctx[i].st));
+    CK(cudaStreamWaitEvent(h->stream, h->ctx[i].done, 0));
+  }
+  return SCFGP_OK;
+}
+
+// C(lower tiles) += AsT . Bs over the valid rows of two slabs of context c
+int run_syrk(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
+  const int K = h->K;
+  int rc = SCFGP_OK;
+  prof_begin(h, SCFGP_FAM_SYRK, c.st);
+  if (h->use_tma) {
+    // TMA reads whole 32-row stages: rows beyond the valid ones must be zero, not stale
+    const int pad = (rows + 31) / 32 * 32;
+    if (pad > rows) {
+      CK(cudaMemsetAsync(c.Phi + (size_t)rows * h->ldk, 0, (size_t)(pad - rows) * h->ldk * sizeof(double), c.st));
+      if (a_is_psi)
+        CK(cudaMemsetAsync(c.Psi + (size_t)rows * h->ldk, 0, (size_t)(pad - rows) * h->ldk * sizeof(double), c.st));
+    }
+    k_syrk_tma<<<h->lowerK.count, TMA_THREADS, TMA_SMEM_BYTES, c.st>>>(a_is_psi ? c.mapPsi : c.mapPhi, c.mapPhi, rows,
+                                                                       K, K, c.acc, h->ldk, h->lowerK.d);
+    h->launches++;
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) { h->err = std::string("k_syrk_tma: ") + cudaGetErrorString(e_); rc = SCFGP_ERR_CUDA; }
+  } else {
+    rc = launch_gemm<CfgBig, false, false, 2, 2>(h, a_is_psi ? c.Psi : c.Phi, h->ldk, K, c.Phi, h->ldk, K, c.acc,
+                                                 h->ldk, 1.0, 1.0, h->lowerK, rows, c.st, true);
+  }
+  prof_end(h, SCFGP_FAM_SYRK, c.st);
+  return rc;
+}
+
+int run_features(scfgp_handle* h, Ctx& c, const double* Xc, int xvec, int rows, const double* rowscale,
+                 double* Psi) {
   const int nfb = cdiv(h->J, 64);
   const int nrb = cdiv(rows, 128);
   const size_t smem = SmemSize<CfgTall, true, true>::BYTES;
-  prof_begin(h, SCFGP_FAM_FEATURES);
-  if (h->xvec == 2)
-    k_features<2><<<nrb * nfb, CfgTall::NT, smem, h->stream>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi,
-                                                               h->J, h->s, h->PhiS, h->ldk, rowscale, Psi, nfb);
+  prof_begin(h, SCFGP_FAM_FEATURES, c.st);
+  if (xvec == 2)
+    k_features<2><<<nrb * nfb, CfgTall::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
+                                                          h->s, c.Phi, h->ldk, rowscale, Psi, nfb);
   else
-    k_features<1><<<nrb * nfb, CfgTall::NT, smem, h->stream>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi,
-                                                               h->J, h->s, h->PhiS, h->ldk, rowscale, Psi, nfb);
-  prof_end(h, SCFGP_FAM_FEATURES);
+    k_features<1><<<nrb * nfb, CfgTall::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
+                                                          h->s, c.Phi, h->ldk, rowscale, Psi, nfb);
+  prof_end(h, SCFGP_FAM_FEATURES, c.st);
   CKL();
   return SCFGP_OK;
 }
 
-// count of T-GEMM items that touch valid rows (items are ordered kb-major, rb-minor over
-// the full chunk; for a short last chunk launch a re-filtered prefix is not possible, so
-// short chunks simply run all items -- invalid row blocks are zero-filled and skipped in
-// the epilogue).
-int run_tgemm(scfgp_handle* h, int rows) {
+// T = Phi.LiT row sums of squares.  Items are ordered deepest-reduction first; CTAs whose
+// row block lies beyond a short last chunk exit immediately.
+int run_tgemm(scfgp_handle* h, Ctx& c, int rows) {
   const size_t smem = SmemSize<CfgBig, true, true>::BYTES;
-  prof_begin(h, SCFGP_FAM_TGEMM);
-  k_tgemm_rowsq<<<h->tgemm.count, CfgBig::NT, smem, h->stream>>>(h->PhiS, h->ldk, rows, h->K, h->Li, h->ldk,
-                                                                h->vpart, h->R, h->tgemm.d);
-  prof_end(h, SCFGP_FAM_TGEMM);
+  prof_begin(h, SCFGP_FAM_TGEMM, c.st);
+  if (h->use_tma)
+    k_tgemm_tma<<<h->tgemm.count, TMA_THREADS, TMA_SMEM_BYTES, c.st>>>(c.mapPhi, h->mapLi, rows, h->K, c.vpart, h->R,
+                                                                       h->tgemm.d);
+  else
+    k_tgemm_rowsq<<<h->tgemm.count, CfgBig::NT, smem, c.st>>>(c.Phi, h->ldk, rows, h->K, h->Li, h->ldk, c.vpart,
+                                                              h->R, h->tgemm.d);
+  prof_end(h, SCFGP_FAM_TGEMM, c.st);
   CKL();
   return SCFGP_OK;
 }
@@ -393,7 +513,15 @@ int build_static_lists(scfgp_handle* h) {
 }
 
 void free_all(scfgp_handle* h) {
-  for (double* p : {h->Wt, h->phi, h->PhiS, h->PsiS, h->Zbar, h->vpart, h->red1, h->red2, h->red3, h->L,
+  for (int i = 0; i < kMaxStreams; ++i) {
+    Ctx& c = h->ctx[i];
+    for (double* p : {c.Phi, c.Psi, c.Zbar, c.vpart})
+      if (p) cudaFree(p);
+    if (c.done) cudaEventDestroy(c.done);
+    if (c.st) cudaStreamDestroy(c.st);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (double* p : {h->acc_all, h->dW_all, h->colpart_all, h->slots_all, h->Wt, h->phi, h->red1, h->red2, h->red3, h->L,
                     h->Li, h->Bm, h->BH, h->BHB, h->A2, h->B2, h->Dinv, h->tmpS, h->alpha, h->beta, h->tvec,
                     h->pbar, h->scal, h->gmu, h->gv, h->colpart, h->slots, h->trslots, h->ownX, h->owny})
     if (p) cudaFree(p);
@@ -480,8 +608,21 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
     if ((rc = dalloc(h, p, K))) return rc;
   if ((rc = dalloc(h, &h->scal, 64))) return rc;
   if ((rc = dalloc(h, &h->colpart, (size_t)kColSplit * K))) return rc;
+  if ((rc = dalloc(h, &h->slots, 1024))) return rc;
+  if (const char* e = getenv("SCFGP_STREAMS")) h->ns = std::min(kMaxStreams, std::max(1, atoi(e)));
+  for (int i = 0; i < kMaxStreams; ++i) {
+    CK(cudaStreamCreateWithFlags(&h->ctx[i].st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ctx[i].done, cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   if ((rc = dalloc(h, &h->trslots, K))) return rc;
   if ((rc = dalloc(h, &h->info, 1))) return rc;
+  if (const char* e = getenv("SCFGP_NO_TMA")) h->use_tma = atoi(e) ? 0 : 1;
+  if (h->use_tma) {
+    if ((rc = make_tmap(h, &h->mapLi, h->Li, K, K, h->ldk))) return rc;
+    if ((rc = make_tmap(h, &h->mapA2, h->A2, K, K, h->ldk))) return rc;
+    if ((rc = make_tmap(h, &h->mapB2, h->B2, K, K, h->ldk))) return rc;
+  }
   if ((rc = build_static_lists(h))) return rc;
   if ((rc = alloc_chunk_buffers(h))) return rc;
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -513,7 +654,7 @@ int scfgp_set_stream(scfgp_handle* h, void* cuda_stream) {
 int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
   if (!h || rows < 128 || rows % 128 != 0) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaDeviceSynchronize());
   h->R = rows;
   return alloc_chunk_buffers(h);
 }
@@ -568,29 +709,34 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   const size_t KK = (size_t)K * h->ldk;
   int rc;
   CK(cudaEventRecord(h->ev[0], h->stream));
-  CK(cudaMemsetAsync(h->red1, 0, (KK + K + 1) * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->colpart, 0, (size_t)kColSplit * K * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->slots, 0, 1024 * sizeof(double), h->stream));
   double* G = h->red1;
   double* p = h->red1 + KK;
   double* yy = p + K;
-  for (long long r0 = 0; r0 < h->N; r0 += h->R) {
+  if ((rc = fork_streams(h))) return rc;
+  for (int i = 0; i < h->ns; ++i) {
+    Ctx& c = h->ctx[i];
+    CK(cudaMemsetAsync(c.acc, 0, KK * sizeof(double), c.st));
+    CK(cudaMemsetAsync(c.colpart, 0, (size_t)kColSplit * K * sizeof(double), c.st));
+  }
+  long long ci = 0;
+  for (long long r0 = 0; r0 < h->N; r0 += h->R, ++ci) {
+    Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
-    if ((rc = run_features(h, h->dX + r0 * h->D, rows, nullptr, nullptr))) return rc;
-    prof_begin(h, SCFGP_FAM_SYRK);
-    rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PhiS, h->ldk, K, h->PhiS, h->ldk, K, G, h->ldk, 1.0, 1.0,
-                                                 h->lowerK, rows);
-    prof_end(h, SCFGP_FAM_SYRK);
-    if (rc) return rc;
-    k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->dy + r0,
-                                                                    h->colpart, K);
+    if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
+    if ((rc = run_syrk(h, c, false, rows))) return rc;
+    k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->dy + r0, c.colpart, K);
     CKL();
   }
-  k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart, K, kColSplit, K, p);
-  CKL();
+  // yy on the main stream while the chunk streams drain
+  CK(cudaMemsetAsync(h->slots, 0, 256 * sizeof(double), h->stream));
   k_sumsq_part<<<256, 256, 0, h->stream>>>(h->dy, h->N, h->slots);
   CKL();
   k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots, 256, 1, 1, yy);
+  CKL();
+  if ((rc = join_streams(h))) return rc;
+  k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns, (int)KK, G);
+  CKL();
+  k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, K, p);
   CKL();
   CK(cudaEventRecord(h->ev[1], h->stream));
   return SCFGP_OK;
@@ -649,37 +795,45 @@ int scfgp_eval_pass2(scfgp_handle* h) {
   const size_t KK = (size_t)K * h->ldk;
   int rc;
   CK(cudaEventRecord(h->ev[2], h->stream));
-  CK(cudaMemsetAsync(h->red2, 0, (KK + K + 2) * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->colpart, 0, (size_t)kColSplit * K * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->slots, 0, 2 * kSeedBlocks * sizeof(double), h->stream));
   double* H = h->red2;
   double* q = h->red2 + KK;
   double* Eg = q + K;
   const int nkb = cdiv(K, 128);
-  for (long long r0 = 0; r0 < h->N; r0 += h->R) {
+  if ((rc = fork_streams(h))) return rc;
+  for (int i = 0; i < h->ns; ++i) {
+    Ctx& c = h->ctx[i];
+    if (h->want_grad) {
+      CK(cudaMemsetAsync(c.acc, 0, KK * sizeof(double), c.st));
+      CK(cudaMemsetAsync(c.colpart, 0, (size_t)kColSplit * K * sizeof(double), c.st));
+    }
+    CK(cudaMemsetAsync(c.slots, 0, (size_t)h->slot_stride * sizeof(double), c.st));
+  }
+  long long ci = 0;
+  for (long long r0 = 0; r0 < h->N; r0 += h->R, ++ci) {
+    Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
-    if ((rc = run_features(h, h->dX + r0 * h->D, rows, nullptr, nullptr))) return rc;
-    if ((rc = run_tgemm(h, rows))) return rc;
-    k_seeds<<<kSeedBlocks, 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->alpha, h->vpart, h->R, nkb,
-                                               h->dy + r0, h->tau, h->gmu + r0, h->gv + r0, h->PsiS, h->slots,
-                                               h->want_grad);
+    if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
+    if ((rc = run_tgemm(h, c, rows))) return rc;
+    k_seeds<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->dy + r0,
+                                          h->tau, h->gmu + r0, h->gv + r0, c.Psi, c.slots, h->want_grad);
     CKL();
     if (h->want_grad) {
-      prof_begin(h, SCFGP_FAM_SYRK);
-      rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->PsiS, h->ldk, K, h->PhiS, h->ldk, K, H, h->ldk, 1.0, 1.0,
-                                                   h->lowerK, rows);
-      prof_end(h, SCFGP_FAM_SYRK);
-      if (rc) return rc;
-      k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->gmu + r0,
-                                                                      h->colpart, K);
+      if ((rc = run_syrk(h, c, true, rows))) return rc;
+      k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
       CKL();
     }
   }
+  if ((rc = join_streams(h))) return rc;
   if (h->want_grad) {
-    k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart, K, kColSplit, K, q);
+    k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns, (int)KK, H);
     CKL();
+    k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, K, q);
+    CKL();
+  } else {
+    CK(cudaMemsetAsync(h->red2, 0, (KK + K) * sizeof(double), h->stream));
   }
-  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots, kSeedBlocks, 2, 2, Eg);
+  // slots are [ns][slot_stride] with (E, g_tau) pairs in the first 2*kSeedBlocks entries of each
+  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots_all, (int)(h->slot_stride / 2) * h->ns, 2, 2, Eg);
   CKL();
   CK(cudaEventRecord(h->ev[3], h->stream));
   return SCFGP_OK;
@@ -720,41 +874,56 @@ int scfgp_eval_pass3(scfgp_handle* h) {
   const int K = h->K, J = h->J, D = h->D;
   int rc;
   CK(cudaEventRecord(h->ev[4], h->stream));
-  const size_t n3 = (size_t)D * h->ldj + h->ldj + 1;
-  CK(cudaMemsetAsync(h->red3, 0, n3 * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->colpart, 0, (size_t)kColSplit * K * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->slots, 0, (size_t)(h->bwd.count + 1) * sizeof(double), h->stream));
+  const size_t DJ = (size_t)D * h->ldj;
   double* dW = h->red3;
-  double* dphi = dW + (size_t)D * h->ldj;
+  double* dphi = dW + DJ;
   double* sbar = dphi + h->ldj;
   const size_t smem = SmemSize<CfgBig, true, true>::BYTES;
   const int nfb = cdiv(J, 64);
-  for (long long r0 = 0; r0 < h->N; r0 += h->R) {
+  CK(cudaMemsetAsync(h->red3, 0, (DJ + h->ldj + 1) * sizeof(double), h->stream));
+  if ((rc = fork_streams(h))) return rc;
+  for (int i = 0; i < h->ns; ++i) {
+    Ctx& c = h->ctx[i];
+    CK(cudaMemsetAsync(c.dW, 0, DJ * sizeof(double), c.st));
+    CK(cudaMemsetAsync(c.colpart, 0, (size_t)kColSplit * K * sizeof(double), c.st));
+    CK(cudaMemsetAsync(c.slots, 0, (size_t)h->slot_stride * sizeof(double), c.st));
+  }
+  long long ci = 0;
+  for (long long r0 = 0; r0 < h->N; r0 += h->R, ++ci) {
+    Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
     const double* Xc = h->dX + r0 * D;
-    if ((rc = run_features(h, Xc, rows, h->gv + r0, h->PsiS))) return rc;
+    if ((rc = run_features(h, c, Xc, h->xvec, rows, h->gv + r0, c.Psi))) return rc;
     const int nitems = cdiv(rows, 128) * nfb;  // items are rb-major
-    prof_begin(h, SCFGP_FAM_BACKWARD);
-    k_backward<<<nitems, CfgBig::NT, smem, h->stream>>>(h->PhiS, h->PsiS, h->ldk, rows, K, J, h->A2, h->B2,
-                                                        h->ldk, h->dy + r0, h->gmu + r0, h->pbar, h->alpha,
-                                                        h->Zbar, h->ldj, h->slots, h->bwd.d);
-    prof_end(h, SCFGP_FAM_BACKWARD);
+    prof_begin(h, SCFGP_FAM_BACKWARD, c.st);
+    if (h->use_tma)
+      k_backward_tma<<<nitems, TMA_THREADS, TMA_SMEM_BYTES, c.st>>>(c.mapPhi, c.mapPsi, h->mapA2, h->mapB2, c.Phi,
+                                                                    h->ldk, rows, K, J, h->dy + r0, h->gmu + r0,
+                                                                    h->pbar, h->alpha, c.Zbar, h->ldj, c.slots,
+                                                                    h->bwd.d);
+    else
+      k_backward<<<nitems, CfgBig::NT, smem, c.st>>>(c.Phi, c.Psi, h->ldk, rows, K, J, h->A2, h->B2, h->ldk,
+                                                     h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj,
+                                                     c.slots, h->bwd.d);
+    prof_end(h, SCFGP_FAM_BACKWARD, c.st);
     CKL();
     // dW += XcT . Zbar
     if (h->xvec == 2)
-      rc = launch_gemm<CfgWide, false, false, 2, 2>(h, Xc, D, D, h->Zbar, h->ldj, J, dW, h->ldj, 1.0, 1.0,
-                                                    h->dw, rows);
+      rc = launch_gemm<CfgWide, false, false, 2, 2>(h, Xc, D, D, c.Zbar, h->ldj, J, c.dW, h->ldj, 1.0, 1.0, h->dw,
+                                                    rows, c.st, true);
     else
-      rc = launch_gemm<CfgWide, false, false, 1, 2>(h, Xc, D, D, h->Zbar, h->ldj, J, dW, h->ldj, 1.0, 1.0,
-                                                    h->dw, rows);
+      rc = launch_gemm<CfgWide, false, false, 1, 2>(h, Xc, D, D, c.Zbar, h->ldj, J, c.dW, h->ldj, 1.0, 1.0, h->dw,
+                                                    rows, c.st, true);
     if (rc) return rc;
-    k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, h->stream>>>(h->Zbar, h->ldj, rows, J, nullptr,
-                                                                    h->colpart, K);
+    k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, J, nullptr, c.colpart, K);
     CKL();
   }
-  k_sum_parts<<<cdiv(J, 256), 256, 0, h->stream>>>(h->colpart, K, kColSplit, J, dphi);
+  if ((rc = join_streams(h))) return rc;
+  k_sum_parts<<<cdiv((long long)DJ, 256), 256, 0, h->stream>>>(h->dW_all, (long long)DJ, h->ns, (int)DJ, dW);
   CKL();
-  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots, h->bwd.count, 1, 1, sbar);
+  k_sum_parts<<<cdiv(J, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, J, dphi);
+  CKL();
+  k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots_all, (int)h->slot_stride * h->ns, 1, 1, sbar);
   CKL();
   CK(cudaEventRecord(h->ev[5], h->stream));
   return SCFGP_OK;
@@ -909,19 +1078,19 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
   if ((rc = unpack_and_upload(h, params))) return rc;
   const int K = h->K;
   const int nkb = cdiv(K, 128);
-  const int save_xvec = h->xvec;
-  h->xvec = (((uintptr_t)dXs % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
-  for (long long r0 = 0; r0 < T; r0 += h->R) {
+  const int xvec = (((uintptr_t)dXs % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
+  if ((rc = fork_streams(h))) return rc;
+  long long ci = 0;
+  for (long long r0 = 0; r0 < T; r0 += h->R, ++ci) {
+    Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, T - r0);
-    if ((rc = run_features(h, dXs + r0 * h->D, rows, nullptr, nullptr))) { h->xvec = save_xvec; return rc; }
-    if ((rc = run_tgemm(h, rows))) { h->xvec = save_xvec; return rc; }
-    k_pred_finish<<<kSeedBlocks, 256, 0, h->stream>>>(h->PhiS, h->ldk, rows, K, h->alpha, h->vpart, h->R, nkb,
-                                                     h->tau, dmu + r0, dstd + r0);
-    h->launches++;
+    if ((rc = run_features(h, c, dXs + r0 * h->D, xvec, rows, nullptr, nullptr))) return rc;
+    if ((rc = run_tgemm(h, c, rows))) return rc;
+    k_pred_finish<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->tau,
+                                                dmu + r0, dstd + r0);
+    CKL();
   }
-  h->xvec = save_xvec;
-  CK(cudaGetLastError());
-  return SCFGP_OK;
+  return join_streams(h);
 }
 
 int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long long T, const double* alpha,
@@ -957,7 +1126,10 @@ int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long 
 // self-test hooks
 // ---------------------------------------------------------------------------------
 int scfgp_dbg_gemm(int device, int layout, int m, int n, int k, const double* A, const double* B, double* C) {
-  if (m <= 0 || n <= 0 || k <= 0 || !A || !B || !C || layout < 0 || layout > 2) return SCFGP_ERR_ARG;
+  const bool tma = layout >= 10;
+  if (tma) layout -= 10;
+  if (m <= 0 || n <= 0 || k <= 0 || !A || !B || !C || layout < 0 || layout > 2 || (tma && layout == 2))
+    return SCFGP_ERR_ARG;
   scfgp_handle tmp;
   scfgp_handle* h = &tmp;
   h->device = device;
@@ -983,7 +1155,21 @@ int scfgp_dbg_gemm(int device, int layout, int m, int n, int k, const double* A,
     for (int j = 0; j < cdiv(n, 128); ++j) v.push_back(make_int4(i, j, 0, -1));
   ItemList il;
   int rc = upload_items(h, v, &il);
-  if (!rc) {
+  if (!rc && tma) {
+    CUtensorMap ta, tb;
+    rc = make_tmap(h, &ta, dA, acols, arows_store, lda);
+    if (!rc) rc = make_tmap(h, &tb, dB, bcols, brows_store, ldb);
+    if (!rc) {
+      dim3 grid(cdiv(n, 128), cdiv(m, 128));
+      if (layout == 0) {
+        cudaFuncSetAttribute(k_gemm_tma_dbg<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES);
+        k_gemm_tma_dbg<true, true><<<grid, TMA_THREADS, TMA_SMEM_BYTES>>>(ta, tb, k, m, n, dC, ldc);
+      } else {
+        cudaFuncSetAttribute(k_gemm_tma_dbg<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES);
+        k_gemm_tma_dbg<false, false><<<grid, TMA_THREADS, TMA_SMEM_BYTES>>>(ta, tb, k, m, n, dC, ldc);
+      }
+    }
+  } else if (!rc) {
     if (layout == 0) rc = launch_gemm<CfgBig, true, true, 2, 2>(h, dA, lda, m, dB, ldb, n, dC, ldc, 1.0, 0.0, il, k);
     else if (layout == 1) rc = launch_gemm<CfgBig, false, false, 2, 2>(h, dA, lda, m, dB, ldb, n, dC, ldc, 1.0, 0.0, il, k);
     else rc = launch_gemm<CfgBig, true, false, 2, 2>(h, dA, lda, m, dB, ldb, n, dC, ldc, 1.0, 0.0, il, k);
@@ -1025,20 +1211,19 @@ int scfgp_dbg_features(scfgp_handle* h, const double* params, const double* X, l
   double* dXs = nullptr;
   CK(cudaMalloc((void**)&dXs, (size_t)N * h->D * sizeof(double)));
   CK(cudaMemcpy(dXs, X, (size_t)N * h->D * sizeof(double), cudaMemcpyHostToDevice));
-  const int save_xvec = h->xvec;
-  h->xvec = (h->D % 2 == 0) ? 2 : 1;
+  const int xvec = (h->D % 2 == 0) ? 2 : 1;
+  Ctx& c = h->ctx[0];
   for (long long r0 = 0; r0 < N && !rc; r0 += h->R) {
     const int rows = (int)std::min<long long>(h->R, N - r0);
-    rc = run_features(h, dXs + r0 * h->D, rows, nullptr, nullptr);
+    rc = run_features(h, c, dXs + r0 * h->D, xvec, rows, nullptr, nullptr);
     if (!rc) {
-      cudaError_t e = cudaMemcpy2DAsync(Phi + r0 * h->K, (size_t)h->K * sizeof(double), h->PhiS,
+      cudaError_t e = cudaMemcpy2DAsync(Phi + r0 * h->K, (size_t)h->K * sizeof(double), c.Phi,
                                         h->ldk * sizeof(double), (size_t)h->K * sizeof(double), rows,
-                                        cudaMemcpyDeviceToHost, h->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+                                        cudaMemcpyDeviceToHost, c.st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
       if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = SCFGP_ERR_CUDA; }
     }
   }
-  h->xvec = save_xvec;
   cudaFree(dXs);
   return rc;
 }

@@ -229,9 +229,9 @@ class Engine:
 def dbg_gemm(layout: int, A, B, device: int = 0):
     lib = _lib.load()
     A, B = _lib.as_f64(A), _lib.as_f64(B)
-    if layout == 0:
+    if layout % 10 == 0:
         m, k = A.shape; n = B.shape[0]
-    elif layout == 1:
+    elif layout % 10 == 1:
         k, m = A.shape; n = B.shape[1]
     else:
         m, k = A.shape; n = B.shape[1]
