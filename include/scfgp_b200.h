@@ -69,7 +69,7 @@ long long scfgp_num_features(const scfgp_handle* h);
 /* Run all work of this handle on `cuda_stream` (a cudaStream_t; NULL = default). */
 int scfgp_set_stream(scfgp_handle* h, void* cuda_stream);
 
-/* Rows per streamed chunk (multiple of 128; default 2048).  Tuning knob only. */
+/* Rows per streamed chunk (multiple of 128; default 4096).  Tuning knob only. */
 int scfgp_set_chunk_rows(scfgp_handle* h, int rows);
 
 /* Training data of train_func/train_iter_func (the X, y arguments at

@@ -89,11 +89,16 @@ struct BoxRows {
   int row0[8];
 };
 
-// Producer side: fill one stage (TMA_KSUB k16 sub-steps of A and B).
+// Producer side: fill one stage (TMA_KSUB k16 sub-steps of A and B).  Only the first
+// `nbox_b` boxes (16 rows each) of the B tile are fetched: narrow tiles (NW < 4) need fewer.
+__device__ __forceinline__ uint32_t tma_stage_tx_bytes(int nbox_b) {
+  return (uint32_t)(TMA_KSUB * (TMA_TILE_BYTES + nbox_b * TMA_BOX_BYTES));
+}
 template <bool AK, bool BKM>
 __device__ __forceinline__ void tma_issue_stage(uint8_t* stage, const CUtensorMap* mapA, const BoxRows& ra,
-                                                const CUtensorMap* mapB, const BoxRows& rb, int k0, uint64_t* full) {
-  mbar_arrive_expect_tx(full, TMA_STAGE_BYTES);
+                                                const CUtensorMap* mapB, const BoxRows& rb, int nbox_b, int k0,
+                                                uint64_t* full) {
+  mbar_arrive_expect_tx(full, tma_stage_tx_bytes(nbox_b));
 #pragma unroll
   for (int sub = 0; sub < TMA_KSUB; ++sub) {
     uint8_t* a = stage + sub * 2 * TMA_TILE_BYTES;
@@ -106,32 +111,37 @@ __device__ __forceinline__ void tma_issue_stage(uint8_t* stage, const CUtensorMa
     }
 #pragma unroll
     for (int bx = 0; bx < 8; ++bx) {
-      if (BKM) tma_load_2d(b + bx * TMA_BOX_BYTES, mapB, k, rb.row0[bx], full);
-      else tma_load_2d(b + bx * TMA_BOX_BYTES, mapB, rb.row0[bx], k, full);
+      if (bx < nbox_b) {
+        if (BKM) tma_load_2d(b + bx * TMA_BOX_BYTES, mapB, k, rb.row0[bx], full);
+        else tma_load_2d(b + bx * TMA_BOX_BYTES, mapB, rb.row0[bx], k, full);
+      }
     }
   }
 }
 
-// Consumer side: 4 k4-steps over one 128x16 A tile and one 128x16 B tile.
-//   warp tile 64 x 32 (MI = 8, NI = 4), same accumulator layout as gemm_dmma.cuh except
-//   for the pi() row permutation of K-major operands (see tma_row / tma_col below).
-template <bool AK, bool BKM>
-__device__ __forceinline__ void tma_compute_k16(double (&acc)[8][4][2], const uint8_t* At, const uint8_t* Bt,
+// Consumer side: 4 k4-steps over one 128x16 A tile and one (32 NW)x16 B tile.
+//   NW = number of 32-column warp columns that hold valid output: the 8 consumer warps
+//   form an (8/NW) x NW grid with warp tiles (16 NW) x 32, so a narrow border tile
+//   (NW = 1 or 2) keeps all eight warps busy on a quarter / half of the work.
+//   acc[i][j][e]: row = wm0 + 8i + (pi8(g) | g), col = wn0 + 8j + (pi8(2t+e) | 2t+e).
+template <bool AK, bool BKM, int NW>
+__device__ __forceinline__ void tma_compute_k16(double (&acc)[2 * NW][4][2], const uint8_t* At, const uint8_t* Bt,
                                                 int wm0, int wn0, int g, int t) {
+  constexpr int MI = 2 * NW;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    double a[8], b[4];
+    double a[MI], b[4];
     if (AK) {
       const int x = ((((2 * kk + (t >> 1)) ^ pi8(g)) << 4) + ((t & 1) << 3));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < MI; ++i) {
         const int r = wm0 + 8 * i;  // multiple of 8
         a[i] = *reinterpret_cast<const double*>(At + (r >> 4) * TMA_BOX_BYTES + (((r & 15) + pi8(g)) << 7) + x);
       }
     } else {
       const int kr = 8 * (kk >> 1) + 2 * t + (kk & 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < MI; ++i) {
         const int m = wm0 + 8 * i + g;
         a[i] = *reinterpret_cast<const double*>(At + (m >> 4) * TMA_BOX_BYTES + (kr << 7) +
                                                  ((((m & 15) >> 1) ^ (kr & 7)) << 4) + ((m & 1) << 3));
@@ -154,7 +164,7 @@ __device__ __forceinline__ void tma_compute_k16(double (&acc)[8][4][2], const ui
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
@@ -206,7 +216,7 @@ __device__ __forceinline__ int tma_total_iters(int nseg, const int* depth) {
 template <bool AK, bool BKM>
 __device__ __forceinline__ void tma_producer(const TmaPipe& pipe, int nseg, const CUtensorMap* const* mapA,
                                              const CUtensorMap* const* mapB, const BoxRows& ra, const BoxRows& rb,
-                                             const int* depth) {
+                                             int nbox_b, const int* depth) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(TMA_PRODUCER_REGS));
   if ((threadIdx.x >> 5) != TMA_CONSUMER_WARPS || (threadIdx.x & 31) != 0) return;
   constexpr int KSTAGE = 16 * TMA_KSUB;
@@ -218,7 +228,7 @@ __device__ __forceinline__ void tma_producer(const TmaPipe& pipe, int nseg, cons
     mbar_wait(&pipe.empty[st], (use & 1) ^ 1);
     const int seg = it < nk0 ? 0 : 1;
     const int k0 = (seg == 0 ? it : it - nk0) * KSTAGE;
-    tma_issue_stage<AK, BKM>(pipe.stages + (size_t)st * TMA_STAGE_BYTES, mapA[seg], ra, mapB[seg], rb, k0,
+    tma_issue_stage<AK, BKM>(pipe.stages + (size_t)st * TMA_STAGE_BYTES, mapA[seg], ra, mapB[seg], rb, nbox_b, k0,
                              &pipe.full[st]);
   }
 }
@@ -228,11 +238,11 @@ __device__ __forceinline__ void tma_producer(const TmaPipe& pipe, int nseg, cons
 __device__ __forceinline__ void tma_consumer_regs() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(TMA_CONSUMER_REGS));
 }
-template <bool AK, bool BKM>
-__device__ __forceinline__ void tma_consumer(double (&acc)[8][4][2], const TmaPipe& pipe, int total) {
+template <bool AK, bool BKM, int NW>
+__device__ __forceinline__ void tma_consumer(double (&acc)[2 * NW][4][2], const TmaPipe& pipe, int total) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wm0 = (warp / NW) * (16 * NW), wn0 = (warp % NW) * 32;
   for (int it = 0; it < total; ++it) {
     const int st = it % TMA_STAGES;
     const uint32_t use = it / TMA_STAGES;
@@ -240,12 +250,14 @@ __device__ __forceinline__ void tma_consumer(double (&acc)[8][4][2], const TmaPi
     const uint8_t* stage = pipe.stages + (size_t)st * TMA_STAGE_BYTES;
 #pragma unroll
     for (int sub = 0; sub < TMA_KSUB; ++sub)
-      tma_compute_k16<AK, BKM>(acc, stage + sub * 2 * TMA_TILE_BYTES, stage + sub * 2 * TMA_TILE_BYTES + TMA_TILE_BYTES,
-                               wm0, wn0, g, t);
+      tma_compute_k16<AK, BKM, NW>(acc, stage + sub * 2 * TMA_TILE_BYTES,
+                                   stage + sub * 2 * TMA_TILE_BYTES + TMA_TILE_BYTES, wm0, wn0, g, t);
     __syncwarp();
     if (lane == 0) mbar_arrive(&pipe.empty[st]);
   }
 }
+// NW for a tile with `valid` useful columns (of 128)
+__device__ __forceinline__ int tma_nw(int valid) { return valid <= 32 ? 1 : (valid <= 64 ? 2 : 4); }
 // barrier among the 256 consumer threads only (the producer warpgroup has left)
 __device__ __forceinline__ void tma_consumer_sync() {
   asm volatile("bar.sync 1, %0;\n" ::"n"(TMA_CONSUMER_WARPS * 32) : "memory");

@@ -9,7 +9,8 @@ namespace scfgp {
 // tile shapes
 // ------------------------------------------------------------------------------------
 using CfgBig = TileCfg<128, 128, 64, 32, 3>;   // 8 warps, 64 accumulators / thread
-using CfgTall = TileCfg<128, 64, 32, 32, 3>;   // 8 warps, features / panels
+using CfgTall = TileCfg<128, 64, 32, 32, 3>;   // 8 warps, panels
+using CfgFeat = TileCfg<128, 64, 32, 32, 2>;   // 8 warps, feature map: 2 stages, 2 CTAs / SM
 using CfgWide = TileCfg<64, 128, 32, 32, 3>;   // 8 warps, D x J contraction
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -72,12 +73,12 @@ k_gemm(const double* __restrict__ A, long long lda, int a_rows,
 //   grid = rowblocks(128) * featblocks(64)
 // ------------------------------------------------------------------------------------
 template <int XVEC>
-__global__ void __launch_bounds__(CfgTall::NT, 1)
+__global__ void __launch_bounds__(CfgFeat::NT, 2)
 k_features(const double* __restrict__ X, long long ldx, int rows, int D,
            const double* __restrict__ Wt, long long ldw, const double* __restrict__ phi,
            int J, double s, double* __restrict__ Phi, long long ldp,
            const double* __restrict__ rowscale, double* __restrict__ Psi, int nfb) {
-  using Cfg = CfgTall;
+  using Cfg = CfgFeat;
   extern __shared__ __align__(16) double smem[];
   const int rb = blockIdx.x / nfb, fb = blockIdx.x % nfb;
   const int m0 = rb * Cfg::BM, n0 = fb * Cfg::BN;

@@ -19,7 +19,7 @@ using namespace scfgp;
 namespace {
 
 constexpr double kEps = 1e-6;  // jitter, SCFGP/SCFGP.py:93
-constexpr int kColSplit = 8;   // row splits of the column-sum kernels
+constexpr int kColSplit = 64;  // row splits of the column-sum kernels (parallelism: ceil(K/256) x 64 CTAs)
 constexpr int kSeedBlocks = 296;
 
 struct ItemList {
@@ -50,7 +50,7 @@ struct scfgp_handle {
   const double* dy = nullptr;
   double* ownX = nullptr;
   double* owny = nullptr;
-  int R = 2048;  // rows per chunk
+  int R = 4096;  // rows per chunk
   int xvec = 2;
   long long ldk = 0;  // leading dimension of K x K matrices and slabs
   long long ldj = 0;  // leading dimension of D x J / Zbar
@@ -62,7 +62,7 @@ struct scfgp_handle {
   // of one chunk's kernels overlaps the head of the next; each context owns its slabs and
   // partial accumulators (deterministic: chunk c always lands in context c % ns)
   Ctx ctx[kMaxStreams];
-  int ns = 3;
+  int ns = 4;
   cudaEvent_t ev_fork = nullptr;
   double *acc_all = nullptr, *dW_all = nullptr, *colpart_all = nullptr, *slots_all = nullptr;
   long long slot_stride = 0;
@@ -79,7 +79,7 @@ struct scfgp_handle {
   int nrb_cap = 0;
 
   // work lists
-  ItemList lowerK, fullK, tgemm, bwd, dw;
+  ItemList lowerK, syrkK, fullK, tgemm, bwd, dw;
   std::vector<ItemList> potrf_panel, potrf_trail, trtri_s, trtri_x;
   std::vector<int4*> to_free;
 
@@ -228,9 +228,9 @@ int launch_gemm(scfgp_handle* h, const double* A, long long lda, int a_rows, con
 
 int set_kernel_attrs(scfgp_handle* h) {
   CK(cudaFuncSetAttribute(k_features<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SmemSize<CfgTall, true, true>::BYTES));
+                          (int)SmemSize<CfgFeat, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_features<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SmemSize<CfgTall, true, true>::BYTES));
+                          (int)SmemSize<CfgFeat, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_tgemm_rowsq, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SmemSize<CfgBig, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -323,8 +323,18 @@ int alloc_chunk_buffers(scfgp_handle* h) {
   // work lists that depend on R
   const int nrb = R / 128;
   std::vector<int4> tg, bw;
-  for (int kb = nkb - 1; kb >= 0; --kb)  // deepest reductions first
-    for (int rb = 0; rb < nrb; ++rb) tg.push_back(make_int4(rb, kb, 0, 0));
+  {
+    // most expensive first: cost = reduction depth x (fraction of the tile that is valid)
+    std::vector<std::pair<double, int>> order;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int valid = std::min(128, K - kb * 128);
+      const double frac = !h->use_tma ? 1.0 : (valid <= 32 ? 0.25 : (valid <= 64 ? 0.5 : 1.0));
+      order.push_back({-frac * std::min(K, (kb + 1) * 128), kb});
+    }
+    std::sort(order.begin(), order.end());
+    for (auto& o : order)
+      for (int rb = 0; rb < nrb; ++rb) tg.push_back(make_int4(rb, o.second, 0, 0));
+  }
   const int nfb = cdiv(h->J, 64);
   for (int rb = 0; rb < nrb; ++rb)
     for (int fb = 0; fb < nfb; ++fb) bw.push_back(make_int4(rb, fb, 0, 0));
@@ -382,8 +392,8 @@ int run_syrk(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
       if (a_is_psi)
         CK(cudaMemsetAsync(c.Psi + (size_t)rows * h->ldk, 0, (size_t)(pad - rows) * h->ldk * sizeof(double), c.st));
     }
-    k_syrk_tma<<<h->lowerK.count, TMA_THREADS, TMA_SMEM_BYTES, c.st>>>(a_is_psi ? c.mapPsi : c.mapPhi, c.mapPhi, rows,
-                                                                       K, K, c.acc, h->ldk, h->lowerK.d);
+    k_syrk_tma<<<h->syrkK.count, TMA_THREADS, TMA_SMEM_BYTES, c.st>>>(a_is_psi ? c.mapPsi : c.mapPhi, c.mapPhi, rows,
+                                                                      K, K, c.acc, h->ldk, h->syrkK.d);
     h->launches++;
     cudaError_t e_ = cudaGetLastError();
     if (e_ != cudaSuccess) { h->err = std::string("k_syrk_tma: ") + cudaGetErrorString(e_); rc = SCFGP_ERR_CUDA; }
@@ -399,13 +409,13 @@ int run_features(scfgp_handle* h, Ctx& c, const double* Xc, int xvec, int rows, 
                  double* Psi) {
   const int nfb = cdiv(h->J, 64);
   const int nrb = cdiv(rows, 128);
-  const size_t smem = SmemSize<CfgTall, true, true>::BYTES;
+  const size_t smem = SmemSize<CfgFeat, true, true>::BYTES;
   prof_begin(h, SCFGP_FAM_FEATURES, c.st);
   if (xvec == 2)
-    k_features<2><<<nrb * nfb, CfgTall::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
+    k_features<2><<<nrb * nfb, CfgFeat::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
                                                           h->s, c.Phi, h->ldk, rowscale, Psi, nfb);
   else
-    k_features<1><<<nrb * nfb, CfgTall::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
+    k_features<1><<<nrb * nfb, CfgFeat::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
                                                           h->s, c.Phi, h->ldk, rowscale, Psi, nfb);
   prof_end(h, SCFGP_FAM_FEATURES, c.st);
   CKL();
@@ -476,6 +486,17 @@ int build_static_lists(scfgp_handle* h) {
   const int K = h->K;
   int rc;
   if ((rc = upload_items(h, lower_tiles(K, 128, 0, -1), &h->lowerK))) return rc;
+  {
+    // TMA Gram kernel: full lower tiles first, then the K mod 128 border row block with the
+    // operand roles swapped (narrow side = n side) and a transposed store
+    std::vector<int4> v;
+    const int B = K / 128, border = K % 128;
+    for (int i = 0; i < B; ++i)
+      for (int j = 0; j <= i; ++j) v.push_back(make_int4(i, j, 0, 0));
+    if (border)
+      for (int j = 0; j <= B; ++j) v.push_back(make_int4(j, B, 1, 0));
+    if ((rc = upload_items(h, v, &h->syrkK))) return rc;
+  }
   {
     std::vector<int4> v;
     int nb = cdiv(K, 128);

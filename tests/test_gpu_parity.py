@@ -62,7 +62,7 @@ def test_dmma_gemm_layouts(layout, mnk):
 
 
 @pytest.mark.parametrize("mnk", [(128, 128, 32), (128, 128, 2080), (130, 70, 34), (300, 260, 200), (256, 384, 1000),
-                                 (2, 2, 2)])
+                                 (2, 2, 2), (200, 160, 100), (140, 192, 70), (128, 33, 64), (64, 64, 64)])
 @pytest.mark.parametrize("layout", [10, 11])
 def test_tma_dmma_gemm(layout, mnk):
     """The TMA/mbarrier pipeline (128-byte swizzled 16x16 boxes, producer warpgroup): NT and TN."""
