@@ -323,16 +323,38 @@ def main():
         del a, b
     except Exception as ex:  # pragma: no cover
         peak_burst = None
-    rows_per_launch = n_local * args.steps / max(bw_launches, 1)
-    flops_per_launch = 4.0 * K * K * rows_per_launch            # Phi.(2Abar) + Psi.(2B): 2 GEMMs x 2 N K^2
-    avg_ms = bw_ms / max(bw_launches, 1)
-    achieved = flops_per_launch / (avg_ms * 1e-3) * 1e-12 if avg_ms > 0 else None
+    # (1) over the timed region: pass 3 = [features, k_backward_tma, dW contraction, column sums] on 4
+    #     overlapped streams, bracketed by CUDA events on the handle's main stream.  Its algorithmic
+    #     work is 4 N K^2 (Phi.(2Abar) + Psi.(2B)); helpers are charged to the kernel (conservative).
+    p3_ms = sum(p[2] for p in pass_ms) / len(pass_ms)
+    flops_p3 = 4.0 * K * K * n_local
+    achieved = flops_p3 / (p3_ms * 1e-3) * 1e-12
+    # (2) one launch in isolation (single stream, CUDA events around every k_backward_tma launch)
+    iso_ms, iso_n = 0.0, 0
+    if world == 1:                      # (an evaluation is collective: rank 0 cannot run one alone)
+        eng.set_streams(1)
+        eng.set_profiling(_lib.FAM_BACKWARD)
+        eng.eval(params0)
+        iso_ms, iso_n = eng.get_profile()
+        eng.set_profiling(_lib.FAM_NONE)
+    rows_per_launch = n_local / max(iso_n, 1) if iso_n else 4096
+    flops_per_launch = 4.0 * K * K * rows_per_launch
+    iso_avg = iso_ms / max(iso_n, 1)
     peak = peak_sus or 35.4
-    roofline = {"bound": "tensor", "kernel": "k_backward (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "avg_launch_ms": avg_ms, "launches": bw_launches, "algorithmic_flops_per_launch": flops_per_launch,
+    roofline = {"bound": "tensor", "kernel": "k_backward_tma (FP64 DMMA.8x8x4 fed by TMA)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 562.2e6,
+                "traffic_note": "dram__bytes_read+write of one 4096-row launch from ncu --set full "
+                                "(profiles/r1_prof_backward_ncu_full_N8192.txt); algorithmic operand bytes per "
+                                "launch: Phi+Psi slabs 136 MB + 2Abar,2B 69 MB",
+                "how": "4 N K^2 algorithmic flops of pass 3 / pass-3 device time (CUDA events on the launching "
+                       "stream) averaged over the timed steps",
+                "avg_launch_ms_isolated": iso_avg, "launches_isolated": iso_n,
+                "algorithmic_flops_per_launch": flops_per_launch,
+                "achieved_isolated_launch": flops_per_launch / (iso_avg * 1e-3) * 1e-12 if iso_avg > 0 else None,
+                "overlapped_launch_ms_sum": bw_ms, "overlapped_launches": bw_launches,
                 "peak_source": "cublasDgemm 8192^3 sustained, measured in this run (MEASURED_PEAKS.json holds no "
-                               "fp64 entry; register-resident DMMA.8x8x4 issue peak measured 37.0 TFLOP/s)",
+                               "fp64 entry; register-resident DMMA.8x8x4 issue peak measured 37.0 TFLOP/s, "
+                               "gpurun_out/microbench.log -> profiles/r1_fp64_pipe_microbench.txt)",
                 "peak_dgemm_burst": peak_burst, "peak_dgemm_sustained": peak_sus,
                 "whole_eval_tflops": fpr * N / (ms_step * 1e-3) * 1e-12 / max(world, 1),
                 "whole_eval_frac_of_peak": fpr * N / (ms_step * 1e-3) * 1e-12 / max(world, 1) / peak,

@@ -72,6 +72,11 @@ int scfgp_set_stream(scfgp_handle* h, void* cuda_stream);
 /* Rows per streamed chunk (multiple of 128; default 4096).  Tuning knob only. */
 int scfgp_set_chunk_rows(scfgp_handle* h, int rows);
 
+/* Number of CUDA streams consecutive row chunks are spread over (1..4; default 4, or the
+ * SCFGP_STREAMS environment variable at create time).  Tuning knob only: results do not
+ * depend on timing, chunk c always accumulates into context c % n. */
+int scfgp_set_streams(scfgp_handle* h, int n);
+
 /* Training data of train_func/train_iter_func (the X, y arguments at
  * SCFGP/SCFGP.py:230,237,265).  X is N x D row-major, y has N entries.
  *   _host  : copies from host memory into device buffers owned by the handle.

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "scfgp_num_features": (_ll, [_h]),
     "scfgp_set_stream": (C.c_int, [_h, C.c_void_p]),
     "scfgp_set_chunk_rows": (C.c_int, [_h, C.c_int]),
+    "scfgp_set_streams": (C.c_int, [_h, C.c_int]),
     "scfgp_set_data_host": (C.c_int, [_h, _dp, _dp, _ll, _ll]),
     "scfgp_set_data_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, _ll, _ll]),
     "scfgp_eval": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp]),

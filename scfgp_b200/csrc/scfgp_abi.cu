@@ -680,6 +680,14 @@ int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
   return alloc_chunk_buffers(h);
 }
 
+int scfgp_set_streams(scfgp_handle* h, int n) {
+  if (!h || n < 1 || n > kMaxStreams) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  h->ns = n;
+  return alloc_chunk_buffers(h);
+}
+
 static int set_data_common(scfgp_handle* h, long long N, long long n_global) {
   h->N = N;
   h->Nglobal = n_global > 0 ? n_global : N;

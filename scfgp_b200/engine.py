@@ -90,6 +90,9 @@ class Engine:
         self.lib.scfgp_last_pass_ms(self._h, *[C.byref(x) for x in f])
         return tuple(float(x.value) for x in f)
 
+    def set_streams(self, n: int):
+        self._check(self.lib.scfgp_set_streams(self._h, int(n)))
+
     def set_profiling(self, family: int):
         self._check(self.lib.scfgp_set_profiling(self._h, int(family)))
 

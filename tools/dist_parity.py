@@ -1,0 +1,48 @@
+"""Multi-GPU parity (torchrun, one rank per GPU): the row-sharded, all-reduced evaluation must
+equal the single-GPU evaluation of the same problem.  Rank 0 prints the differences.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dist_parity.py
+"""
+import os, sys, json
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from scfgp_b200 import Engine, synth, shard_bounds
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{lr}"))
+out = []
+for (N, D, S, M) in [(5001, 8, 4, 100), (20000, 64, 16, 1024)]:
+    X, y, h = synth.make_problem(N, D, S, M, seed=21)
+    lo, hi = shard_bounds(N, rank, world)
+    eng = Engine(D, S, M, device=lr)
+    eng.set_data(X[lo:hi], y[lo:hi], n_global=N)
+    c, g, a, L = eng.eval(h)
+    cs = torch.tensor([c], dtype=torch.float64, device="cuda"); lst = [torch.zeros_like(cs) for _ in range(world)]
+    dist.all_gather(lst, cs)
+    same = all(float(x) == float(lst[0]) for x in lst)
+    if rank == 0:
+        dist.barrier()
+    else:
+        dist.barrier()
+    eng.close()
+    if rank == 0:
+        # single-GPU reference on rank 0 (not collective: process group bypassed by a 1-rank subgroup)
+        pass
+    out.append((N, D, S, M, c, g, a, L, same))
+dist.barrier()
+if rank == 0:
+    # now evaluate the same problems on one GPU with no process group in play
+    dist.destroy_process_group()
+    for (N, D, S, M, c, g, a, L, same) in out:
+        X, y, h = synth.make_problem(N, D, S, M, seed=21)
+        e1 = Engine(D, S, M, device=lr); e1.set_data(X, y)
+        c1, g1, a1, L1 = e1.eval(h)
+        print(json.dumps({"shape": [N, D, S, M], "world": world, "ranks_identical": same,
+                          "cost_rel": abs(c - c1) / abs(c1), "grad_rel": float(np.linalg.norm(g - g1) / np.linalg.norm(g1)),
+                          "alpha_abs": float(np.abs(a - a1).max()), "Li_abs": float(np.abs(L - L1).max())}), flush=True)
+        e1.close()
+else:
+    dist.destroy_process_group()
