@@ -1,0 +1,250 @@
+// Emulated-FP64 GEMM mainloop on the 5th-generation tensor cores (sm_100a):
+// tcgen05.mma.kind::i8 with int32 accumulators in tensor memory, operands staged by TMA.
+//
+// Number format ("slices").  A real matrix X with |X| <= scale is held as KS signed
+// base-128 digits  X ~= scale * 2^-(7 KS - 1) * sum_i d_i 128^(KS-1-i),  |d_i| <= 64  (int8).
+// A product  sum_c X[m,c] Y[n,c]  is then the integer sum
+//     sum_{i,j} 2^(-7(i+j)) * ( sum_c dX_i[m,c] dY_j[n,c] )   * scaleX scaleY 2^-12 ,
+// truncated to the "classes"  i + j = q < KS  (the dropped terms are below the digit
+// quantisation error).  Every class sum is an exact int32 (depth * (q+1) * 4096 < 2^31).
+//
+// Tile = 128 rows (TMEM lanes) x 64 columns.  Class q owns TMEM columns [64 q, 64 q + 64):
+// all KS classes are resident, so one pass over the contraction does every digit product.
+// The B digits of a stage lie slice-major in shared memory ([slice][64 rows][64 B]), so the
+// products of A digit i with B digits j..j+3 are ONE instruction of N = 256 whose output
+// columns [64 (i+j), 64 (i+j) + 256) are exactly classes i+j .. i+j+3.
+//
+// Pipeline (no CTA-wide barrier in the loop):
+//   warp 0    : TMA producer, one 3-D box per operand per stage (64 contraction bytes,
+//               128 or 64 rows, KS slices), 64-byte swizzle, completion on an mbarrier
+//   warp 1    : allocates TMEM, one lane issues the tcgen05.mma stream and commits each
+//               stage back to the producer (tcgen05.commit -> mbarrier)
+//   warps 2-9 : epilogue; tcgen05.ld the class accumulators, combine them in float64
+//               registers (2^-7q weights) and hand 32 columns of one row to a functor
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_tma.cuh"
+
+namespace scfgp {
+namespace umma {
+
+constexpr int TM = 128;  // tile rows  (M of the instruction, TMEM lanes)
+constexpr int TN = 64;   // tile columns per class
+constexpr int KB = 64;   // contraction bytes per pipeline stage (one 64-byte swizzle atom)
+constexpr int THREADS = 320;
+constexpr int EPI_WARP0 = 2;
+constexpr int EPI_THREADS = 256;
+
+template <int KS>
+struct Geo {
+  static constexpr int A_BYTES = KS * TM * KB;
+  static constexpr int B_BYTES = KS * TN * KB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (224 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+  static constexpr int CLASS_COLS = KS * TN;
+  static constexpr int TMEM_COLS = CLASS_COLS <= 256 ? 256 : 512;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(KS >= 2 && KS <= 8, "2..8 digits");
+  static_assert(STAGES >= 2, "need a double buffer");
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// all tcgen05.mma issued so far by this thread arrive (once) on the mbarrier when they retire
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T,  int8 x int8 -> int32, K = 32 bytes per instruction
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (quarter*32 + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major operand whose rows are 64 bytes apart and
+// 64-byte swizzled (8-row groups 512 bytes apart).  `byte_addr` may point 32 bytes into
+// the swizzle atom (second K = 32 step): the swizzle is a function of the absolute address.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t byte_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((byte_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(512 >> 4) << 32;              // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                       // layout type SWIZZLE_64B
+  return d;
+}
+// instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_i8(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+struct Tile {
+  int m0;       // first row of the A tensor map (dimension 1)
+  int n0;       // first row of the B tensor map (dimension 1)
+  int c_begin;  // contraction range in bytes = elements; c_begin multiple of 64
+  int c_end;
+};
+
+struct Pipe {
+  uint8_t* stages;
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* acc_full;
+  uint32_t* tmem_slot;
+};
+
+template <int KS>
+__device__ __forceinline__ Pipe pipe_init(uint8_t* smem_raw) {
+  using G = Geo<KS>;
+  Pipe p;
+  const uint32_t off = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  p.stages = smem_raw + off;
+  p.full = reinterpret_cast<uint64_t*>(p.stages + (size_t)G::STAGES * G::STAGE_BYTES);
+  p.empty = p.full + G::STAGES;
+  p.acc_full = p.empty + G::STAGES;
+  p.tmem_slot = reinterpret_cast<uint32_t*>(p.acc_full + 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G::STAGES; ++s) {
+      mbar_init(&p.full[s], 1);
+      mbar_init(&p.empty[s], 1);
+    }
+    mbar_init(p.acc_full, 1);
+    mbar_fence_init();
+  }
+  if ((threadIdx.x >> 5) == 1) tmem_alloc(p.tmem_slot, G::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return p;
+}
+
+template <int KS>
+__device__ __forceinline__ void pipe_teardown(const Pipe& p, uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Geo<KS>::TMEM_COLS);
+  }
+}
+
+// producer + MMA roles of one tile (warps 0 and 1).  `it0` = pipeline iterations already
+// consumed by earlier tiles of this CTA (keeps the barrier phases running).
+template <int KS>
+__device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, const CUtensorMap* mapA,
+                                             const CUtensorMap* mapB, const Tile& t, int it0) {
+  using G = Geo<KS>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (t.c_end - t.c_begin + KB - 1) / KB;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int it = it0 + kb;
+        const int st = it % G::STAGES;
+        const uint32_t use = it / G::STAGES;
+        mbar_wait(&p.empty[st], (use & 1) ^ 1);
+        uint8_t* sa = p.stages + (size_t)st * G::STAGE_BYTES;
+        mbar_arrive_expect_tx(&p.full[st], G::STAGE_BYTES);
+        tma_load_3d(sa, mapA, t.c_begin + kb * KB, t.m0, 0, &p.full[st]);
+        tma_load_3d(sa + G::A_BYTES, mapB, t.c_begin + kb * KB, t.n0, 0, &p.full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int it = it0 + kb;
+        const int st = it % G::STAGES;
+        const uint32_t use = it / G::STAGES;
+        mbar_wait(&p.full[st], use & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(p.stages + (size_t)st * G::STAGE_BYTES);
+        const uint32_t sb = sa + G::A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < KB / 32; ++ks) {
+#pragma unroll
+          for (int i = 0; i < KS; ++i) {
+            const uint64_t adesc = smem_desc_sw64(sa + i * (TM * KB) + ks * 32);
+#pragma unroll
+            for (int j0 = 0; j0 < KS - i; j0 += 4) {
+              const int cnt = (KS - i - j0) < 4 ? (KS - i - j0) : 4;
+              const uint64_t bdesc = smem_desc_sw64(sb + j0 * (TN * KB) + ks * 32);
+              const uint32_t acc = (kb == 0 && ks == 0 && i == 0) ? 0u : 1u;
+              mma_i8(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc, idesc_i8(TN * cnt), acc);
+            }
+          }
+        }
+        tc_commit(&p.empty[st]);  // stage reusable once these MMAs have read it
+      }
+      tc_commit(p.acc_full);  // accumulators complete
+    }
+  }
+}
+
+// epilogue role (warps 2..9): returns v[c] = sum_q 2^(-7q) acc_q[row][col0 + c], c < 32
+template <int KS>
+__device__ __forceinline__ void epilogue_collect(const Pipe& p, uint32_t tmem_base, uint32_t acc_parity, int& row,
+                                                 int& col0, double (&v)[32]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+  const int half = (warp - EPI_WARP0) >> 2;     // which 32 of the 64 columns
+  row = quarter * 32 + lane;
+  col0 = half * 32;
+  mbar_wait(p.acc_full, acc_parity);
+  tc_fence_after();
+#pragma unroll
+  for (int c = 0; c < 32; ++c) v[c] = 0.0;
+#pragma unroll
+  for (int q = KS - 1; q >= 0; --q) {  // least significant class first
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN + col0), r);
+    const double w = __longlong_as_double((long long)(1023 - 7 * q) << 52);  // 2^(-7q)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)r[c], w, v[c]);
+  }
+}
+
+}  // namespace umma
+}  // namespace scfgp
