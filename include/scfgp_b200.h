@@ -77,6 +77,20 @@ int scfgp_set_chunk_rows(scfgp_handle* h, int rows);
  * depend on timing, chunk c always accumulates into context c % n. */
 int scfgp_set_streams(scfgp_handle* h, int n);
 
+/* Arithmetic of the three streaming products (Gram, Phi.LiT, backward).  The reference
+ * computes in float64 (TT.dmatrices, SCFGP/SCFGP.py:95-96); both modes return float64 and
+ * meet the stated tolerances (cost 1e-6, gradient/alpha/Li/predictions 1e-5).
+ *   SCFGP_PREC_FP64   : FP64 tensor path (DMMA.8x8x4), the default.
+ *   SCFGP_PREC_EMU_I8 : float64 emulated on the int8 tensor cores (tcgen05.mma kind::i8,
+ *                       exact int32 accumulation in tensor memory).  Operands are cut into
+ *                       `digits` signed base-128 digits (4..8; 0 = default 6, i.e. 41
+ *                       fractional bits of each operand row's maximum).  Feature map, Cholesky,
+ *                       triangular inverse and the small dense backward stay in true FP64.
+ * Default at create time: environment SCFGP_PRECISION = "fp64" | "emu" | "emu<digits>". */
+enum { SCFGP_PREC_FP64 = 0, SCFGP_PREC_EMU_I8 = 1 };
+int scfgp_set_precision(scfgp_handle* h, int mode, int digits);
+int scfgp_get_precision(const scfgp_handle* h, int* mode, int* digits);
+
 /* Training data of train_func/train_iter_func (the X, y arguments at
  * SCFGP/SCFGP.py:230,237,265).  X is N x D row-major, y has N entries.
  *   _host  : copies from host memory into device buffers owned by the handle.
@@ -158,6 +172,10 @@ int scfgp_get_profile(const scfgp_handle* h, double* total_ms, long long* launch
  *   layout 2: NN  C[i,j] = sum_k A[i,k] B[k,j]   (A m x k, B k x n) */
 int scfgp_dbg_gemm(int device, int layout, int m, int n, int k, const double* A,
                    const double* B, double* C);
+/* C (m x n) = A (m x k) . B^T (n x k) through digit extraction (per-row power-of-two
+ * scales) + the int8 tensor-core mainloop with `digits` digits. */
+int scfgp_dbg_emu_gemm(int device, int digits, int m, int n, int k, const double* A, const double* B,
+                       double* C);
 /* lower Cholesky + inverse factor of a symmetric K x K matrix (info = pivot+1 or 0) */
 int scfgp_dbg_factor(int device, int K, const double* A, double* L, double* Li, long long* info);
 /* Phi (N x K) for given params through the feature kernel */

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libscfgp_b200.so")
 OK, ERR_ARG, ERR_CUDA, ERR_NOT_PD, ERR_NONFINITE = 0, 1, 2, 3, 4
 FF_PHASE, FF_NOPHASE = 0, 1
 RED1, RED2, RED3 = 1, 2, 3
+PREC_FP64, PREC_EMU_I8 = 0, 1
 FAM_NONE, FAM_FEATURES, FAM_TGEMM, FAM_BACKWARD, FAM_SYRK = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)
@@ -34,6 +35,8 @@ PROTOTYPES = {
     "scfgp_set_stream": (C.c_int, [_h, C.c_void_p]),
     "scfgp_set_chunk_rows": (C.c_int, [_h, C.c_int]),
     "scfgp_set_streams": (C.c_int, [_h, C.c_int]),
+    "scfgp_set_precision": (C.c_int, [_h, C.c_int, C.c_int]),
+    "scfgp_get_precision": (C.c_int, [_h, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "scfgp_set_data_host": (C.c_int, [_h, _dp, _dp, _ll, _ll]),
     "scfgp_set_data_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, _ll, _ll]),
     "scfgp_eval": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp]),
@@ -54,6 +57,7 @@ PROTOTYPES = {
     "scfgp_set_profiling": (C.c_int, [_h, C.c_int]),
     "scfgp_get_profile": (C.c_int, [_h, C.POINTER(C.c_double), C.POINTER(_ll)]),
     "scfgp_dbg_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
+    "scfgp_dbg_emu_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
     "scfgp_dbg_factor": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, C.POINTER(_ll)]),
     "scfgp_dbg_features": (C.c_int, [_h, _dp, _dp, _ll, _dp]),
 }

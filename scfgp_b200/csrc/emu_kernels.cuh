@@ -1,0 +1,366 @@
+// Emulated-FP64 versions of the three hot products on the int8 tensor cores (tcgen05.mma
+// kind::i8, see umma_i8.cuh for the number format and the pipeline), plus the digit
+// extraction kernels that feed them.  Same math as kernels_tma.cuh:
+//   k_gram_i8      G += PhiT.Phi, H += PsiT.Phi          SCFGP.py:103-105, A.3
+//   k_tgemm_i8     v_n = |Phi_n LiT|^2                   SCFGP.py:112
+//   k_backward_i8  Phibar = [Phi | Psi'].[2Abar | 2 sigma B]T, fused trig derivative   A.5
+// All scales are powers of two, so scaling is exact; the only approximation is the
+// truncation of each operand to 7*KS-1 fractional bits of its row (or global) maximum.
+#pragma once
+#include "umma_i8.cuh"
+#include "kernels.cuh"
+
+namespace scfgp {
+namespace emu {
+
+using umma::TM;
+using umma::TN;
+using umma::KB;
+
+// smallest power of two >= x  (1 for x == 0 / non-finite input falls through to the caller's checks)
+__device__ __forceinline__ double pow2_ceil(double x) {
+  if (!(x > 0.0)) return 1.0;
+  int e;
+  const double m = frexp(x, &e);  // x = m 2^e, m in [0.5, 1)
+  return ldexp(1.0, m == 0.5 ? e - 1 : e);
+}
+
+// row permutation of the backward B operand: cos and sin halves of a feature become
+// neighbours so that both land in the same epilogue thread
+__device__ __forceinline__ int trig_perm(int j, int J) { return j < J ? 2 * j : 2 * (j - J) + 1; }
+
+// balanced base-128 digits of q (|q| <= 2^(7 KS - 1)); digit[0] most significant, |digit| <= 64
+template <int KS>
+__device__ __forceinline__ void digits_of(long long q, int (&d)[KS]) {
+  const long long lim = 1ll << (7 * KS - 1);
+  q = q > lim ? lim : (q < -lim ? -lim : q);
+#pragma unroll
+  for (int i = KS - 1; i >= 1; --i) {
+    const int lo = (int)((q + 64) & 127) - 64;
+    d[i] = lo;
+    q = (q - lo) >> 7;
+  }
+  d[0] = (int)q;
+}
+
+// ------------------------------------------------------------------------------------
+// per-row power-of-two scales of [M1 | f2 * M2] (either may be absent)
+//   scale[p(r)] = pow2_ceil(max_c |row r|), inv[p(r)] = 1 / scale
+// ------------------------------------------------------------------------------------
+__global__ void k_rowscale(const double* __restrict__ M1, long long ld1, const double* __restrict__ M2, long long ld2,
+                           const double* __restrict__ f2_ptr, int rows, int cols, int perm_J,
+                           double* __restrict__ scale, double* __restrict__ inv) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const double f2 = f2_ptr ? fabs(*f2_ptr) : 1.0;
+  double m = 0;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    m = fmax(m, fabs(M1[(long long)r * ld1 + c]));
+    if (M2) m = fmax(m, f2 * fabs(M2[(long long)r * ld2 + c]));
+  }
+  __shared__ double sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+    const double s = pow2_ceil(m);
+    const int o = perm_J > 0 ? trig_perm(r, perm_J) : r;
+    scale[o] = s;
+    inv[o] = 1.0 / s;
+  }
+}
+
+// power-of-two bound of |v[0..n)|: out[0] = scale, out[1] = 1/scale; running maximum of the
+// scale in gmax (bit pattern of a positive double orders like an integer)
+__global__ void k_absmax_pow2(const double* __restrict__ v, int n, double* __restrict__ out,
+                              unsigned long long* __restrict__ gmax) {
+  double m = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(v[i]));
+  __shared__ double sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+    const double s = pow2_ceil(m);
+    out[0] = s;
+    out[1] = 1.0 / s;
+    if (gmax) atomicMax(gmax, (unsigned long long)__double_as_longlong(s));
+  }
+}
+// out[0] = *gmax (as double), out[1] = 1 / out[0]
+__global__ void k_scale_from_bits(const unsigned long long* __restrict__ gmax, double* __restrict__ out) {
+  const double s = __longlong_as_double((long long)*gmax);
+  out[0] = s > 0 ? s : 1.0;
+  out[1] = 1.0 / out[0];
+}
+
+// ------------------------------------------------------------------------------------
+// digits of a row-major matrix, contraction index = column (K-major operand)
+//   x = src[r][c] * rowmul[r] * rowinv[p(r)] * ginv * *ginv_ptr  (absent factors = 1; |x| <= 1)
+//   dst[s][p(r)][col_off + c] = digit s of x;   one thread = 16 consecutive columns
+// ------------------------------------------------------------------------------------
+template <int KS>
+__global__ void k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols,
+                              const double* __restrict__ rowmul, const double* __restrict__ rowinv, double ginv,
+                              const double* __restrict__ ginv_ptr, int perm_J, int8_t* __restrict__ dst,
+                              long long pitch, long long slice_stride, int col_off) {
+  const int ngroups = (cols + 15) / 16;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * ngroups) return;
+  const int r = (int)(idx / ngroups), g = (int)(idx % ngroups);
+  const int orow = perm_J > 0 ? trig_perm(r, perm_J) : r;
+  double mult = ldexp(1.0, 7 * KS - 1) * ginv;
+  if (ginv_ptr) mult *= *ginv_ptr;
+  if (rowmul) mult *= rowmul[r];
+  if (rowinv) mult *= rowinv[orow];
+  const double* p = src + (long long)r * ld + g * 16;
+  uint32_t packed[KS][4];
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) packed[s][w] = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int c = g * 16 + e;
+    const double x = c < cols ? p[e] : 0.0;
+    int d[KS];
+    digits_of<KS>(llrint(x * mult), d);
+#pragma unroll
+    for (int s = 0; s < KS; ++s) packed[s][e >> 2] |= (uint32_t)(d[s] & 0xff) << (8 * (e & 3));
+  }
+  int8_t* o = dst + (long long)orow * pitch + col_off + g * 16;
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+    *reinterpret_cast<uint4*>(o + (long long)s * slice_stride) =
+        make_uint4(packed[s][0], packed[s][1], packed[s][2], packed[s][3]);
+}
+
+// ------------------------------------------------------------------------------------
+// digits of the TRANSPOSE of a row slab, contraction index = row (Gram operands)
+//   dst[s][c][r] = digit s of src[r][c] * rowmul[r] * ginv * *ginv_ptr ; rows beyond `rows`
+//   up to the 128-row tile boundary are written as zeros (they are inside the reduction)
+//   grid = (ceil(cols/64), ceil(rows/128)), 256 threads: thread = (column, 32 rows)
+// ------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256)
+k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, const double* __restrict__ rowmul,
+              double ginv, const double* __restrict__ ginv_ptr, int8_t* __restrict__ dst, long long pitch,
+              long long slice_stride) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int r0 = blockIdx.y * 128 + (threadIdx.x >> 6) * 32;
+  const double base = ldexp(1.0, 7 * KS - 1) * ginv * (ginv_ptr ? *ginv_ptr : 1.0);
+  uint32_t packed[KS][8];
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+#pragma unroll
+    for (int w = 0; w < 8; ++w) packed[s][w] = 0;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const int r = r0 + e;
+    double x = 0.0;
+    if (r < rows && c < cols) {
+      x = src[(long long)r * ld + c] * base;
+      if (rowmul) x *= rowmul[r];
+    }
+    int d[KS];
+    digits_of<KS>(llrint(x), d);
+#pragma unroll
+    for (int s = 0; s < KS; ++s) packed[s][e >> 2] |= (uint32_t)(d[s] & 0xff) << (8 * (e & 3));
+  }
+  if (c < cols) {
+    int8_t* o = dst + (long long)c * pitch + r0;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      uint4* q = reinterpret_cast<uint4*>(o + (long long)s * slice_stride);
+      q[0] = make_uint4(packed[s][0], packed[s][1], packed[s][2], packed[s][3]);
+      q[1] = make_uint4(packed[s][4], packed[s][5], packed[s][6], packed[s][7]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Gram accumulation over one row chunk:  C[a][b] += sc * sum_r A[r,a] B[r,b]
+//   operands: transposed digits [KS][K][R]; items (a block of 128, b block of 64) cover the
+//   lower triangle (blocks that cross the diagonal are computed whole).
+//   sc = scale * *scale_ptr * 2^-12
+// ------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(umma::THREADS, 1)
+k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int depth, int K,
+          const int2* __restrict__ items, double* __restrict__ C, long long ldc, double scale,
+          const double* __restrict__ scale_ptr) {
+  extern __shared__ uint8_t smem_raw[];
+  umma::Pipe p = umma::pipe_init<KS>(smem_raw);
+  const uint32_t tmem_base = *p.tmem_slot;
+  const int2 it = items[blockIdx.x];
+  umma::Tile t;
+  t.m0 = it.x * TM;
+  t.n0 = it.y * TN;
+  t.c_begin = 0;
+  t.c_end = depth;
+  if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
+    umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, 0);
+  } else {
+    int row, col0;
+    double v[32];
+    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
+    const int a = t.m0 + row;
+    if (a < K) {
+      const double sc = scale * (scale_ptr ? *scale_ptr : 1.0) * (1.0 / 4096.0);
+      double* crow = C + (long long)a * ldc + t.n0 + col0;
+      const int nvalid = K - (t.n0 + col0);
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        if (c + 1 < nvalid) {
+          double2 o = *reinterpret_cast<double2*>(crow + c);
+          o.x += sc * v[c];
+          o.y += sc * v[c + 1];
+          *reinterpret_cast<double2*>(crow + c) = o;
+        } else if (c < nvalid) {
+          crow[c] += sc * v[c];
+        }
+      }
+    }
+  }
+  umma::pipe_teardown<KS>(p, tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// v_n partials of T = Phi.LiT:  vpart[2 nb + half][n] = sum over 32 columns of T[n, .]^2
+//   A: row digits of Phi (scale sA), B: row digits of Li with per-row scales liscale
+//   grid = (nblocks of 64 Li rows, row blocks of 128); deepest reduction (last nb) first
+// ------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(umma::THREADS, 1)
+k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int rows, int K,
+           const double* __restrict__ liscale, double sA, double* __restrict__ vpart, long long ldv) {
+  extern __shared__ uint8_t smem_raw[];
+  const int nb = (int)gridDim.x - 1 - (int)blockIdx.x;
+  umma::Tile t;
+  t.m0 = blockIdx.y * TM;
+  t.n0 = nb * TN;
+  t.c_begin = 0;
+  t.c_end = min(K, t.n0 + TN);  // Li is lower triangular
+  if (t.m0 >= rows) return;     // short last chunk: the whole CTA leaves before any barrier
+  umma::Pipe p = umma::pipe_init<KS>(smem_raw);
+  const uint32_t tmem_base = *p.tmem_slot;
+  if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
+    umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapLi, t, 0);
+  } else {
+    int row, col0;
+    double v[32];
+    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
+    double sq = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int j = t.n0 + col0 + c;
+      const double tv = j < K ? v[c] * liscale[j] : 0.0;
+      sq = fma(tv, tv, sq);
+    }
+    const double sc = sA * (1.0 / 4096.0);
+    const int r = t.m0 + row;
+    if (r < rows) vpart[(long long)(2 * nb + (col0 >> 5)) * ldv + r] = sq * sc * sc;
+  }
+  umma::pipe_teardown<KS>(p, tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// backward tile: 128 rows x 32 features (64 permuted columns: cos/sin interleaved)
+//   Phibar = sA 2^-12 cscale[j] * sum_c [Phi|Psi'] digits . Cmat digits  + y pbarT + gmu alphaT
+//   Zbar = -Phibar_c * Phi_s + Phibar_s * Phi_c ;  slots[cta] += <Phibar, Phi>
+//   grid = (feature blocks of 32, row blocks of 128)
+// ------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(umma::THREADS, 1)
+k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, int rows, int J,
+              int depth2, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
+              long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
+              const double* __restrict__ pbar, const double* __restrict__ alpha, double* __restrict__ Zbar,
+              long long ldz, double* __restrict__ slots) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ double sh[8];
+  umma::Tile t;
+  t.m0 = blockIdx.y * TM;
+  t.n0 = blockIdx.x * TN;
+  t.c_begin = 0;
+  t.c_end = depth2;
+  if (t.m0 >= rows) return;
+  umma::Pipe p = umma::pipe_init<KS>(smem_raw);
+  const uint32_t tmem_base = *p.tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < umma::EPI_WARP0) {
+    umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapC, t, 0);
+  } else {
+    int row, col0;
+    double v[32];
+    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
+    const int r = t.m0 + row;
+    double sacc = 0;
+    if (r < rows) {
+      const double sc = sA * (1.0 / 4096.0);
+      const double yn = y[r], gm = gmu[r];
+      const double* prow = Phi + (long long)r * ldp;
+      const int f0 = (t.n0 + col0) >> 1;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int f = f0 + e;
+        if (f < J) {
+          const int pj = t.n0 + col0 + 2 * e;
+          const double pc = v[2 * e] * (cscale[pj] * sc) + yn * pbar[f] + gm * alpha[f];
+          const double ps = v[2 * e + 1] * (cscale[pj + 1] * sc) + yn * pbar[J + f] + gm * alpha[J + f];
+          const double phc = prow[f], phs = prow[J + f];
+          Zbar[(long long)r * ldz + f] = -pc * phs + ps * phc;
+          sacc += pc * phc + ps * phs;
+        }
+      }
+    }
+    sacc = warp_sum(sacc);
+    if (lane == 0) sh[warp - umma::EPI_WARP0] = sacc;
+    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");
+    if (warp == umma::EPI_WARP0 && lane == 0) {
+      double s = 0;
+      for (int w = 0; w < 8; ++w) s += sh[w];
+      slots[blockIdx.y * gridDim.x + blockIdx.x] += s;
+    }
+  }
+  umma::pipe_teardown<KS>(p, tmem_base);
+}
+
+// generic C[m][n] = sum_c A[m,c] B[n,c] with per-row scales on both sides (self-test hook)
+template <int KS>
+__global__ void __launch_bounds__(umma::THREADS, 1)
+k_gemm_i8_dbg(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int Nn,
+              int depth, const double* __restrict__ ascale, const double* __restrict__ bscale, double* __restrict__ C,
+              long long ldc) {
+  extern __shared__ uint8_t smem_raw[];
+  umma::Pipe p = umma::pipe_init<KS>(smem_raw);
+  const uint32_t tmem_base = *p.tmem_slot;
+  umma::Tile t;
+  t.m0 = blockIdx.y * TM;
+  t.n0 = blockIdx.x * TN;
+  t.c_begin = 0;
+  t.c_end = depth;
+  if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
+    umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, 0);
+  } else {
+    int row, col0;
+    double v[32];
+    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
+    const int r = t.m0 + row;
+    if (r < M) {
+      const double sa = ascale[r] * (1.0 / 4096.0);
+      for (int c = 0; c < 32; ++c) {
+        const int j = t.n0 + col0 + c;
+        if (j < Nn) C[(long long)r * ldc + j] = v[c] * sa * bscale[j];
+      }
+    }
+  }
+  umma::pipe_teardown<KS>(p, tmem_base);
+}
+
+}  // namespace emu
+}  // namespace scfgp

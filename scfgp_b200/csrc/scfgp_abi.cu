@@ -13,6 +13,7 @@
 #include "../../include/scfgp_b200.h"
 #include "kernels.cuh"
 #include "kernels_tma.cuh"
+#include "emu_kernels.cuh"
 
 using namespace scfgp;
 
@@ -37,6 +38,12 @@ struct Ctx {
   double *colpart = nullptr;  // kColSplit x K
   double *slots = nullptr;    // slot_stride scalars
   CUtensorMap mapPhi, mapPsi; // 16x16-box TMA views of the slabs
+  // emulated-FP64 path (int8 digits, see emu_kernels.cuh)
+  int8_t *digR = nullptr;     // [KS][R][2 Kp]  row digits of [Phi | Psi']
+  int8_t *digPhiT = nullptr;  // [KS][K][R]     transposed digits of Phi
+  int8_t *digPsiT = nullptr;  // [KS][K][R]     transposed digits of gv * Phi / sigma_chunk
+  double *sig = nullptr;      // {sigma_chunk, 1/sigma_chunk}
+  CUtensorMap mapRowsA, mapPhiT_A, mapPhiT_B, mapPsiT_A;
 };
 
 }  // namespace
@@ -50,7 +57,8 @@ struct scfgp_handle {
   const double* dy = nullptr;
   double* ownX = nullptr;
   double* owny = nullptr;
-  int R = 4096;  // rows per chunk
+  int R = 4096;  // rows per chunk (8192 in the emulated mode unless set by the caller)
+  bool R_user = false;
   int xvec = 2;
   long long ldk = 0;  // leading dimension of K x K matrices and slabs
   long long ldj = 0;  // leading dimension of D x J / Zbar
@@ -77,6 +85,20 @@ struct scfgp_handle {
   double *colpart = nullptr, *slots = nullptr, *trslots = nullptr;   // main-stream scratch
   long long* info = nullptr;
   int nrb_cap = 0;
+
+  // emulated-FP64 path: precision mode, digit count and the replicated digit operands
+  int prec = SCFGP_PREC_FP64;
+  int ks = 6;
+  long long Kp = 0;            // K rounded up to 16 (digit row pitch / offset of the Psi' half)
+  double s2 = 1.0;             // power of two >= s: scale of the Phi digits
+  int8_t *digLi = nullptr;     // [KS][K][Kp]
+  int8_t *digC = nullptr;      // [KS][K][2 Kp]   rows permuted (cos/sin interleaved): [2Abar | 2 sigma B]
+  double *liscale = nullptr, *liinv = nullptr, *cscale = nullptr, *cinv = nullptr, *sigg = nullptr;
+  unsigned long long* gvmax = nullptr;
+  CUtensorMap mapLiB, mapCB;
+  int2* gram_items = nullptr;
+  int gram_count = 0;
+  int vparts = 0;              // partial rows of vpart per chunk
 
   // work lists
   ItemList lowerK, syrkK, fullK, tgemm, bwd, dw;
@@ -155,6 +177,34 @@ int make_tmap(scfgp_handle* h, CUtensorMap* out, const double* base, long long c
   if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return SCFGP_ERR_CUDA; }
   return SCFGP_OK;
 }
+
+// 3-D int8 view of a digit array [ks][rows][pitch] (contraction index contiguous): boxes of
+// 64 contraction bytes x box_rows rows x ks digits, 64-byte swizzle, zero fill out of bounds
+int make_tmap_digits(scfgp_handle* h, CUtensorMap* out, const int8_t* base, long long depth, long long rows,
+                     long long pitch, int ks, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { h->err = "cuTensorMapEncodeTiled not available"; return SCFGP_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)depth, (cuuint64_t)rows, (cuuint64_t)ks};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)umma::KB, (cuuint32_t)box_rows, (cuuint32_t)ks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(digits) failed: " + std::to_string((int)r); return SCFGP_ERR_CUDA; }
+  return SCFGP_OK;
+}
+
+// run `...` with a compile-time digit count KS matching the handle's runtime one
+#define EMU_KS_SWITCH(ks, ...)                                   \
+  switch (ks) {                                                  \
+    case 4: { constexpr int KS = 4; __VA_ARGS__; } break;        \
+    case 5: { constexpr int KS = 5; __VA_ARGS__; } break;        \
+    case 6: { constexpr int KS = 6; __VA_ARGS__; } break;        \
+    case 7: { constexpr int KS = 7; __VA_ARGS__; } break;        \
+    case 8: { constexpr int KS = 8; __VA_ARGS__; } break;        \
+    default: h->err = "unsupported digit count"; return SCFGP_ERR_ARG; \
+  }
 
 // profiling brackets: record an event pair around launches of the selected family
 inline void prof_begin(scfgp_handle* h, int fam, cudaStream_t st) {
@@ -242,6 +292,16 @@ int set_kernel_attrs(scfgp_handle* h) {
   return SCFGP_OK;
 }
 
+template <int KS>
+int set_emu_attrs(scfgp_handle* h) {
+  const int smem = (int)umma::Geo<KS>::SMEM;
+  CK(cudaFuncSetAttribute(emu::k_gram_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(emu::k_tgemm_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(emu::k_backward_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(emu::k_gemm_i8_dbg<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  return SCFGP_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // host-side unpack of the flat parameter vector            SCFGP/SCFGP.py:74-90, A.1
 // ---------------------------------------------------------------------------------
@@ -286,6 +346,11 @@ int unpack_and_upload(scfgp_handle* h, const double* params) {
   h->sigf = std::exp(h->b);
   h->tau = std::log(1 + std::exp(h->c));
   h->s = h->sigf * std::sqrt(2.0 / M);
+  {
+    int e;
+    const double m = std::frexp(h->s, &e);
+    h->s2 = std::ldexp(1.0, m == 0.5 ? e - 1 : e);  // power of two >= s = max |Phi|
+  }
   CK(cudaMemcpyAsync(h->Wt, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->phi, h->phi_h.data(), (size_t)J * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));  // wt is a stack-lifetime staging buffer
@@ -308,7 +373,11 @@ int ensure_row_arrays(scfgp_handle* h, long long n) {
 int alloc_chunk_buffers(scfgp_handle* h) {
   for (int i = 0; i < kMaxStreams; ++i) {
     Ctx& c = h->ctx[i];
-    for (double** p : {&c.Phi, &c.Psi, &c.Zbar, &c.vpart}) {
+    for (double** p : {&c.Phi, &c.Psi, &c.Zbar, &c.vpart, &c.sig}) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+    for (int8_t** p : {&c.digR, &c.digPhiT, &c.digPsiT}) {
       if (*p) cudaFree(*p);
       *p = nullptr;
     }
@@ -340,7 +409,11 @@ int alloc_chunk_buffers(scfgp_handle* h) {
     for (int fb = 0; fb < nfb; ++fb) bw.push_back(make_int4(rb, fb, 0, 0));
   if ((rc = upload_items(h, tg, &h->tgemm))) return rc;
   if ((rc = upload_items(h, bw, &h->bwd))) return rc;
-  h->slot_stride = (std::max<long long>(std::max(2 * kSeedBlocks, (int)bw.size()), 256) + 1) / 2 * 2;
+  const bool emu_on = h->prec == SCFGP_PREC_EMU_I8;
+  const int emu_bwd_ctas = emu_on ? nrb * cdiv(h->J, 32) : 0;
+  h->vparts = emu_on ? 2 * cdiv(K, umma::TN) : nkb;
+  h->slot_stride =
+      (std::max<long long>(std::max(std::max(2 * kSeedBlocks, (int)bw.size()), emu_bwd_ctas), 256) + 1) / 2 * 2;
   const size_t KK = (size_t)K * h->ldk, DJ = (size_t)h->D * h->ldj;
   if ((rc = dalloc(h, &h->acc_all, KK * h->ns))) return rc;
   if ((rc = dalloc(h, &h->dW_all, DJ * h->ns))) return rc;
@@ -351,7 +424,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
     if ((rc = dalloc(h, &c.Phi, (size_t)R * h->ldk))) return rc;
     if ((rc = dalloc(h, &c.Psi, (size_t)R * h->ldk))) return rc;
     if ((rc = dalloc(h, &c.Zbar, (size_t)R * h->ldj))) return rc;
-    if ((rc = dalloc(h, &c.vpart, (size_t)nkb * R))) return rc;
+    if ((rc = dalloc(h, &c.vpart, (size_t)std::max(nkb, h->vparts) * R))) return rc;
     c.acc = h->acc_all + KK * i;
     c.dW = h->dW_all + DJ * i;
     c.colpart = h->colpart_all + (size_t)kColSplit * K * i;
@@ -360,7 +433,61 @@ int alloc_chunk_buffers(scfgp_handle* h) {
       if ((rc = make_tmap(h, &c.mapPhi, c.Phi, K, R, h->ldk))) return rc;
       if ((rc = make_tmap(h, &c.mapPsi, c.Psi, K, R, h->ldk))) return rc;
     }
+    if (emu_on) {
+      const long long Kp = h->Kp;
+      const int ks = h->ks;
+      if ((rc = dalloc(h, &c.digR, (size_t)ks * R * 2 * Kp))) return rc;
+      if ((rc = dalloc(h, &c.digPhiT, (size_t)ks * K * R))) return rc;
+      if ((rc = dalloc(h, &c.digPsiT, (size_t)ks * K * R))) return rc;
+      if ((rc = dalloc(h, &c.sig, 2))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapRowsA, c.digR, Kp + K, R, 2 * Kp, ks, umma::TM))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPhiT_A, c.digPhiT, R, K, R, ks, umma::TM))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPhiT_B, c.digPhiT, R, K, R, ks, umma::TN))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPsiT_A, c.digPsiT, R, K, R, ks, umma::TM))) return rc;
+    }
   }
+  return SCFGP_OK;
+}
+
+void free_emu_static(scfgp_handle* h) {
+  for (int8_t** p : {&h->digLi, &h->digC}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  for (double** p : {&h->liscale, &h->liinv, &h->cscale, &h->cinv, &h->sigg}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  if (h->gvmax) cudaFree(h->gvmax);
+  h->gvmax = nullptr;
+  if (h->gram_items) cudaFree(h->gram_items);
+  h->gram_items = nullptr;
+  h->gram_count = 0;
+}
+
+// replicated digit operands (Li, [2Abar | 2 sigma B]) and the Gram tile list of the emulated path
+int alloc_emu_static(scfgp_handle* h) {
+  free_emu_static(h);
+  if (h->prec != SCFGP_PREC_EMU_I8) return SCFGP_OK;
+  const int K = h->K, ks = h->ks;
+  const long long Kp = h->Kp;
+  int rc;
+  if ((rc = dalloc(h, &h->digLi, (size_t)ks * K * Kp))) return rc;
+  if ((rc = dalloc(h, &h->digC, (size_t)ks * K * 2 * Kp))) return rc;
+  for (double** p : {&h->liscale, &h->liinv, &h->cscale, &h->cinv})
+    if ((rc = dalloc(h, p, K))) return rc;
+  if ((rc = dalloc(h, &h->sigg, 2))) return rc;
+  if ((rc = dalloc(h, &h->gvmax, 1))) return rc;
+  if ((rc = make_tmap_digits(h, &h->mapLiB, h->digLi, K, K, Kp, ks, umma::TN))) return rc;
+  if ((rc = make_tmap_digits(h, &h->mapCB, h->digC, Kp + K, K, 2 * Kp, ks, umma::TN))) return rc;
+  std::vector<int2> v;
+  for (int mt = 0; mt < cdiv(K, umma::TM); ++mt)
+    for (int nt = 0; nt < cdiv(K, umma::TN); ++nt)
+      if (nt * umma::TN <= mt * umma::TM + umma::TM - 1) v.push_back(make_int2(mt, nt));
+  h->gram_count = (int)v.size();
+  CK(cudaMalloc((void**)&h->gram_items, v.size() * sizeof(int2)));
+  CK(cudaMemcpy(h->gram_items, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  EMU_KS_SWITCH(ks, if ((rc = set_emu_attrs<KS>(h))) return rc);
   return SCFGP_OK;
 }
 
@@ -436,6 +563,87 @@ int run_tgemm(scfgp_handle* h, Ctx& c, int rows) {
   prof_end(h, SCFGP_FAM_TGEMM, c.st);
   CKL();
   return SCFGP_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// emulated-FP64 path: digit extraction + int8 tensor-core products (emu_kernels.cuh)
+// ---------------------------------------------------------------------------------
+int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
+                    const double* rowmul, const double* rowinv, double ginv, const double* ginv_ptr, int permJ,
+                    int8_t* dst, long long pitch, long long slice_stride, int col_off) {
+  const long long total = (long long)rows * cdiv(cols, 16);
+  EMU_KS_SWITCH(h->ks, emu::k_digits_rows<KS><<<cdiv(total, 256), 256, 0, st>>>(
+                           src, ld, rows, cols, rowmul, rowinv, ginv, ginv_ptr, permJ, dst, pitch, slice_stride, col_off));
+  CKL();
+  return SCFGP_OK;
+}
+
+int emu_digits_cols(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
+                    const double* rowmul, double ginv, const double* ginv_ptr, int8_t* dst, long long pitch,
+                    long long slice_stride) {
+  const dim3 grid(cdiv(cols, 64), cdiv(rows, 128));
+  EMU_KS_SWITCH(h->ks, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
+                                                                    pitch, slice_stride));
+  CKL();
+  return SCFGP_OK;
+}
+
+// acc(lower tiles) += sc * digits(A)T . digits(Phi) over the rows of one chunk
+int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
+  const int depth = (rows + umma::KB - 1) / umma::KB * umma::KB;
+  prof_begin(h, SCFGP_FAM_SYRK, c.st);
+  EMU_KS_SWITCH(h->ks, emu::k_gram_i8<KS><<<h->gram_count, umma::THREADS, umma::Geo<KS>::SMEM, c.st>>>(
+                           a_is_psi ? c.mapPsiT_A : c.mapPhiT_A, c.mapPhiT_B, depth, h->K, h->gram_items, c.acc, h->ldk,
+                           h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
+  prof_end(h, SCFGP_FAM_SYRK, c.st);
+  CKL();
+  return SCFGP_OK;
+}
+
+int emu_tgemm(scfgp_handle* h, Ctx& c, int rows) {
+  const dim3 grid(cdiv(h->K, umma::TN), cdiv(rows, umma::TM));
+  prof_begin(h, SCFGP_FAM_TGEMM, c.st);
+  EMU_KS_SWITCH(h->ks, emu::k_tgemm_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.st>>>(
+                           c.mapRowsA, h->mapLiB, rows, h->K, h->liscale, h->s2, c.vpart, h->R));
+  prof_end(h, SCFGP_FAM_TGEMM, c.st);
+  CKL();
+  return SCFGP_OK;
+}
+
+int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0) {
+  const dim3 grid(cdiv(h->J, 32), cdiv(rows, umma::TM));
+  prof_begin(h, SCFGP_FAM_BACKWARD, c.st);
+  EMU_KS_SWITCH(h->ks, emu::k_backward_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.st>>>(
+                           c.mapRowsA, h->mapCB, rows, h->J, (int)(h->Kp + h->K), h->cscale, h->s2, c.Phi, h->ldk,
+                           h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj, c.slots));
+  prof_end(h, SCFGP_FAM_BACKWARD, c.st);
+  CKL();
+  return SCFGP_OK;
+}
+
+// digits of Li with per-row power-of-two scales (B operand of Phi.LiT)
+int emu_prepare_li(scfgp_handle* h) {
+  const int K = h->K;
+  emu::k_rowscale<<<K, 128, 0, h->stream>>>(h->Li, h->ldk, nullptr, 0, nullptr, K, K, 0, h->liscale, h->liinv);
+  CKL();
+  return emu_digits_rows(h, h->stream, h->Li, h->ldk, K, K, nullptr, h->liinv, 1.0, nullptr, 0, h->digLi, h->Kp,
+                         (long long)K * h->Kp, 0);
+}
+
+// digits of Cmat = [2 Abar | 2 sigma B] (rows permuted cos/sin-interleaved, per-row scales);
+// sigma = power-of-two bound of |gv| over this rank's rows (pass 2)
+int emu_prepare_c(scfgp_handle* h) {
+  const int K = h->K;
+  int rc;
+  emu::k_scale_from_bits<<<1, 1, 0, h->stream>>>(h->gvmax, h->sigg);
+  CKL();
+  emu::k_rowscale<<<K, 128, 0, h->stream>>>(h->A2, h->ldk, h->B2, h->ldk, h->sigg, K, K, h->J, h->cscale, h->cinv);
+  CKL();
+  if ((rc = emu_digits_rows(h, h->stream, h->A2, h->ldk, K, K, nullptr, h->cinv, 1.0, nullptr, h->J, h->digC,
+                            2 * h->Kp, (long long)K * 2 * h->Kp, 0)))
+    return rc;
+  return emu_digits_rows(h, h->stream, h->B2, h->ldk, K, K, nullptr, h->cinv, 1.0, h->sigg, h->J, h->digC, 2 * h->Kp,
+                         (long long)K * 2 * h->Kp, (int)h->Kp);
 }
 
 // lower Cholesky of h->L in place + Li = inv(L)                SCFGP/SCFGP.py:106-107
@@ -536,12 +744,15 @@ int build_static_lists(scfgp_handle* h) {
 void free_all(scfgp_handle* h) {
   for (int i = 0; i < kMaxStreams; ++i) {
     Ctx& c = h->ctx[i];
-    for (double* p : {c.Phi, c.Psi, c.Zbar, c.vpart})
+    for (double* p : {c.Phi, c.Psi, c.Zbar, c.vpart, c.sig})
+      if (p) cudaFree(p);
+    for (int8_t* p : {c.digR, c.digPhiT, c.digPsiT})
       if (p) cudaFree(p);
     if (c.done) cudaEventDestroy(c.done);
     if (c.st) cudaStreamDestroy(c.st);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  free_emu_static(h);
   for (double* p : {h->acc_all, h->dW_all, h->colpart_all, h->slots_all, h->Wt, h->phi, h->red1, h->red2, h->red3, h->L,
                     h->Li, h->Bm, h->BH, h->BHB, h->A2, h->B2, h->Dinv, h->tmpS, h->alpha, h->beta, h->tvec,
                     h->pbar, h->scal, h->gmu, h->gv, h->colpart, h->slots, h->trslots, h->ownX, h->owny})
@@ -609,6 +820,15 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   h->ldk = h->K;                       // K = 2J is even: 16-byte row alignment holds
   h->ldj = (h->J + 1) / 2 * 2;
   h->ldw = (D + 1) / 2 * 2;
+  h->Kp = (h->K + 15) / 16 * 16;
+  if (const char* e = getenv("SCFGP_PRECISION")) {
+    if (!strncmp(e, "emu", 3)) {
+      h->prec = SCFGP_PREC_EMU_I8;
+      const int d = atoi(e + 3);
+      h->ks = (d >= 4 && d <= 8) ? d : 6;
+      h->R = 8192;
+    }
+  }
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) { h->err = "no such CUDA device"; return SCFGP_ERR_CUDA; }
@@ -645,6 +865,7 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
     if ((rc = make_tmap(h, &h->mapB2, h->B2, K, K, h->ldk))) return rc;
   }
   if ((rc = build_static_lists(h))) return rc;
+  if ((rc = alloc_emu_static(h))) return rc;
   if ((rc = alloc_chunk_buffers(h))) return rc;
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
   CK(cudaStreamSynchronize(h->stream));
@@ -677,7 +898,30 @@ int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
   h->R = rows;
+  h->R_user = true;
   return alloc_chunk_buffers(h);
+}
+
+int scfgp_set_precision(scfgp_handle* h, int mode, int digits) {
+  if (!h || (mode != SCFGP_PREC_FP64 && mode != SCFGP_PREC_EMU_I8)) return SCFGP_ERR_ARG;
+  if (digits == 0) digits = 6;
+  if (digits < 4 || digits > 8) { h->err = "digits must be 4..8"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  h->prec = mode;
+  h->ks = digits;
+  if (!h->R_user) h->R = mode == SCFGP_PREC_EMU_I8 ? 8192 : 4096;
+  h->have_factors = false;
+  int rc;
+  if ((rc = alloc_emu_static(h))) return rc;
+  return alloc_chunk_buffers(h);
+}
+
+int scfgp_get_precision(const scfgp_handle* h, int* mode, int* digits) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (mode) *mode = h->prec;
+  if (digits) *digits = h->ks;
+  return SCFGP_OK;
 }
 
 int scfgp_set_streams(scfgp_handle* h, int n) {
@@ -752,7 +996,14 @@ int scfgp_eval_pass1(scfgp_handle* h) {
     Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
     if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
-    if ((rc = run_syrk(h, c, false, rows))) return rc;
+    if (h->prec == SCFGP_PREC_EMU_I8) {
+      if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
+                                (long long)K * h->R)))
+        return rc;
+      if ((rc = emu_gram(h, c, false, rows))) return rc;
+    } else {
+      if ((rc = run_syrk(h, c, false, rows))) return rc;
+    }
     k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->dy + r0, c.colpart, K);
     CKL();
   }
@@ -785,6 +1036,7 @@ int scfgp_eval_factor(scfgp_handle* h) {
   k_add_diag<<<cdiv(K, 256), 256, 0, h->stream>>>(h->L, h->ldk, K, h->sig2n + kEps);
   CKL();
   if ((rc = factor_device(h, h->L, h->Li, K, h->ldk))) return rc;
+  if (h->prec == SCFGP_PREC_EMU_I8 && (rc = emu_prepare_li(h))) return rc;
   // beta = Li p ; alpha = LiT beta                           SCFGP/SCFGP.py:108-110
   k_gemv_n<<<cdiv(K, 8), 256, 0, h->stream>>>(h->Li, h->ldk, K, K, p, h->beta);
   CKL();
@@ -827,7 +1079,9 @@ int scfgp_eval_pass2(scfgp_handle* h) {
   double* H = h->red2;
   double* q = h->red2 + KK;
   double* Eg = q + K;
-  const int nkb = cdiv(K, 128);
+  const int nkb = h->vparts;
+  const bool emu_on = h->prec == SCFGP_PREC_EMU_I8;
+  if (emu_on) CK(cudaMemsetAsync(h->gvmax, 0, sizeof(unsigned long long), h->stream));
   if ((rc = fork_streams(h))) return rc;
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
@@ -842,11 +1096,32 @@ int scfgp_eval_pass2(scfgp_handle* h) {
     Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
     if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
-    if ((rc = run_tgemm(h, c, rows))) return rc;
+    if (emu_on) {
+      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, nullptr, nullptr, 1.0 / h->s2, nullptr, 0, c.digR,
+                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0)))
+        return rc;
+      if ((rc = emu_tgemm(h, c, rows))) return rc;
+    } else {
+      if ((rc = run_tgemm(h, c, rows))) return rc;
+    }
     k_seeds<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->dy + r0,
-                                          h->tau, h->gmu + r0, h->gv + r0, c.Psi, c.slots, h->want_grad);
+                                          h->tau, h->gmu + r0, h->gv + r0, c.Psi, c.slots,
+                                          emu_on ? 0 : h->want_grad);
     CKL();
-    if (h->want_grad) {
+    if (h->want_grad && emu_on) {
+      // H += (gv Phi)T Phi with the chunk's own power-of-two bound of |gv|
+      emu::k_absmax_pow2<<<1, 1024, 0, c.st>>>(h->gv + r0, rows, c.sig, h->gvmax);
+      CKL();
+      if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
+                                (long long)K * h->R)))
+        return rc;
+      if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, h->gv + r0, 1.0 / h->s2, c.sig + 1, c.digPsiT, h->R,
+                                (long long)K * h->R)))
+        return rc;
+      if ((rc = emu_gram(h, c, true, rows))) return rc;
+      k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
+      CKL();
+    } else if (h->want_grad) {
       if ((rc = run_syrk(h, c, true, rows))) return rc;
       k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
       CKL();
@@ -893,6 +1168,7 @@ int scfgp_eval_backward(scfgp_handle* h) {
   CKL();
   k_reduce_slots<<<1, 256, 0, h->stream>>>(h->trslots, K, 1, 1, h->scal + 3);
   CKL();
+  if (h->prec == SCFGP_PREC_EMU_I8 && (rc = emu_prepare_c(h))) return rc;
   return SCFGP_OK;
 }
 
@@ -922,20 +1198,33 @@ int scfgp_eval_pass3(scfgp_handle* h) {
     Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
     const double* Xc = h->dX + r0 * D;
-    if ((rc = run_features(h, c, Xc, h->xvec, rows, h->gv + r0, c.Psi))) return rc;
+    const bool emu_on = h->prec == SCFGP_PREC_EMU_I8;
+    if (emu_on) {
+      if ((rc = run_features(h, c, Xc, h->xvec, rows, nullptr, nullptr))) return rc;
+      // A operand digits: [Phi | (gv / sigma) Phi], both against the scale s2
+      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, nullptr, nullptr, 1.0 / h->s2, nullptr, 0, c.digR,
+                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0)))
+        return rc;
+      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, h->gv + r0, nullptr, 1.0 / h->s2, h->sigg + 1, 0,
+                                c.digR, 2 * h->Kp, (long long)h->R * 2 * h->Kp, (int)h->Kp)))
+        return rc;
+      if ((rc = emu_backward(h, c, rows, r0))) return rc;
+    } else if ((rc = run_features(h, c, Xc, h->xvec, rows, h->gv + r0, c.Psi))) return rc;
     const int nitems = cdiv(rows, 128) * nfb;  // items are rb-major
-    prof_begin(h, SCFGP_FAM_BACKWARD, c.st);
-    if (h->use_tma)
-      k_backward_tma<<<nitems, TMA_THREADS, TMA_SMEM_BYTES, c.st>>>(c.mapPhi, c.mapPsi, h->mapA2, h->mapB2, c.Phi,
-                                                                    h->ldk, rows, K, J, h->dy + r0, h->gmu + r0,
-                                                                    h->pbar, h->alpha, c.Zbar, h->ldj, c.slots,
-                                                                    h->bwd.d);
-    else
-      k_backward<<<nitems, CfgBig::NT, smem, c.st>>>(c.Phi, c.Psi, h->ldk, rows, K, J, h->A2, h->B2, h->ldk,
-                                                     h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj,
-                                                     c.slots, h->bwd.d);
-    prof_end(h, SCFGP_FAM_BACKWARD, c.st);
-    CKL();
+    if (!emu_on) {
+      prof_begin(h, SCFGP_FAM_BACKWARD, c.st);
+      if (h->use_tma)
+        k_backward_tma<<<nitems, TMA_THREADS, TMA_SMEM_BYTES, c.st>>>(c.mapPhi, c.mapPsi, h->mapA2, h->mapB2, c.Phi,
+                                                                      h->ldk, rows, K, J, h->dy + r0, h->gmu + r0,
+                                                                      h->pbar, h->alpha, c.Zbar, h->ldj, c.slots,
+                                                                      h->bwd.d);
+      else
+        k_backward<<<nitems, CfgBig::NT, smem, c.st>>>(c.Phi, c.Psi, h->ldk, rows, K, J, h->A2, h->B2, h->ldk,
+                                                       h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj,
+                                                       c.slots, h->bwd.d);
+      prof_end(h, SCFGP_FAM_BACKWARD, c.st);
+      CKL();
+    }
     // dW += XcT . Zbar
     if (h->xvec == 2)
       rc = launch_gemm<CfgWide, false, false, 2, 2>(h, Xc, D, D, c.Zbar, h->ldj, J, c.dW, h->ldj, 1.0, 1.0, h->dw,
@@ -1106,7 +1395,7 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
   int rc;
   if ((rc = unpack_and_upload(h, params))) return rc;
   const int K = h->K;
-  const int nkb = cdiv(K, 128);
+  const int nkb = h->vparts;
   const int xvec = (((uintptr_t)dXs % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
   if ((rc = fork_streams(h))) return rc;
   long long ci = 0;
@@ -1114,7 +1403,12 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
     Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, T - r0);
     if ((rc = run_features(h, c, dXs + r0 * h->D, xvec, rows, nullptr, nullptr))) return rc;
-    if ((rc = run_tgemm(h, c, rows))) return rc;
+    if (h->prec == SCFGP_PREC_EMU_I8) {
+      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, nullptr, nullptr, 1.0 / h->s2, nullptr, 0, c.digR,
+                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0)))
+        return rc;
+      if ((rc = emu_tgemm(h, c, rows))) return rc;
+    } else if ((rc = run_tgemm(h, c, rows))) return rc;
     k_pred_finish<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->tau,
                                                 dmu + r0, dstd + r0);
     CKL();
@@ -1133,6 +1427,8 @@ int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long 
     CK(cudaMemcpy2DAsync(h->Li, h->ldk * sizeof(double), Li, (size_t)K * sizeof(double),
                          (size_t)K * sizeof(double), K, cudaMemcpyHostToDevice, h->stream));
     h->have_factors = true;
+    int rcl;
+    if (h->prec == SCFGP_PREC_EMU_I8 && (rcl = emu_prepare_li(h))) return rcl;
   }
   double *dXs = nullptr, *dout = nullptr;
   CK(cudaMalloc((void**)&dXs, (size_t)T * h->D * sizeof(double)));
@@ -1208,6 +1504,47 @@ int scfgp_dbg_gemm(int device, int layout, int m, int n, int k, const double* A,
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
   for (int4* p : h->to_free) cudaFree(p);
   h->to_free.clear();
+  if (rc) return rc;
+  return e == cudaSuccess ? SCFGP_OK : SCFGP_ERR_CUDA;
+}
+
+int scfgp_dbg_emu_gemm(int device, int digits, int m, int n, int k, const double* A, const double* B, double* C) {
+  if (m <= 0 || n <= 0 || k <= 0 || !A || !B || !C || digits < 4 || digits > 8) return SCFGP_ERR_ARG;
+  scfgp_handle tmp;
+  scfgp_handle* h = &tmp;
+  h->device = device;
+  h->ks = digits;
+  CK(cudaSetDevice(device));
+  const long long kp = (k + 15) / 16 * 16;
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr, *sc = nullptr;
+  int8_t *gA = nullptr, *gB = nullptr;
+  CK(cudaMalloc((void**)&dA, (size_t)m * k * sizeof(double)));
+  CK(cudaMalloc((void**)&dB, (size_t)n * k * sizeof(double)));
+  CK(cudaMalloc((void**)&dC, (size_t)m * n * sizeof(double)));
+  CK(cudaMalloc((void**)&sc, (size_t)2 * (m + n) * sizeof(double)));
+  CK(cudaMalloc((void**)&gA, (size_t)digits * m * kp));
+  CK(cudaMalloc((void**)&gB, (size_t)digits * n * kp));
+  CK(cudaMemcpy(dA, A, (size_t)m * k * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice));
+  double *as = sc, *ai = sc + m, *bs = sc + 2 * m, *bi = bs + n;
+  emu::k_rowscale<<<m, 128>>>(dA, k, nullptr, 0, nullptr, m, k, 0, as, ai);
+  emu::k_rowscale<<<n, 128>>>(dB, k, nullptr, 0, nullptr, n, k, 0, bs, bi);
+  int rc = emu_digits_rows(h, nullptr, dA, k, m, k, nullptr, ai, 1.0, nullptr, 0, gA, kp, (long long)m * kp, 0);
+  if (!rc) rc = emu_digits_rows(h, nullptr, dB, k, n, k, nullptr, bi, 1.0, nullptr, 0, gB, kp, (long long)n * kp, 0);
+  CUtensorMap ma, mb;
+  if (!rc) rc = make_tmap_digits(h, &ma, gA, k, m, kp, digits, umma::TM);
+  if (!rc) rc = make_tmap_digits(h, &mb, gB, k, n, kp, digits, umma::TN);
+  if (!rc) {
+    const dim3 grid(cdiv(n, umma::TN), cdiv(m, umma::TM));
+    EMU_KS_SWITCH(digits, {
+      rc = set_emu_attrs<KS>(h);
+      if (!rc)
+        emu::k_gemm_i8_dbg<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM>>>(ma, mb, m, n, k, as, bs, dC, n);
+    });
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(C, dC, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(sc); cudaFree(gA); cudaFree(gB);
   if (rc) return rc;
   return e == cudaSuccess ? SCFGP_OK : SCFGP_ERR_CUDA;
 }

@@ -30,7 +30,7 @@ class _DevBuf:
 
 class Engine:
     def __init__(self, D: int, S: int, M: int, fftype: int = _lib.FF_PHASE, device: int = 0,
-                 chunk_rows: int | None = None):
+                 chunk_rows: int | None = None, precision: str | None = None):
         self.lib = _lib.load()
         self.D, self.S, self.M = int(D), int(S), int(M)
         self.J = self.S + self.M
@@ -47,6 +47,8 @@ class Engine:
             raise ScfgpError(f"scfgp_create failed ({rc}): {msg}")
         if chunk_rows:
             self._check(self.lib.scfgp_set_chunk_rows(self._h, int(chunk_rows)))
+        if precision is not None:
+            self.set_precision(precision)
         self.N = 0
         self._keep = None   # keeps borrowed torch tensors alive
         self._red = {}
@@ -89,6 +91,24 @@ class Engine:
         f = [C.c_float() for _ in range(4)]
         self.lib.scfgp_last_pass_ms(self._h, *[C.byref(x) for x in f])
         return tuple(float(x.value) for x in f)
+
+    def set_precision(self, precision: str):
+        """'fp64' (FP64 tensor path) or 'emu' / 'emu<digits>' (float64 emulated on the int8
+        tensor cores with 4..8 base-128 digits; 'emu' = 6)."""
+        p = str(precision).lower()
+        if p == "fp64":
+            mode, digits = _lib.PREC_FP64, 0
+        elif p.startswith("emu"):
+            mode, digits = _lib.PREC_EMU_I8, int(p[3:] or 0)
+        else:
+            raise ValueError(f"unknown precision {precision!r}")
+        self._check(self.lib.scfgp_set_precision(self._h, mode, digits))
+
+    @property
+    def precision(self) -> str:
+        m, d = C.c_int(), C.c_int()
+        self.lib.scfgp_get_precision(self._h, C.byref(m), C.byref(d))
+        return "fp64" if m.value == _lib.PREC_FP64 else f"emu{d.value}"
 
     def set_streams(self, n: int):
         self._check(self.lib.scfgp_set_streams(self._h, int(n)))
@@ -255,3 +275,16 @@ def dbg_factor(A, device: int = 0):
     if rc:
         raise ScfgpError(f"scfgp_dbg_factor rc={rc}")
     return L, Li, int(info.value)
+
+
+def dbg_emu_gemm(A, B, digits: int = 6, device: int = 0):
+    """C = A . B^T through digit extraction + the int8 tensor-core mainloop."""
+    lib = _lib.load()
+    A, B = _lib.as_f64(A), _lib.as_f64(B)
+    m, k = A.shape
+    n = B.shape[0]
+    Cm = np.zeros((m, n))
+    rc = lib.scfgp_dbg_emu_gemm(device, int(digits), m, n, k, _lib.dptr(A), _lib.dptr(B), _lib.dptr(Cm))
+    if rc:
+        raise ScfgpError(f"scfgp_dbg_emu_gemm rc={rc}")
+    return Cm
