@@ -29,18 +29,34 @@ __device__ __forceinline__ double pow2_ceil(double x) {
 // neighbours so that both land in the same epilogue thread
 __device__ __forceinline__ int trig_perm(int j, int J) { return j < J ? 2 * j : 2 * (j - J) + 1; }
 
-// balanced base-128 digits of q (|q| <= 2^(7 KS - 1)); digit[0] most significant, |digit| <= 64
+// Balanced base-128 digits of q (|q| <= 2^(7 KS - 1)); digit 0 most significant, |digit| <= 64.
+// Adding 64 at every digit position below the top one (the constant `kDigitBias`) turns the
+// balanced digits into plain 7-bit fields u_i of q' = q + bias with digit_i = u_i - 64; the top
+// digit is q' >> 7 (KS - 1).  digit_byte<KS>(q', i) returns u_i (i >= 1) or the top digit's
+// two's-complement byte (i == 0); fix_bytes turns four packed u fields into four int8 digits.
 template <int KS>
-__device__ __forceinline__ void digits_of(long long q, int (&d)[KS]) {
-  const long long lim = 1ll << (7 * KS - 1);
-  q = q > lim ? lim : (q < -lim ? -lim : q);
+__device__ __forceinline__ long long digit_bias() {
+  long long b = 0;
 #pragma unroll
-  for (int i = KS - 1; i >= 1; --i) {
-    const int lo = (int)((q + 64) & 127) - 64;
-    d[i] = lo;
-    q = (q - lo) >> 7;
-  }
-  d[0] = (int)q;
+  for (int t = 0; t < KS - 1; ++t) b += 64ll << (7 * t);
+  return b;
+}
+template <int KS>
+__device__ __forceinline__ long long biased_q(double x) {
+  const long long lim = 1ll << (7 * KS - 1);
+  long long q = llrint(x);
+  q = q > lim ? lim : (q < -lim ? -lim : q);
+  return q + digit_bias<KS>();
+}
+template <int KS>
+__device__ __forceinline__ uint32_t digit_byte(long long qp, int i) {
+  const int shift = 7 * (KS - 1 - i);
+  if (i == 0) return (uint32_t)(qp >> shift) & 0xffu;
+  return (uint32_t)((unsigned long long)qp >> shift) & 127u;
+}
+__device__ __forceinline__ uint32_t fix_bytes(uint32_t w) {  // per byte: u -> (u - 64) mod 256, u in [0, 127]
+  const uint32_t t = w ^ 0x40404040u;
+  return t | ((t & 0x40404040u) << 1);
 }
 
 // ------------------------------------------------------------------------------------
@@ -101,14 +117,15 @@ __global__ void k_scale_from_bits(const unsigned long long* __restrict__ gmax, d
 // ------------------------------------------------------------------------------------
 // digits of a row-major matrix, contraction index = column (K-major operand)
 //   x = src[r][c] * rowmul[r] * rowinv[p(r)] * ginv * *ginv_ptr  (absent factors = 1; |x| <= 1)
-//   dst[s][p(r)][col_off + c] = digit s of x;   one thread = 16 consecutive columns
+//   dst[s][p(r)][col_off + c] = digit s of x;   one thread = 4 consecutive columns (32 bytes in,
+//   4 bytes per digit out: both fully coalesced); columns [cols, round_up(cols, 16)) are zeroed
 // ------------------------------------------------------------------------------------
 template <int KS>
-__global__ void k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols,
-                              const double* __restrict__ rowmul, const double* __restrict__ rowinv, double ginv,
-                              const double* __restrict__ ginv_ptr, int perm_J, int8_t* __restrict__ dst,
-                              long long pitch, long long slice_stride, int col_off) {
-  const int ngroups = (cols + 15) / 16;
+__global__ void __launch_bounds__(256)
+k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols, const double* __restrict__ rowmul,
+              const double* __restrict__ rowinv, double ginv, const double* __restrict__ ginv_ptr, int perm_J,
+              int8_t* __restrict__ dst, long long pitch, long long slice_stride, int col_off) {
+  const int ngroups = (cols + 15) / 16 * 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)rows * ngroups) return;
   const int r = (int)(idx / ngroups), g = (int)(idx % ngroups);
@@ -117,26 +134,29 @@ __global__ void k_digits_rows(const double* __restrict__ src, long long ld, int 
   if (ginv_ptr) mult *= *ginv_ptr;
   if (rowmul) mult *= rowmul[r];
   if (rowinv) mult *= rowinv[orow];
-  const double* p = src + (long long)r * ld + g * 16;
-  uint32_t packed[KS][4];
+  const double* p = src + (long long)r * ld + g * 4;
+  double x[4];
+  if (g * 4 + 3 < cols && ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *reinterpret_cast<const double2*>(p + 2);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+  } else {
 #pragma unroll
-  for (int s = 0; s < KS; ++s)
-#pragma unroll
-    for (int w = 0; w < 4; ++w) packed[s][w] = 0;
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const int c = g * 16 + e;
-    const double x = c < cols ? p[e] : 0.0;
-    int d[KS];
-    digits_of<KS>(llrint(x * mult), d);
-#pragma unroll
-    for (int s = 0; s < KS; ++s) packed[s][e >> 2] |= (uint32_t)(d[s] & 0xff) << (8 * (e & 3));
+    for (int e = 0; e < 4; ++e) x[e] = (g * 4 + e < cols) ? p[e] : 0.0;
   }
-  int8_t* o = dst + (long long)orow * pitch + col_off + g * 16;
+  uint32_t packed[KS];
 #pragma unroll
-  for (int s = 0; s < KS; ++s)
-    *reinterpret_cast<uint4*>(o + (long long)s * slice_stride) =
-        make_uint4(packed[s][0], packed[s][1], packed[s][2], packed[s][3]);
+  for (int s = 0; s < KS; ++s) packed[s] = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const long long qp = biased_q<KS>(x[e] * mult);
+#pragma unroll
+    for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
+  }
+  int8_t* o = dst + (long long)orow * pitch + col_off + g * 4;
+  *reinterpret_cast<uint32_t*>(o) = packed[0];
+#pragma unroll
+  for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * slice_stride) = fix_bytes(packed[s]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -166,15 +186,18 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
       x = src[(long long)r * ld + c] * base;
       if (rowmul) x *= rowmul[r];
     }
-    int d[KS];
-    digits_of<KS>(llrint(x), d);
+    const long long qp = biased_q<KS>(x);
 #pragma unroll
-    for (int s = 0; s < KS; ++s) packed[s][e >> 2] |= (uint32_t)(d[s] & 0xff) << (8 * (e & 3));
+    for (int s = 0; s < KS; ++s) packed[s][e >> 2] |= digit_byte<KS>(qp, s) << (8 * (e & 3));
   }
   if (c < cols) {
     int8_t* o = dst + (long long)c * pitch + r0;
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
+      if (s > 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) packed[s][w] = fix_bytes(packed[s][w]);
+      }
       uint4* q = reinterpret_cast<uint4*>(o + (long long)s * slice_stride);
       q[0] = make_uint4(packed[s][0], packed[s][1], packed[s][2], packed[s][3]);
       q[1] = make_uint4(packed[s][4], packed[s][5], packed[s][6], packed[s][7]);

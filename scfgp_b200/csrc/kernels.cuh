@@ -67,6 +67,47 @@ k_gemm(const double* __restrict__ A, long long lda, int a_rows,
 }
 
 // ------------------------------------------------------------------------------------
+// dW partials:  part[split][d][j] += sum over the split's rows of X[r,d] Zbar[r,j]   (A.5)
+//   The D x J output has only a handful of tiles, so the row reduction is cut into
+//   gridDim.y splits (one partial buffer each; summed in fixed order afterwards).
+//   items: (d block of 64, j block of 128)
+// ------------------------------------------------------------------------------------
+template <int AVEC>
+__global__ void __launch_bounds__(TileCfg<64, 128, 32, 32, 3>::NT, 1)
+k_dw_splitk(const double* __restrict__ X, long long ldx, int D, const double* __restrict__ Z, long long ldz, int J,
+            int rows, int split_len, double* __restrict__ part, long long ldc, long long part_stride,
+            const int4* __restrict__ items) {
+  using Cfg = TileCfg<64, 128, 32, 32, 3>;
+  extern __shared__ __align__(16) double smem[];
+  const int4 it = items[blockIdx.x];
+  const int m0 = it.x * Cfg::BM, n0 = it.y * Cfg::BN;
+  const int k0 = blockIdx.y * split_len;
+  const int depth = min(split_len, rows - k0);
+  if (depth <= 0) return;
+  double acc[Cfg::MI][Cfg::NI][2];
+  zero_acc<Cfg>(acc);
+  IdentMap am{m0, D}, bm{n0, J};
+  gemm_mainloop<Cfg, false, false, AVEC, 2>(acc, X + (long long)k0 * ldx, ldx, am, Z + (long long)k0 * ldz, ldz, bm,
+                                            depth, smem);
+  double* C = part + (long long)blockIdx.y * part_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i) {
+    const int r = m0 + wm0 + 8 * i + g;
+    if (r >= D) continue;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = n0 + wn0 + 8 * j + 2 * t + e;
+        if (c < J) C[(long long)r * ldc + c] += acc[i][j][e];
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // (a) feature map  Phi = s*[cos(X.W + phi) | sin(X.W + phi)]        SCFGP.py:98-102
 //   X chunk (rows x D, row-major), Wt (J x D row-major, ld = ldw), phi (J)
 //   Phi slab (rows x K, ld = ldp);  optional Psi = rowscale[n] * Phi

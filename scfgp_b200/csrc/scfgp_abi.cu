@@ -22,6 +22,7 @@ namespace {
 constexpr double kEps = 1e-6;  // jitter, SCFGP/SCFGP.py:93
 constexpr int kColSplit = 64;  // row splits of the column-sum kernels (parallelism: ceil(K/256) x 64 CTAs)
 constexpr int kSeedBlocks = 296;
+constexpr int kDwSplit = 16;   // row splits of the dW = XT.Zbar contraction (partial buffers per chunk stream)
 
 struct ItemList {
   int4* d = nullptr;
@@ -286,6 +287,10 @@ int set_kernel_attrs(scfgp_handle* h) {
   CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SmemSize<CfgBig, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+  CK(cudaFuncSetAttribute(k_dw_splitk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgWide, false, false>::BYTES));
+  CK(cudaFuncSetAttribute(k_dw_splitk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgWide, false, false>::BYTES));
   CK(cudaFuncSetAttribute(k_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_tgemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_backward_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
@@ -416,7 +421,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
       (std::max<long long>(std::max(std::max(2 * kSeedBlocks, (int)bw.size()), emu_bwd_ctas), 256) + 1) / 2 * 2;
   const size_t KK = (size_t)K * h->ldk, DJ = (size_t)h->D * h->ldj;
   if ((rc = dalloc(h, &h->acc_all, KK * h->ns))) return rc;
-  if ((rc = dalloc(h, &h->dW_all, DJ * h->ns))) return rc;
+  if ((rc = dalloc(h, &h->dW_all, DJ * kDwSplit * h->ns))) return rc;
   if ((rc = dalloc(h, &h->colpart_all, (size_t)kColSplit * K * h->ns))) return rc;
   if ((rc = dalloc(h, &h->slots_all, (size_t)h->slot_stride * h->ns))) return rc;
   for (int i = 0; i < h->ns; ++i) {
@@ -426,7 +431,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
     if ((rc = dalloc(h, &c.Zbar, (size_t)R * h->ldj))) return rc;
     if ((rc = dalloc(h, &c.vpart, (size_t)std::max(nkb, h->vparts) * R))) return rc;
     c.acc = h->acc_all + KK * i;
-    c.dW = h->dW_all + DJ * i;
+    c.dW = h->dW_all + DJ * kDwSplit * i;
     c.colpart = h->colpart_all + (size_t)kColSplit * K * i;
     c.slots = h->slots_all + (size_t)h->slot_stride * i;
     if (h->use_tma) {
@@ -571,7 +576,7 @@ int run_tgemm(scfgp_handle* h, Ctx& c, int rows) {
 int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
                     const double* rowmul, const double* rowinv, double ginv, const double* ginv_ptr, int permJ,
                     int8_t* dst, long long pitch, long long slice_stride, int col_off) {
-  const long long total = (long long)rows * cdiv(cols, 16);
+  const long long total = (long long)rows * (cdiv(cols, 16) * 4);
   EMU_KS_SWITCH(h->ks, emu::k_digits_rows<KS><<<cdiv(total, 256), 256, 0, st>>>(
                            src, ld, rows, cols, rowmul, rowinv, ginv, ginv_ptr, permJ, dst, pitch, slice_stride, col_off));
   CKL();
@@ -1189,7 +1194,7 @@ int scfgp_eval_pass3(scfgp_handle* h) {
   if ((rc = fork_streams(h))) return rc;
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
-    CK(cudaMemsetAsync(c.dW, 0, DJ * sizeof(double), c.st));
+    CK(cudaMemsetAsync(c.dW, 0, DJ * kDwSplit * sizeof(double), c.st));
     CK(cudaMemsetAsync(c.colpart, 0, (size_t)kColSplit * K * sizeof(double), c.st));
     CK(cudaMemsetAsync(c.slots, 0, (size_t)h->slot_stride * sizeof(double), c.st));
   }
@@ -1225,19 +1230,24 @@ int scfgp_eval_pass3(scfgp_handle* h) {
       prof_end(h, SCFGP_FAM_BACKWARD, c.st);
       CKL();
     }
-    // dW += XcT . Zbar
-    if (h->xvec == 2)
-      rc = launch_gemm<CfgWide, false, false, 2, 2>(h, Xc, D, D, c.Zbar, h->ldj, J, c.dW, h->ldj, 1.0, 1.0, h->dw,
-                                                    rows, c.st, true);
-    else
-      rc = launch_gemm<CfgWide, false, false, 1, 2>(h, Xc, D, D, c.Zbar, h->ldj, J, c.dW, h->ldj, 1.0, 1.0, h->dw,
-                                                    rows, c.st, true);
-    if (rc) return rc;
+    // dW partials += XcT . Zbar, the row reduction split over kDwSplit CTAs per tile
+    {
+      const int split_len = cdiv(cdiv(rows, kDwSplit), 16) * 16;
+      const dim3 grid(h->dw.count, kDwSplit);
+      const size_t dsm = SmemSize<CfgWide, false, false>::BYTES;
+      if (h->xvec == 2)
+        k_dw_splitk<2><<<grid, CfgWide::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
+                                                         (long long)DJ, h->dw.d);
+      else
+        k_dw_splitk<1><<<grid, CfgWide::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
+                                                         (long long)DJ, h->dw.d);
+      CKL();
+    }
     k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, J, nullptr, c.colpart, K);
     CKL();
   }
   if ((rc = join_streams(h))) return rc;
-  k_sum_parts<<<cdiv((long long)DJ, 256), 256, 0, h->stream>>>(h->dW_all, (long long)DJ, h->ns, (int)DJ, dW);
+  k_sum_parts<<<cdiv((long long)DJ, 256), 256, 0, h->stream>>>(h->dW_all, (long long)DJ, h->ns * kDwSplit, (int)DJ, dW);
   CKL();
   k_sum_parts<<<cdiv(J, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, J, dphi);
   CKL();
