@@ -83,8 +83,8 @@ int scfgp_set_streams(scfgp_handle* h, int n);
  *   SCFGP_PREC_FP64   : FP64 tensor path (DMMA.8x8x4), the default.
  *   SCFGP_PREC_EMU_I8 : float64 emulated on the int8 tensor cores (tcgen05.mma kind::i8,
  *                       exact int32 accumulation in tensor memory).  Operands are cut into
- *                       `digits` signed base-128 digits (4..8; 0 = default 6, i.e. 41
- *                       fractional bits of each operand row's maximum).  Feature map, Cholesky,
+ *                       `digits` signed base-256 digits (4..8; 0 = default 5, i.e. 38
+ *                       fractional bits of each operand row's power-of-two scale).  Feature map, Cholesky,
  *                       triangular inverse and the small dense backward stay in true FP64.
  * Default at create time: environment SCFGP_PRECISION = "fp64" | "emu" | "emu<digits>". */
 enum { SCFGP_PREC_FP64 = 0, SCFGP_PREC_EMU_I8 = 1 };

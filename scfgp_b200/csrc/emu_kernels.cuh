@@ -5,7 +5,7 @@
 //   k_tgemm_i8     v_n = |Phi_n LiT|^2                   SCFGP.py:112
 //   k_backward_i8  Phibar = [Phi | Psi'].[2Abar | 2 sigma B]T, fused trig derivative   A.5
 // All scales are powers of two, so scaling is exact; the only approximation is the
-// truncation of each operand to 7*KS-1 fractional bits of its row (or global) maximum.
+// truncation of each operand to 8*KS-2 fractional bits of its row (or global) scale.
 #pragma once
 #include "umma_i8.cuh"
 #include "kernels.cuh"
@@ -17,47 +17,49 @@ using umma::TM;
 using umma::TN;
 using umma::KB;
 
-// smallest power of two >= x  (1 for x == 0 / non-finite input falls through to the caller's checks)
+// digit scale of a quantity bounded by x: the smallest power of two >= 2 x (2 for x == 0), so that
+// |value| / scale <= 1/2 and the leading digit stays within +-64
 __device__ __forceinline__ double pow2_ceil(double x) {
-  if (!(x > 0.0)) return 1.0;
+  if (!(x > 0.0)) return 2.0;
   int e;
   const double m = frexp(x, &e);  // x = m 2^e, m in [0.5, 1)
-  return ldexp(1.0, m == 0.5 ? e - 1 : e);
+  return ldexp(1.0, (m == 0.5 ? e - 1 : e) + 1);
 }
 
 // row permutation of the backward B operand: cos and sin halves of a feature become
 // neighbours so that both land in the same epilogue thread
 __device__ __forceinline__ int trig_perm(int j, int J) { return j < J ? 2 * j : 2 * (j - J) + 1; }
 
-// Balanced base-128 digits of q (|q| <= 2^(7 KS - 1)); digit 0 most significant, |digit| <= 64.
-// Adding 64 at every digit position below the top one (the constant `kDigitBias`) turns the
-// balanced digits into plain 7-bit fields u_i of q' = q + bias with digit_i = u_i - 64; the top
-// digit is q' >> 7 (KS - 1).  digit_byte<KS>(q', i) returns u_i (i >= 1) or the top digit's
-// two's-complement byte (i == 0); fix_bytes turns four packed u fields into four int8 digits.
+// Balanced base-256 digits of q (|q| <= 2^(8 KS - 2)); digit 0 most significant (|.| <= 64),
+// the others in [-128, 127].  Adding 128 at every digit position below the top one (the
+// constant digit_bias) turns the balanced digits into plain 8-bit fields u_i of q' = q + bias
+// with digit_i = u_i - 128, i.e. the int8 byte is u_i ^ 0x80; the top digit is q' >> 8 (KS - 1).
+// digit_byte<KS>(q', i) returns u_i (i >= 1) or the top digit's two's-complement byte (i == 0);
+// fix_bytes turns four packed u fields into four int8 digits.
+constexpr int DB = umma::DIGIT_BITS;
 template <int KS>
 __device__ __forceinline__ long long digit_bias() {
   long long b = 0;
 #pragma unroll
-  for (int t = 0; t < KS - 1; ++t) b += 64ll << (7 * t);
+  for (int t = 0; t < KS - 1; ++t) b += 128ll << (DB * t);
   return b;
 }
+// multiplier that maps |x| <= 1/2 (x already divided by its power-of-two scale) to |q| <= 2^(8 KS - 2)
+template <int KS>
+__device__ __forceinline__ double digit_mult() { return ldexp(1.0, DB * KS - 1); }
 template <int KS>
 __device__ __forceinline__ long long biased_q(double x) {
-  const long long lim = 1ll << (7 * KS - 1);
+  const long long lim = 1ll << (DB * KS - 2);
   long long q = llrint(x);
   q = q > lim ? lim : (q < -lim ? -lim : q);
   return q + digit_bias<KS>();
 }
 template <int KS>
 __device__ __forceinline__ uint32_t digit_byte(long long qp, int i) {
-  const int shift = 7 * (KS - 1 - i);
-  if (i == 0) return (uint32_t)(qp >> shift) & 0xffu;
-  return (uint32_t)((unsigned long long)qp >> shift) & 127u;
+  const int shift = DB * (KS - 1 - i);
+  return (uint32_t)((unsigned long long)(qp >> shift)) & 0xffu;
 }
-__device__ __forceinline__ uint32_t fix_bytes(uint32_t w) {  // per byte: u -> (u - 64) mod 256, u in [0, 127]
-  const uint32_t t = w ^ 0x40404040u;
-  return t | ((t & 0x40404040u) << 1);
-}
+__device__ __forceinline__ uint32_t fix_bytes(uint32_t w) { return w ^ 0x80808080u; }  // per byte: u -> u - 128
 
 // ------------------------------------------------------------------------------------
 // per-row power-of-two scales of [M1 | f2 * M2] (either may be absent)
@@ -130,7 +132,7 @@ k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols, 
   if (idx >= (long long)rows * ngroups) return;
   const int r = (int)(idx / ngroups), g = (int)(idx % ngroups);
   const int orow = perm_J > 0 ? trig_perm(r, perm_J) : r;
-  double mult = ldexp(1.0, 7 * KS - 1) * ginv;
+  double mult = digit_mult<KS>() * ginv;
   if (ginv_ptr) mult *= *ginv_ptr;
   if (rowmul) mult *= rowmul[r];
   if (rowinv) mult *= rowinv[orow];
@@ -163,45 +165,55 @@ k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols, 
 // digits of the TRANSPOSE of a row slab, contraction index = row (Gram operands)
 //   dst[s][c][r] = digit s of src[r][c] * rowmul[r] * ginv * *ginv_ptr ; rows beyond `rows`
 //   up to the 128-row tile boundary are written as zeros (they are inside the reduction)
-//   grid = (ceil(cols/64), ceil(rows/128)), 256 threads: thread = (column, 32 rows)
+//   grid = (ceil(cols/32), ceil(rows/128)), 256 threads.  Phase 1: lane = column, warp = 16
+//   rows (coalesced 256-byte reads, 16 independent loads per thread); the digit bytes are
+//   transposed through shared memory (row pitch 33 words: conflict-free both ways).
+//   Phase 2: lane = 4 rows, one (digit, column) per warp iteration: 128-byte coalesced writes.
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __launch_bounds__(256)
 k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, const double* __restrict__ rowmul,
               double ginv, const double* __restrict__ ginv_ptr, int8_t* __restrict__ dst, long long pitch,
               long long slice_stride) {
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int r0 = blockIdx.y * 128 + (threadIdx.x >> 6) * 32;
-  const double base = ldexp(1.0, 7 * KS - 1) * ginv * (ginv_ptr ? *ginv_ptr : 1.0);
-  uint32_t packed[KS][8];
+  __shared__ uint32_t sm[KS][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 128;
+  const int c = c0 + lane;
+  const double base = digit_mult<KS>() * ginv * (ginv_ptr ? *ginv_ptr : 1.0);
+  double x[16];
 #pragma unroll
-  for (int s = 0; s < KS; ++s)
-#pragma unroll
-    for (int w = 0; w < 8; ++w) packed[s][w] = 0;
-#pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    const int r = r0 + e;
-    double x = 0.0;
-    if (r < rows && c < cols) {
-      x = src[(long long)r * ld + c] * base;
-      if (rowmul) x *= rowmul[r];
-    }
-    const long long qp = biased_q<KS>(x);
-#pragma unroll
-    for (int s = 0; s < KS; ++s) packed[s][e >> 2] |= digit_byte<KS>(qp, s) << (8 * (e & 3));
+  for (int e = 0; e < 16; ++e) {
+    const int r = r0 + warp * 16 + e;
+    x[e] = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.0;
   }
-  if (c < cols) {
-    int8_t* o = dst + (long long)c * pitch + r0;
+  if (rowmul) {
 #pragma unroll
-    for (int s = 0; s < KS; ++s) {
-      if (s > 0) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) packed[s][w] = fix_bytes(packed[s][w]);
-      }
-      uint4* q = reinterpret_cast<uint4*>(o + (long long)s * slice_stride);
-      q[0] = make_uint4(packed[s][0], packed[s][1], packed[s][2], packed[s][3]);
-      q[1] = make_uint4(packed[s][4], packed[s][5], packed[s][6], packed[s][7]);
+    for (int e = 0; e < 16; ++e) {
+      const int r = r0 + warp * 16 + e;
+      if (r < rows) x[e] *= rowmul[r];
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t packed[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) packed[s] = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long qp = biased_q<KS>(x[4 * k + e] * base);
+#pragma unroll
+      for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
+    }
+    sm[0][lane][warp * 4 + k] = packed[0];
+#pragma unroll
+    for (int s = 1; s < KS; ++s) sm[s][lane][warp * 4 + k] = fix_bytes(packed[s]);
+  }
+  __syncthreads();
+  for (int p = warp; p < KS * 32; p += 8) {
+    const int s = p >> 5, cc = p & 31;
+    if (c0 + cc < cols)
+      *reinterpret_cast<uint32_t*>(dst + (long long)s * slice_stride + (long long)(c0 + cc) * pitch + r0 + 4 * lane) =
+          sm[s][cc][lane];
   }
 }
 
@@ -209,7 +221,7 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
 // Gram accumulation over one row chunk:  C[a][b] += sc * sum_r A[r,a] B[r,b]
 //   operands: transposed digits [KS][K][R]; items (a block of 128, b block of 64) cover the
 //   lower triangle (blocks that cross the diagonal are computed whole).
-//   sc = scale * *scale_ptr * 2^-12
+//   sc = scale * *scale_ptr * 2^-14
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __launch_bounds__(umma::THREADS, 1)
@@ -233,7 +245,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
     const int a = t.m0 + row;
     if (a < K) {
-      const double sc = scale * (scale_ptr ? *scale_ptr : 1.0) * (1.0 / 4096.0);
+      const double sc = scale * (scale_ptr ? *scale_ptr : 1.0) * umma::PROD_SCALE;
       double* crow = C + (long long)a * ldc + t.n0 + col0;
       const int nvalid = K - (t.n0 + col0);
 #pragma unroll
@@ -284,7 +296,7 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       const double tv = j < K ? v[c] * liscale[j] : 0.0;
       sq = fma(tv, tv, sq);
     }
-    const double sc = sA * (1.0 / 4096.0);
+    const double sc = sA * umma::PROD_SCALE;
     const int r = t.m0 + row;
     if (r < rows) vpart[(long long)(2 * nb + (col0 >> 5)) * ldv + r] = sq * sc * sc;
   }
@@ -293,7 +305,7 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 
 // ------------------------------------------------------------------------------------
 // backward tile: 128 rows x 32 features (64 permuted columns: cos/sin interleaved)
-//   Phibar = sA 2^-12 cscale[j] * sum_c [Phi|Psi'] digits . Cmat digits  + y pbarT + gmu alphaT
+//   Phibar = sA 2^-14 cscale[j] * sum_c [Phi|Psi'] digits . Cmat digits  + y pbarT + gmu alphaT
 //   Zbar = -Phibar_c * Phi_s + Phibar_s * Phi_c ;  slots[cta] += <Phibar, Phi>
 //   grid = (feature blocks of 32, row blocks of 128)
 // ------------------------------------------------------------------------------------
@@ -324,7 +336,7 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int r = t.m0 + row;
     double sacc = 0;
     if (r < rows) {
-      const double sc = sA * (1.0 / 4096.0);
+      const double sc = sA * umma::PROD_SCALE;
       const double yn = y[r], gm = gmu[r];
       const double* prow = Phi + (long long)r * ldp;
       const int f0 = (t.n0 + col0) >> 1;
@@ -375,7 +387,7 @@ k_gemm_i8_dbg(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
     const int r = t.m0 + row;
     if (r < M) {
-      const double sa = ascale[r] * (1.0 / 4096.0);
+      const double sa = ascale[r] * umma::PROD_SCALE;
       for (int c = 0; c < 32; ++c) {
         const int j = t.n0 + col0 + c;
         if (j < Nn) C[(long long)r * ldc + j] = v[c] * sa * bscale[j];

@@ -89,7 +89,7 @@ struct scfgp_handle {
 
   // emulated-FP64 path: precision mode, digit count and the replicated digit operands
   int prec = SCFGP_PREC_FP64;
-  int ks = 6;
+  int ks = 5;
   long long Kp = 0;            // K rounded up to 16 (digit row pitch / offset of the Psi' half)
   double s2 = 1.0;             // power of two >= s: scale of the Phi digits
   int8_t *digLi = nullptr;     // [KS][K][Kp]
@@ -354,7 +354,7 @@ int unpack_and_upload(scfgp_handle* h, const double* params) {
   {
     int e;
     const double m = std::frexp(h->s, &e);
-    h->s2 = std::ldexp(1.0, m == 0.5 ? e - 1 : e);  // power of two >= s = max |Phi|
+    h->s2 = std::ldexp(1.0, (m == 0.5 ? e - 1 : e) + 1);  // digit scale of Phi: power of two >= 2 s = 2 max |Phi|
   }
   CK(cudaMemcpyAsync(h->Wt, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->phi, h->phi_h.data(), (size_t)J * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -586,7 +586,7 @@ int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long lo
 int emu_digits_cols(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
                     const double* rowmul, double ginv, const double* ginv_ptr, int8_t* dst, long long pitch,
                     long long slice_stride) {
-  const dim3 grid(cdiv(cols, 64), cdiv(rows, 128));
+  const dim3 grid(cdiv(cols, 32), cdiv(rows, 128));
   EMU_KS_SWITCH(h->ks, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
                                                                     pitch, slice_stride));
   CKL();
@@ -830,7 +830,7 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
     if (!strncmp(e, "emu", 3)) {
       h->prec = SCFGP_PREC_EMU_I8;
       const int d = atoi(e + 3);
-      h->ks = (d >= 4 && d <= 8) ? d : 6;
+      h->ks = (d >= 4 && d <= 8) ? d : 5;
       h->R = 8192;
     }
   }
@@ -909,7 +909,7 @@ int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
 
 int scfgp_set_precision(scfgp_handle* h, int mode, int digits) {
   if (!h || (mode != SCFGP_PREC_FP64 && mode != SCFGP_PREC_EMU_I8)) return SCFGP_ERR_ARG;
-  if (digits == 0) digits = 6;
+  if (digits == 0) digits = 5;
   if (digits < 4 || digits > 8) { h->err = "digits must be 4..8"; return SCFGP_ERR_ARG; }
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());

@@ -1,12 +1,14 @@
 // Emulated-FP64 GEMM mainloop on the 5th-generation tensor cores (sm_100a):
 // tcgen05.mma.kind::i8 with int32 accumulators in tensor memory, operands staged by TMA.
 //
-// Number format ("slices").  A real matrix X with |X| <= scale is held as KS signed
-// base-128 digits  X ~= scale * 2^-(7 KS - 1) * sum_i d_i 128^(KS-1-i),  |d_i| <= 64  (int8).
-// A product  sum_c X[m,c] Y[n,c]  is then the integer sum
-//     sum_{i,j} 2^(-7(i+j)) * ( sum_c dX_i[m,c] dY_j[n,c] )   * scaleX scaleY 2^-12 ,
+// Number format ("digits").  A real matrix X with |X| <= scale/2 is held as KS signed
+// base-256 digits  X ~= scale * 2^-(8 KS - 1) * sum_i d_i 256^(KS-1-i),  d_i in [-128, 127]
+// (int8; the leading digit stays within +-64 because of the factor-2 headroom, which is what
+// keeps the balanced representation inside int8).  A product  sum_c X[m,c] Y[n,c]  is then
+//     sum_{i,j} 2^(-8(i+j)) * ( sum_c dX_i[m,c] dY_j[n,c] )   * scaleX scaleY 2^-14 ,
 // truncated to the "classes"  i + j = q < KS  (the dropped terms are below the digit
-// quantisation error).  Every class sum is an exact int32 (depth * (q+1) * 4096 < 2^31).
+// quantisation error).  Every class sum is an exact int32 (depth * (q+1) * 2^14 < 2^31, i.e.
+// reduction depths up to 16384 at 8 digits).
 //
 // Tile = 128 rows (TMEM lanes) x 64 columns.  Class q owns TMEM columns [64 q, 64 q + 64):
 // all KS classes are resident, so one pass over the contraction does every digit product.
@@ -20,7 +22,7 @@
 //   warp 1    : allocates TMEM, one lane issues the tcgen05.mma stream and commits each
 //               stage back to the producer (tcgen05.commit -> mbarrier)
 //   warps 2-9 : epilogue; tcgen05.ld the class accumulators, combine them in float64
-//               registers (2^-7q weights) and hand 32 columns of one row to a functor
+//               registers (2^-8q weights) and hand 32 columns of one row to a functor
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -34,6 +36,8 @@ namespace umma {
 constexpr int TM = 128;  // tile rows  (M of the instruction, TMEM lanes)
 constexpr int TN = 64;   // tile columns per class
 constexpr int KB = 64;   // contraction bytes per pipeline stage (one 64-byte swizzle atom)
+constexpr int DIGIT_BITS = 8;
+constexpr double PROD_SCALE = 1.0 / 16384.0;  // 2^-14: product of the two leading-digit weights 2^-7
 constexpr int THREADS = 320;
 constexpr int EPI_WARP0 = 2;
 constexpr int EPI_THREADS = 256;
@@ -44,7 +48,10 @@ struct Geo {
   static constexpr int B_BYTES = KS * TN * KB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (224 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+#ifndef UMMA_MAX_STAGES
+#define UMMA_MAX_STAGES 4
+#endif
+  static constexpr int STAGES = STAGES_RAW > UMMA_MAX_STAGES ? UMMA_MAX_STAGES : STAGES_RAW;
   static constexpr int CLASS_COLS = KS * TN;
   static constexpr int TMEM_COLS = CLASS_COLS <= 256 ? 256 : 512;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -223,7 +230,7 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
   }
 }
 
-// epilogue role (warps 2..9): returns v[c] = sum_q 2^(-7q) acc_q[row][col0 + c], c < 32
+// epilogue role (warps 2..9): returns v[c] = sum_q 2^(-8q) acc_q[row][col0 + c], c < 32
 template <int KS>
 __device__ __forceinline__ void epilogue_collect(const Pipe& p, uint32_t tmem_base, uint32_t acc_parity, int& row,
                                                  int& col0, double (&v)[32]) {
@@ -240,7 +247,7 @@ __device__ __forceinline__ void epilogue_collect(const Pipe& p, uint32_t tmem_ba
   for (int q = KS - 1; q >= 0; --q) {  // least significant class first
     uint32_t r[32];
     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN + col0), r);
-    const double w = __longlong_as_double((long long)(1023 - 7 * q) << 52);  // 2^(-7q)
+    const double w = __longlong_as_double((long long)(1023 - DIGIT_BITS * q) << 52);  // 2^(-8q)
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)r[c], w, v[c]);
   }

@@ -94,7 +94,7 @@ class Engine:
 
     def set_precision(self, precision: str):
         """'fp64' (FP64 tensor path) or 'emu' / 'emu<digits>' (float64 emulated on the int8
-        tensor cores with 4..8 base-128 digits; 'emu' = 6)."""
+        tensor cores with 4..8 base-256 digits; 'emu' = 5)."""
         p = str(precision).lower()
         if p == "fp64":
             mode, digits = _lib.PREC_FP64, 0

@@ -30,7 +30,7 @@ def main():
             ref = A @ B.T
             bound = np.abs(A).max(1)[:, None] * np.abs(B).max(1)[None, :] * k
             print("emu gemm digits", digits, (m, n, k), "err/bound", float((np.abs(Cm - ref) / bound).max()),
-                  "2^-7d", 2.0 ** (-7 * digits), flush=True)
+                  "2^-(8d-2)", 2.0 ** (-(8 * digits - 2)), flush=True)
 
     shapes = [(400, 13, 20, 50), (506, 13, 5, 50), (1000, 8, 4, 100), (333, 1, 100, 50), (2500, 10, 5, 50),
               (5000, 64, 16, 120), (9000, 8, 4, 100)]
@@ -39,7 +39,7 @@ def main():
         c0, g0, al0, Li0 = O.streaming_eval(h0, X, y, S, M, chunk=1024)
         Xs = np.random.default_rng(5).random((257, D))
         mu0, sd0 = O.literal_predict(h0, Xs, al0, Li0, S, M)
-        for prec in ("emu5", "emu6", "emu7"):
+        for prec in ("emu4", "emu5", "emu6"):
             eng = E.Engine(D, S, M, precision=prec)
             eng.set_data(X, y)
             c, g, al, Li = eng.eval(h0)
@@ -59,7 +59,7 @@ def main():
         N, D, S, M = 200_000, 64, 16, 1024
         X, y, h0 = synth.make_problem(N, D, S, M, seed=3)
         res = {}
-        for prec in ("fp64", "emu6", "emu5", "emu7"):
+        for prec in ("fp64", "emu5", "emu4", "emu6"):
             eng = E.Engine(D, S, M, precision=prec)
             eng.set_data(X, y)
             for rep in range(2):
@@ -70,7 +70,7 @@ def main():
             res[prec] = (c, g, al, Li)
             eng.close()
         c0, g0, al0, Li0 = res["fp64"]
-        for prec in ("emu5", "emu6", "emu7"):
+        for prec in ("emu4", "emu5", "emu6"):
             c, g, al, Li = res[prec]
             print("cfg4-geometry N=200000", prec, "vs fp64: cost rel", abs(c - c0) / abs(c0), "grad rel", rel(g, g0),
                   "grad max rel-to-max", float(np.abs(g - g0).max() / np.abs(g0).max()),

@@ -93,7 +93,7 @@ static int run_case(int M, int Nn, int C, int c_begin, int c_end, bool verify, i
   const long long pitch = (C + 15) / 16 * 16;
   std::vector<int8_t> hA((size_t)KS * M * pitch, 0), hB((size_t)KS * Nn * pitch, 0);
   std::mt19937 rng(1234 + M + Nn + C);
-  std::uniform_int_distribution<int> dist(-64, 64);
+  std::uniform_int_distribution<int> dist(-128, 127);
   for (int s = 0; s < KS; ++s) {
     for (int r = 0; r < M; ++r)
       for (int c = 0; c < C; ++c) hA[((size_t)s * M + r) * pitch + c] = (int8_t)dist(rng);
@@ -138,7 +138,7 @@ static int run_case(int M, int Nn, int C, int c_begin, int c_end, bool verify, i
             if (bad < 10) printf("  mismatch class %d row %d col %d: got %d want %lld\n", q, r, n, got, acc);
             ++bad;
           }
-          want += (double)acc * ldexp(1.0, -7 * q);
+          want += (double)acc * ldexp(1.0, -DIGIT_BITS * q);
         }
         const double got = out[(size_t)r * Nn + n];
         if (fabs(got - want) > 1e-9 * (1 + fabs(want))) {
@@ -188,6 +188,10 @@ int main(int argc, char** argv) {
     bad += run_case<4>(256, 64, 512, 0, 512, true, 0);
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
   } else {
+    // chip-level contention check: 33, 66, 132 CTAs (all resident at once) vs many waves
+    run_case<6>(128, 2080, 4160, 0, 4160, false, 5);
+    run_case<6>(256, 2080, 4160, 0, 4160, false, 5);
+    run_case<6>(512, 2080, 4160, 0, 4160, false, 5);
     run_case<6>(8192, 2080, 4160, 0, 4160, false, 5);
     run_case<5>(8192, 2080, 4160, 0, 4160, false, 5);
     run_case<7>(8192, 2080, 4160, 0, 4160, false, 5);
