@@ -52,7 +52,7 @@ class SCFGP(object):
 
     def __init__(self, rank=None, feature_size=None, fftype=None, msg=None, *, sparsity=None, nfeats=None,
                  evals=None, X_scaling_method='auto-inv-normal', y_scaling_method='auto-normal',
-                 verbose=None, device=0, chunk_rows=None):
+                 verbose=None, device=0, chunk_rows=None, precision=None):
         # G2 spelling: SCFGP(sparsity=20, nfeats=18, ...) (SCFGP.py:33-35);
         # G1 spelling: SCFGP(rank, feature_size, fftype, msg) (README.md:47-50).
         S = sparsity if sparsity is not None else (rank if rank is not None else 20)
@@ -70,6 +70,7 @@ class SCFGP(object):
         self.evals = _new_evals() if evals is None else evals
         self.device = device
         self.chunk_rows = chunk_rows
+        self.precision = precision     # None/'fp64' (FP64 tensor path) or 'emu'/'emu<digits>' (int8 tensor cores)
         self.N = self.D = -1
         self.X = self.y = self.params = self.alpha = self.Li = None
         self.train_func = self.train_iter_func = self.pred_func = None
@@ -109,7 +110,8 @@ class SCFGP(object):
                 raise ValueError("injected funcs were built for a different (D, S, M)")
             self._engine = engine
         if self._engine is None:
-            self._engine = Engine(self.D, self.S, self.M, self.fftype, self.device, self.chunk_rows)
+            self._engine = Engine(self.D, self.S, self.M, self.fftype, self.device, self.chunk_rows,
+                                  precision=self.precision)
         return self._engine
 
     def _upload(self, X, y):

@@ -1,0 +1,263 @@
+"""Parity of the emulated-FP64 path (int8 tensor cores, tcgen05.mma kind::i8 through the C
+ABI) against the CPU oracle and against the FP64 DMMA path.
+
+north_star's tolerances are cost <= 1e-6 relative, gradient / alpha / Li / predictions
+<= 1e-5.  The default of the emulated mode (5 base-256 digits = 38 fractional bits of every
+operand row's power-of-two scale) is held to bounds 10x tighter than that here; 6 digits
+to 1000x tighter."""
+import numpy as np
+import pytest
+
+from oracle import scfgp_oracle as O
+from scfgp_b200 import Engine, SCFGP, _lib, engine as E, synth, shard_bounds
+
+pytestmark = pytest.mark.gpu
+
+TOL = {  # precision -> (cost rtol, gradient block rtol / phase atol, alpha & Li & prediction atol)
+    "emu5": (1e-7, 1e-6, 1e-6),
+    "emu6": (1e-9, 1e-8, 1e-8),
+}
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def grad_blocks(D, S, M):
+    P = 3 + D * S + M * S + S + M
+    return {"abc": slice(0, 3), "l_f": slice(3, 3 + D * S), "r_f": slice(3 + D * S, 3 + D * S + M * S),
+            "phase": slice(3 + D * S + M * S, P)}
+
+
+def check_eval(eng, prec, h, X, y, S, M, chunk=1024):
+    ctol, gtol, atol = TOL[prec]
+    D = X.shape[1]
+    c, g, al, Li = eng.eval(h)
+    c0, g0, al0, Li0 = O.streaming_eval(h, X, y, S, M, chunk=chunk)
+    assert abs(c - c0) <= ctol * abs(c0), (c, c0)
+    for name, sl in grad_blocks(D, S, M).items():
+        if name == "phase":
+            assert np.abs(g[sl] - g0[sl]).max() <= gtol, name
+        else:
+            assert rel(g[sl], g0[sl]) <= gtol, (name, rel(g[sl], g0[sl]))
+    assert np.abs(al - al0).max() <= atol * max(1.0, np.abs(al0).max())
+    assert np.abs(Li - Li0).max() <= atol * max(1.0, np.abs(Li0).max())
+    assert np.abs(np.triu(Li, 1)).max() == 0.0
+    return c, g, al, Li
+
+
+# ------------------------------------------------------------------ digit GEMM (extraction + tcgen05 mainloop)
+@pytest.mark.parametrize("digits", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("mnk", [(128, 64, 64), (130, 70, 33), (300, 260, 200), (257, 129, 1000), (1, 1, 1),
+                                 (64, 512, 4160)])
+def test_digit_gemm_error_bound(digits, mnk):
+    """C = A.BT with per-row power-of-two scales.  Each operand entry is rounded to
+    2^-(8 digits) of its row scale (scale < 4 rowmax), i.e. an absolute error below
+    2^-(8 digits - 2) rowmax; both operands and the dropped digit products (i + j >= digits)
+    together stay below 4 * 2^-(8 digits - 2) * k * rowmax(A) * rowmax(B)."""
+    m, n, k = mnk
+    rng = np.random.default_rng(m + 3 * n + 7 * k + digits)
+    A = rng.standard_normal((m, k)) * np.exp(3 * rng.standard_normal((m, 1)))   # rows of very different size
+    B = rng.standard_normal((n, k)) * np.exp(3 * rng.standard_normal((n, 1)))
+    Cm = E.dbg_emu_gemm(A, B, digits)
+    bound = np.abs(A).max(1)[:, None] * np.abs(B).max(1)[None, :] * k
+    err = np.abs(Cm - A @ B.T) / bound
+    assert err.max() <= max(4 * 2.0 ** (-(8 * digits - 2)), 4e-16)
+
+
+def test_digit_gemm_exact_on_integers():
+    """Small integers are representable exactly in 4 digits: the product must be exact."""
+    rng = np.random.default_rng(0)
+    A = rng.integers(-100, 100, (200, 300)).astype(float)
+    B = rng.integers(-100, 100, (100, 300)).astype(float)
+    np.testing.assert_array_equal(E.dbg_emu_gemm(A, B, 4), A @ B.T)
+
+
+def test_digit_gemm_zero_rows_and_columns():
+    A = np.zeros((130, 70)); B = np.ones((65, 70))
+    A[3] = 2.5
+    Cm = E.dbg_emu_gemm(A, B, 5)
+    ref = A @ B.T
+    np.testing.assert_array_equal(Cm, ref)
+
+
+# ------------------------------------------------------------------ full evaluations (BASELINE configs)
+@pytest.mark.parametrize("prec", ["emu5", "emu6"])
+@pytest.mark.parametrize("name,shape", [
+    ("boston cfg1 (train split)", (400, 13, 5, 50)),
+    ("boston shipped-pickle shape", (400, 13, 20, 50)),
+    ("kin8nm cfg2", (5000, 8, 4, 100)),
+    ("abalone cfg3", (3133, 10, 5, 50)),
+    ("co2 cfg3", (2225, 1, 100, 50)),
+    ("ragged: odd D, odd J, N not a tile multiple", (777, 7, 3, 30)),
+    ("more than one 8192-row chunk", (9000, 8, 4, 100)),
+    ("tiny", (5, 2, 2, 2)),
+])
+def test_eval_matches_oracle(name, shape, prec):
+    N, D, S, M = shape
+    X, y, h = synth.make_problem(N, D, S, M, seed=N)
+    eng = Engine(D, S, M, precision=prec)
+    assert eng.precision == prec
+    eng.set_data(X, y)
+    c, g, al, Li = check_eval(eng, prec, h, X, y, S, M)
+    c2, g2, al2, Li2 = eng.eval(h, want_grad=False)          # train_func: same cost / factors
+    assert g2 is None and c2 == c
+    np.testing.assert_array_equal(al2, al)
+    eng.close()
+
+
+def test_eval_cfg4_geometry_reduced_rows():
+    N, D, S, M = 6000, 64, 16, 1024
+    X, y, h = synth.make_problem(N, D, S, M, seed=4)
+    eng = Engine(D, S, M, precision="emu5")
+    eng.set_data(X, y)
+    check_eval(eng, "emu5", h, X, y, S, M, chunk=2048)
+    eng.close()
+
+
+def test_modes_agree_on_one_engine():
+    """Switching the same handle between the FP64 tensor path and the emulated one."""
+    N, D, S, M = 3000, 8, 4, 100
+    X, y, h = synth.make_problem(N, D, S, M, seed=21)
+    eng = Engine(D, S, M)
+    assert eng.precision == "fp64"
+    eng.set_data(X, y)
+    c0, g0, al0, Li0 = eng.eval(h)
+    eng.set_precision("emu")
+    assert eng.precision == "emu5"
+    c1, g1, al1, Li1 = eng.eval(h)
+    eng.set_precision("fp64")
+    c2, g2, al2, Li2 = eng.eval(h)
+    assert c2 == c0
+    np.testing.assert_array_equal(g2, g0)
+    assert abs(c1 - c0) <= 1e-8 * abs(c0)
+    assert rel(g1, g0) <= 1e-6
+    with pytest.raises(ValueError):
+        eng.set_precision("emu3")
+    with pytest.raises(ValueError):
+        eng.set_precision("bf16")
+    eng.close()
+
+
+@pytest.mark.parametrize("chunk", [128, 384, 1024])
+def test_chunk_size_does_not_change_results(chunk):
+    N, D, S, M = 1500, 8, 4, 60
+    X, y, h = synth.make_problem(N, D, S, M, seed=6)
+    eng = Engine(D, S, M, chunk_rows=chunk, precision="emu5")
+    eng.set_data(X, y)
+    check_eval(eng, "emu5", h, X, y, S, M)
+    eng.close()
+
+
+def test_repeatable_bitwise():
+    """Integer accumulation + fixed-order float64 sums: evaluations repeat bit for bit."""
+    N, D, S, M = 20000, 8, 4, 100
+    X, y, h = synth.make_problem(N, D, S, M, seed=8)
+    eng = Engine(D, S, M, precision="emu5")
+    eng.set_data(X, y)
+    r1 = eng.eval(h)
+    r2 = eng.eval(h)
+    assert r1[0] == r2[0]
+    np.testing.assert_array_equal(r1[1], r2[1])
+    np.testing.assert_array_equal(r1[3], r2[3])
+    eng.close()
+
+
+# ------------------------------------------------------------------ prediction
+@pytest.mark.parametrize("shape,T", [((400, 13, 20, 50), 106), ((2000, 8, 4, 100), 3192), ((300, 3, 2, 10), 1)])
+def test_predict_matches_oracle(shape, T):
+    N, D, S, M = shape
+    X, y, h = synth.make_problem(N, D, S, M, seed=12)
+    Xs = np.random.default_rng(1).random((T, D))
+    c0, g0, al0, Li0 = O.streaming_eval(h, X, y, S, M)
+    eng = Engine(D, S, M, precision="emu5")
+    mu, sd = eng.predict(h, Xs, al0, Li0)                     # pred_func(Xs, alpha, Li)
+    mu0, sd0 = O.literal_predict(h, Xs, al0, Li0, S, M)
+    assert mu.shape == (T, 1) and sd.shape == (T,)
+    np.testing.assert_allclose(mu, mu0, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(sd, sd0, rtol=0, atol=1e-6)
+    eng.set_data(X, y)
+    eng.eval(h, want_grad=False)
+    mu2, sd2 = eng.predict(h, Xs)
+    np.testing.assert_allclose(mu2, mu0, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(sd2, sd0, rtol=0, atol=1e-6)
+    eng.close()
+
+
+def test_shipped_boston_model_predicts(golden):
+    D, S, M = int(golden["D"]), int(golden["S"]), int(golden["M"])
+    h, al, Li = golden["params"], golden["alpha"], golden["Li"]
+    Xs = np.random.default_rng(0).random((106, D))
+    eng = Engine(D, S, M, precision="emu5")
+    mu, sd = eng.predict(h, Xs, al, Li)
+    mu0, sd0 = O.literal_predict(h, Xs, al, Li, S, M)
+    np.testing.assert_allclose(mu, mu0, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(sd, sd0, rtol=0, atol=1e-6)
+    eng.close()
+
+
+# ------------------------------------------------------------------ sharding
+def test_shard_additivity():
+    """Two row shards through the phase API, reduce buffers summed on the host (what the
+    NCCL all-reduce does), against the single evaluation."""
+    import torch
+    N, D, S, M = 4100, 8, 4, 100
+    X, y, h = synth.make_problem(N, D, S, M, seed=14)
+    lib = _lib.load()
+    full = Engine(D, S, M, precision="emu5"); full.set_data(X, y)
+    c_full, g_full, al_full, Li_full = full.eval(h)
+    engs = []
+    for r in range(2):
+        lo, hi = shard_bounds(N, r, 2)
+        e = Engine(D, S, M, precision="emu5"); e.set_data(X[lo:hi], y[lo:hi], n_global=N)
+        engs.append(e)
+    hp = _lib.dptr(_lib.as_f64(h))
+    for e in engs:
+        e._check(lib.scfgp_eval_begin(e._h, hp, 1))
+
+    def allreduce(which):
+        bufs = [e._reduce_tensor(which) for e in engs]
+        tot = bufs[0] + bufs[1]
+        for b in bufs:
+            b.copy_(tot)
+        torch.cuda.synchronize()
+    for e in engs: e._check(lib.scfgp_eval_pass1(e._h))
+    allreduce(1)
+    for e in engs: e._check(lib.scfgp_eval_factor(e._h))
+    for e in engs: e._check(lib.scfgp_eval_pass2(e._h))
+    allreduce(2)
+    for e in engs: e._check(lib.scfgp_eval_backward(e._h))
+    for e in engs: e._check(lib.scfgp_eval_pass3(e._h))
+    allreduce(3)
+    outs = []
+    for e in engs:
+        cost = np.zeros(1); g = np.zeros(e.P); al = np.zeros(e.K); Li = np.zeros((e.K, e.K))
+        e._check(lib.scfgp_eval_finish(e._h, _lib.dptr(cost), _lib.dptr(g), _lib.dptr(al), _lib.dptr(Li)))
+        outs.append((cost[0], g, al, Li))
+    # the reduce buffers are identical after the all-reduce, so every rank finishes with the
+    # same bits; against the unsharded evaluation only the digit rounding differs (each rank
+    # scales its Psi digits by its own bound of |gv|)
+    assert outs[0][0] == outs[1][0]
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][3], outs[1][3])
+    assert abs(outs[0][0] - c_full) <= 1e-9 * abs(c_full)
+    assert rel(outs[0][1], g_full) <= 1e-7
+    for e in engs + [full]:
+        e.close()
+
+
+# ------------------------------------------------------------------ facade
+def test_facade_fit_in_emulated_mode():
+    rng = np.random.default_rng(3)
+    N, D = 506, 13
+    X = rng.lognormal(size=(N, D))
+    yraw = np.tanh(X @ rng.standard_normal(D) / 5) * 10 + 22 + rng.standard_normal(N)
+    tr = rng.choice(N, 400, replace=False); te = np.setdiff1d(np.arange(N), tr)
+    np.random.seed(7)
+    model = SCFGP(rank=5, feature_size=50, fftype="phase", msg=False, precision="emu")
+    model.fit(X[tr], yraw[tr, None], X[te], yraw[te, None], max_iter=40)
+    costs = model.evals["COST"][1]
+    assert costs[-1] < costs[0]
+    assert model.get_compiled_funcs().engine.precision == "emu5"
+    mu, sd = model.predict(X[te], yraw[te, None])
+    assert np.all(np.isfinite(mu)) and np.all(sd > 0)
