@@ -151,6 +151,13 @@ long long scfgp_launch_count(const scfgp_handle* h);
 int scfgp_last_pass_ms(const scfgp_handle* h, float* pass1, float* pass2, float* pass3,
                        float* dense);
 
+/* Optional launch trace: a CUDA event pair around every streaming-kernel launch (per chunk
+ * stream) from scfgp_set_tracing(h, 1) on; scfgp_trace_dump writes them as Chrome-trace JSON
+ * (one "thread" per chunk stream; open in chrome://tracing or Perfetto).  Developer tool:
+ * the events add a little serialisation, never time a benchmark with tracing on. */
+int scfgp_set_tracing(scfgp_handle* h, int on);
+int scfgp_trace_dump(scfgp_handle* h, const char* path);
+
 /* Optional kernel-family timing for the roofline report: CUDA events (on the handle's
  * stream) around every launch of ONE family; totals accumulate until the next
  * scfgp_set_profiling call and are collected at scfgp_eval_finish. */

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "scfgp_launch_count": (_ll, [_h]),
     "scfgp_last_pass_ms": (C.c_int, [_h, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),
+    "scfgp_set_tracing": (C.c_int, [_h, C.c_int]),
+    "scfgp_trace_dump": (C.c_int, [_h, C.c_char_p]),
     "scfgp_set_profiling": (C.c_int, [_h, C.c_int]),
     "scfgp_get_profile": (C.c_int, [_h, C.POINTER(C.c_double), C.POINTER(_ll)]),
     "scfgp_dbg_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),

@@ -224,7 +224,7 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
 //   sc = scale * *scale_ptr * 2^-14
 // ------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(umma::THREADS, 1)
+__global__ void __maxnreg__(umma::MAX_REGS)
 k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int depth, int K,
           const int2* __restrict__ items, double* __restrict__ C, long long ldc, double scale,
           const double* __restrict__ scale_ptr) {
@@ -240,23 +240,27 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
     umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, 0);
   } else {
-    int row, col0;
-    double v[32];
-    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
-    const int a = t.m0 + row;
-    if (a < K) {
-      const double sc = scale * (scale_ptr ? *scale_ptr : 1.0) * umma::PROD_SCALE;
-      double* crow = C + (long long)a * ldc + t.n0 + col0;
-      const int nvalid = K - (t.n0 + col0);
+    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, 0);
+    const int a = t.m0 + e.row;
+    const double sc = scale * (scale_ptr ? *scale_ptr : 1.0) * umma::PROD_SCALE;
+#pragma unroll 1
+    for (int h16 = 0; h16 < 2; ++h16) {
+      double v[16];
+      umma::epilogue_load16<KS>(e, e.col0 + 16 * h16, v);   // warp-collective: before any row guard
+      if (a < K) {
+        const int b0 = t.n0 + e.col0 + 16 * h16;
+        double* crow = C + (long long)a * ldc + b0;
+        const int nvalid = K - b0;
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        if (c + 1 < nvalid) {
-          double2 o = *reinterpret_cast<double2*>(crow + c);
-          o.x += sc * v[c];
-          o.y += sc * v[c + 1];
-          *reinterpret_cast<double2*>(crow + c) = o;
-        } else if (c < nvalid) {
-          crow[c] += sc * v[c];
+        for (int c = 0; c < 16; c += 2) {
+          if (c + 1 < nvalid) {
+            double2 o = *reinterpret_cast<double2*>(crow + c);
+            o.x += sc * v[c];
+            o.y += sc * v[c + 1];
+            *reinterpret_cast<double2*>(crow + c) = o;
+          } else if (c < nvalid) {
+            crow[c] += sc * v[c];
+          }
         }
       }
     }
@@ -270,7 +274,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 //   grid = (nblocks of 64 Li rows, row blocks of 128); deepest reduction (last nb) first
 // ------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(umma::THREADS, 1)
+__global__ void __maxnreg__(umma::MAX_REGS)
 k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int rows, int K,
            const double* __restrict__ liscale, double sA, double* __restrict__ vpart, long long ldv) {
   extern __shared__ uint8_t smem_raw[];
@@ -286,19 +290,22 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
     umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapLi, t, 0);
   } else {
-    int row, col0;
-    double v[32];
-    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
+    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, 0);
     double sq = 0;
+#pragma unroll 1
+    for (int h16 = 0; h16 < 2; ++h16) {
+      double v[16];
+      umma::epilogue_load16<KS>(e, e.col0 + 16 * h16, v);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int j = t.n0 + col0 + c;
-      const double tv = j < K ? v[c] * liscale[j] : 0.0;
-      sq = fma(tv, tv, sq);
+      for (int c = 0; c < 16; ++c) {
+        const int j = t.n0 + e.col0 + 16 * h16 + c;
+        const double tv = j < K ? v[c] * liscale[j] : 0.0;
+        sq = fma(tv, tv, sq);
+      }
     }
     const double sc = sA * umma::PROD_SCALE;
-    const int r = t.m0 + row;
-    if (r < rows) vpart[(long long)(2 * nb + (col0 >> 5)) * ldv + r] = sq * sc * sc;
+    const int r = t.m0 + e.row;
+    if (r < rows) vpart[(long long)(2 * nb + (e.col0 >> 5)) * ldv + r] = sq * sc * sc;
   }
   umma::pipe_teardown<KS>(p, tmem_base);
 }
@@ -310,7 +317,7 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 //   grid = (feature blocks of 32, row blocks of 128)
 // ------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(umma::THREADS, 1)
+__global__ void __maxnreg__(umma::MAX_REGS)
 k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, int rows, int J,
               int depth2, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
               long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
@@ -330,26 +337,31 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   if (warp < umma::EPI_WARP0) {
     umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapC, t, 0);
   } else {
-    int row, col0;
-    double v[32];
-    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
-    const int r = t.m0 + row;
+    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, 0);
+    const int r = t.m0 + e.row;
+    const bool rvalid = r < rows;
+    const double sc = sA * umma::PROD_SCALE;
+    const double yn = rvalid ? y[r] : 0.0, gm = rvalid ? gmu[r] : 0.0;
+    const double* prow = Phi + (long long)(rvalid ? r : 0) * ldp;
     double sacc = 0;
-    if (r < rows) {
-      const double sc = sA * umma::PROD_SCALE;
-      const double yn = y[r], gm = gmu[r];
-      const double* prow = Phi + (long long)r * ldp;
-      const int f0 = (t.n0 + col0) >> 1;
+#pragma unroll 1
+    for (int h16 = 0; h16 < 2; ++h16) {
+      double v[16];
+      const int pcol = e.col0 + 16 * h16;                 // permuted tile column of v[0]
+      umma::epilogue_load16<KS>(e, pcol, v);
+      if (rvalid) {
+        const int f0 = (t.n0 + pcol) >> 1;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int f = f0 + e;
-        if (f < J) {
-          const int pj = t.n0 + col0 + 2 * e;
-          const double pc = v[2 * e] * (cscale[pj] * sc) + yn * pbar[f] + gm * alpha[f];
-          const double ps = v[2 * e + 1] * (cscale[pj + 1] * sc) + yn * pbar[J + f] + gm * alpha[J + f];
-          const double phc = prow[f], phs = prow[J + f];
-          Zbar[(long long)r * ldz + f] = -pc * phs + ps * phc;
-          sacc += pc * phc + ps * phs;
+        for (int i = 0; i < 8; ++i) {
+          const int f = f0 + i;
+          if (f < J) {
+            const int pj = t.n0 + pcol + 2 * i;
+            const double pc = v[2 * i] * (cscale[pj] * sc) + yn * pbar[f] + gm * alpha[f];
+            const double ps = v[2 * i + 1] * (cscale[pj + 1] * sc) + yn * pbar[J + f] + gm * alpha[J + f];
+            const double phc = prow[f], phs = prow[J + f];
+            Zbar[(long long)r * ldz + f] = -pc * phs + ps * phc;
+            sacc += pc * phc + ps * phs;
+          }
         }
       }
     }
@@ -367,7 +379,7 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 
 // generic C[m][n] = sum_c A[m,c] B[n,c] with per-row scales on both sides (self-test hook)
 template <int KS>
-__global__ void __launch_bounds__(umma::THREADS, 1)
+__global__ void __maxnreg__(umma::MAX_REGS)
 k_gemm_i8_dbg(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int Nn,
               int depth, const double* __restrict__ ascale, const double* __restrict__ bscale, double* __restrict__ C,
               long long ldc) {
@@ -382,15 +394,18 @@ k_gemm_i8_dbg(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
     umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, 0);
   } else {
-    int row, col0;
-    double v[32];
-    umma::epilogue_collect<KS>(p, tmem_base, 0, row, col0, v);
-    const int r = t.m0 + row;
-    if (r < M) {
-      const double sa = ascale[r] * umma::PROD_SCALE;
-      for (int c = 0; c < 32; ++c) {
-        const int j = t.n0 + col0 + c;
-        if (j < Nn) C[(long long)r * ldc + j] = v[c] * sa * bscale[j];
+    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, 0);
+    const int r = t.m0 + e.row;
+#pragma unroll 1
+    for (int h16 = 0; h16 < 2; ++h16) {
+      double v[16];
+      umma::epilogue_load16<KS>(e, e.col0 + 16 * h16, v);
+      if (r < M) {
+        const double sa = ascale[r] * umma::PROD_SCALE;
+        for (int c = 0; c < 16; ++c) {
+          const int j = t.n0 + e.col0 + 16 * h16 + c;
+          if (j < Nn) C[(long long)r * ldc + j] = v[c] * sa * bscale[j];
+        }
       }
     }
   }

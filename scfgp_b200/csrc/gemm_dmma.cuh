@@ -18,7 +18,7 @@
 
 namespace scfgp {
 
-constexpr int BK = 16;  // reduction depth per pipeline stage (doubles)
+constexpr int BK = 16;  // default reduction depth per pipeline stage (doubles); TileCfg::BKT overrides it
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
   asm volatile(
@@ -45,10 +45,10 @@ __device__ __forceinline__ void cp_async_wait() {
 // Shared-memory tile of one operand for one stage.  The +4 padding makes the DMMA
 // fragment reads (8 rows x 4 k, one double per lane) hit 16 distinct 8-byte banks per
 // half warp in both storage orders (LD = 4 mod 16).
-template <int ROWS, bool KMAJOR>
+template <int ROWS, bool KMAJOR, int BKT = BK>
 struct TileLayout {
-  static constexpr int LD = KMAJOR ? (BK + 4) : (ROWS + 4);
-  static constexpr int SIZE = KMAJOR ? ROWS * LD : BK * LD;
+  static constexpr int LD = KMAJOR ? (BKT + 4) : (ROWS + 4);
+  static constexpr int SIZE = KMAJOR ? ROWS * LD : BKT * LD;
   __device__ __forceinline__ static int idx(int row, int k) { return KMAJOR ? row * LD + k : k * LD + row; }
 };
 
@@ -64,12 +64,12 @@ struct IdentMap {
 
 // Global -> shared copy of one ROWS x BK operand tile at reduction offset k0.
 // VEC = 2: 16-byte copies (needs 16B-aligned ptr and even ld); VEC = 1: 8-byte copies.
-template <int ROWS, bool KMAJOR, int VEC, int NT, class RowMap>
+template <int ROWS, bool KMAJOR, int VEC, int NT, int BKT, class RowMap>
 __device__ __forceinline__ void load_tile(double* __restrict__ smem, const double* __restrict__ ptr,
                                           long long ld, const RowMap& map, int k0, int depth, int tid) {
-  using L = TileLayout<ROWS, KMAJOR>;
+  using L = TileLayout<ROWS, KMAJOR, BKT>;
   if constexpr (KMAJOR) {
-    constexpr int CPR = BK / VEC;
+    constexpr int CPR = BKT / VEC;
     constexpr int TOTAL = ROWS * CPR;
 #pragma unroll
     for (int it = 0; it < (TOTAL + NT - 1) / NT; ++it) {
@@ -85,7 +85,7 @@ __device__ __forceinline__ void load_tile(double* __restrict__ smem, const doubl
     }
   } else {
     constexpr int CPR = ROWS / VEC;
-    constexpr int TOTAL = BK * CPR;
+    constexpr int TOTAL = BKT * CPR;
 #pragma unroll
     for (int it = 0; it < (TOTAL + NT - 1) / NT; ++it) {
       int c = it * NT + tid;
@@ -102,9 +102,9 @@ __device__ __forceinline__ void load_tile(double* __restrict__ smem, const doubl
   }
 }
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BKT_ = BK>
 struct TileCfg {
-  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, BKT = BKT_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int NWARPS = WARPS_M * WARPS_N;
   static constexpr int NT = NWARPS * 32;
@@ -113,7 +113,7 @@ struct TileCfg {
 
 template <class Cfg, bool AK, bool BKM>
 struct SmemSize {
-  static constexpr int STAGE = TileLayout<Cfg::BM, AK>::SIZE + TileLayout<Cfg::BN, BKM>::SIZE;
+  static constexpr int STAGE = TileLayout<Cfg::BM, AK, Cfg::BKT>::SIZE + TileLayout<Cfg::BN, BKM, Cfg::BKT>::SIZE;
   static constexpr int DOUBLES = STAGE * Cfg::STAGES;
   static constexpr size_t BYTES = (size_t)DOUBLES * sizeof(double);
 };
@@ -124,8 +124,9 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[Cfg::MI][Cfg::NI][2]
                                               const double* __restrict__ A, long long lda, const AMap& amap,
                                               const double* __restrict__ B, long long ldb, const BMap& bmap,
                                               int depth, double* smem) {
-  using LA = TileLayout<Cfg::BM, AK>;
-  using LB = TileLayout<Cfg::BN, BKM>;
+  constexpr int BKT = Cfg::BKT;
+  using LA = TileLayout<Cfg::BM, AK, BKT>;
+  using LB = TileLayout<Cfg::BN, BKM, BKT>;
   constexpr int STAGE = LA::SIZE + LB::SIZE;
   constexpr int STAGES = Cfg::STAGES;
   const int tid = threadIdx.x;
@@ -133,15 +134,15 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[Cfg::MI][Cfg::NI][2]
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM;
   const int wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
-  const int nk = (depth + BK - 1) / BK;
+  const int nk = (depth + BKT - 1) / BKT;
 
   __syncthreads();  // smem may still be in use by a previous segment / epilogue
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
       double* st = smem + s * STAGE;
-      load_tile<Cfg::BM, AK, AVEC, Cfg::NT>(st, A, lda, amap, s * BK, depth, tid);
-      load_tile<Cfg::BN, BKM, BVEC, Cfg::NT>(st + LA::SIZE, B, ldb, bmap, s * BK, depth, tid);
+      load_tile<Cfg::BM, AK, AVEC, Cfg::NT, BKT>(st, A, lda, amap, s * BKT, depth, tid);
+      load_tile<Cfg::BN, BKM, BVEC, Cfg::NT, BKT>(st + LA::SIZE, B, ldb, bmap, s * BKT, depth, tid);
     }
     cp_async_commit();
   }
@@ -152,15 +153,15 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[Cfg::MI][Cfg::NI][2]
       int kn = kt + STAGES - 1;
       if (kn < nk) {
         double* st = smem + (kn % STAGES) * STAGE;
-        load_tile<Cfg::BM, AK, AVEC, Cfg::NT>(st, A, lda, amap, kn * BK, depth, tid);
-        load_tile<Cfg::BN, BKM, BVEC, Cfg::NT>(st + LA::SIZE, B, ldb, bmap, kn * BK, depth, tid);
+        load_tile<Cfg::BM, AK, AVEC, Cfg::NT, BKT>(st, A, lda, amap, kn * BKT, depth, tid);
+        load_tile<Cfg::BN, BKM, BVEC, Cfg::NT, BKT>(st + LA::SIZE, B, ldb, bmap, kn * BKT, depth, tid);
       }
       cp_async_commit();
     }
     const double* As = smem + (kt % STAGES) * STAGE;
     const double* Bs = As + LA::SIZE;
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
+    for (int kk = 0; kk < BKT / 4; ++kk) {
       double a[Cfg::MI], b[Cfg::NI];
 #pragma unroll
       for (int i = 0; i < Cfg::MI; ++i) a[i] = As[LA::idx(wm0 + 8 * i + g, kk * 4 + t)];

@@ -10,8 +10,11 @@ namespace scfgp {
 // ------------------------------------------------------------------------------------
 using CfgBig = TileCfg<128, 128, 64, 32, 3>;   // 8 warps, 64 accumulators / thread
 using CfgTall = TileCfg<128, 64, 32, 32, 3>;   // 8 warps, panels
-using CfgFeat = TileCfg<128, 64, 32, 32, 2>;   // 8 warps, feature map: 2 stages, 2 CTAs / SM
-using CfgWide = TileCfg<64, 128, 32, 32, 3>;   // 8 warps, D x J contraction
+// feature map and dW contraction: depth-8 stages keep their shared memory (36 KB / 26 KB) small
+// enough to share an SM with a resident tcgen05 CTA of the emulated path (186 KB at 5 digits)
+using CfgFeat = TileCfg<128, 64, 32, 32, 2, 8>;   // 8 warps, 2 stages
+using CfgWide = TileCfg<64, 128, 32, 32, 3>;   // 8 warps, small dense NN products
+using CfgDw = TileCfg<64, 128, 32, 32, 2, 8>;  // 8 warps, D x J contraction (dW)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -73,11 +76,11 @@ k_gemm(const double* __restrict__ A, long long lda, int a_rows,
 //   items: (d block of 64, j block of 128)
 // ------------------------------------------------------------------------------------
 template <int AVEC>
-__global__ void __launch_bounds__(TileCfg<64, 128, 32, 32, 3>::NT, 1)
+__global__ void __launch_bounds__(CfgDw::NT, 1)
 k_dw_splitk(const double* __restrict__ X, long long ldx, int D, const double* __restrict__ Z, long long ldz, int J,
             int rows, int split_len, double* __restrict__ part, long long ldc, long long part_stride,
             const int4* __restrict__ items) {
-  using Cfg = TileCfg<64, 128, 32, 32, 3>;
+  using Cfg = CfgDw;
   extern __shared__ __align__(16) double smem[];
   const int4 it = items[blockIdx.x];
   const int m0 = it.x * Cfg::BM, n0 = it.y * Cfg::BN;

@@ -31,7 +31,9 @@ struct ItemList {
 
 constexpr int kMaxStreams = 4;
 struct Ctx {
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;   // chunk stream (high priority): features, digits, reductions
+  cudaStream_t sg = nullptr;   // low-priority stream of the tcgen05 GEMM kernels of this chunk stream
+  cudaEvent_t ev_sg = nullptr, ev_gs = nullptr;  // st -> sg and sg -> st hand-offs
   cudaEvent_t done = nullptr;
   double *Phi = nullptr, *Psi = nullptr, *Zbar = nullptr, *vpart = nullptr;  // slabs
   double *acc = nullptr;      // K x ldk partial of G / H
@@ -117,6 +119,11 @@ struct scfgp_handle {
   long long launches = 0;
   cudaEvent_t ev[8] = {};
   float ms_pass[4] = {0, 0, 0, 0};
+
+  // optional launch trace (CUDA event pair around every streaming-kernel launch)
+  struct TraceRec { const char* name; int lane; cudaEvent_t e0, e1; };
+  bool tracing = false;
+  std::vector<TraceRec> trace;
 
   // optional per-kernel-family timing (CUDA events around every launch of one family)
   int prof_family = SCFGP_FAM_NONE;
@@ -208,7 +215,19 @@ int make_tmap_digits(scfgp_handle* h, CUtensorMap* out, const int8_t* base, long
   }
 
 // profiling brackets: record an event pair around launches of the selected family
+inline void trace_begin(scfgp_handle* h, const char* name, cudaStream_t st);
+inline void trace_end(scfgp_handle* h, cudaStream_t st);
+inline const char* fam_name(int fam) {
+  switch (fam) {
+    case SCFGP_FAM_FEATURES: return "features";
+    case SCFGP_FAM_TGEMM: return "tgemm";
+    case SCFGP_FAM_BACKWARD: return "backward";
+    case SCFGP_FAM_SYRK: return "gram";
+    default: return "other";
+  }
+}
 inline void prof_begin(scfgp_handle* h, int fam, cudaStream_t st) {
+  trace_begin(h, fam_name(fam), st);
   if (h->prof_family != fam) return;
   if (h->prof_used + 2 > h->prof_ev.size()) {
     cudaEvent_t a, b;
@@ -218,6 +237,7 @@ inline void prof_begin(scfgp_handle* h, int fam, cudaStream_t st) {
   cudaEventRecord(h->prof_ev[h->prof_used], st);
 }
 inline void prof_end(scfgp_handle* h, int fam, cudaStream_t st) {
+  trace_end(h, st);
   if (h->prof_family != fam) return;
   cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
   h->prof_used += 2;
@@ -230,6 +250,29 @@ inline void prof_collect(scfgp_handle* h) {
     } else (void)cudaGetLastError();
   }
   h->prof_used = 0;
+}
+
+// launch trace: lane = index of the chunk stream (or -1 for the handle's main stream)
+inline int trace_lane(const scfgp_handle* h, cudaStream_t st) {
+  for (int i = 0; i < kMaxStreams; ++i) {
+    if (h->ctx[i].st == st) return i;
+    if (h->ctx[i].sg == st) return kMaxStreams + i;
+  }
+  return -1;
+}
+inline void trace_begin(scfgp_handle* h, const char* name, cudaStream_t st) {
+  if (!h->tracing) return;
+  scfgp_handle::TraceRec r;
+  r.name = name;
+  r.lane = trace_lane(h, st);
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  h->trace.push_back(r);
+}
+inline void trace_end(scfgp_handle* h, cudaStream_t st) {
+  if (!h->tracing || h->trace.empty()) return;
+  cudaEventRecord(h->trace.back().e1, st);
 }
 
 template <class T>
@@ -288,12 +331,24 @@ int set_kernel_attrs(scfgp_handle* h) {
                           (int)SmemSize<CfgBig, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
   CK(cudaFuncSetAttribute(k_dw_splitk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SmemSize<CfgWide, false, false>::BYTES));
+                          (int)SmemSize<CfgDw, false, false>::BYTES));
   CK(cudaFuncSetAttribute(k_dw_splitk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SmemSize<CfgWide, false, false>::BYTES));
+                          (int)SmemSize<CfgDw, false, false>::BYTES));
   CK(cudaFuncSetAttribute(k_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_tgemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_backward_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
+  // Kernels of different chunk streams share SMs (a resident tcgen05 CTA leaves registers and
+  // ~40 KB of shared memory free).  That only happens if they agree on the L1 / shared-memory
+  // split, so every streaming kernel asks for the maximum shared-memory carveout.
+  const int mx = (int)cudaSharedmemCarveoutMaxShared;
+  CK(cudaFuncSetAttribute(k_features<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(k_features<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(k_dw_splitk<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(k_dw_splitk<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(k_colsum, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(k_seeds, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(k_pred_finish, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(emu::k_absmax_pow2, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   return SCFGP_OK;
 }
 
@@ -304,6 +359,12 @@ int set_emu_attrs(scfgp_handle* h) {
   CK(cudaFuncSetAttribute(emu::k_tgemm_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(emu::k_backward_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(emu::k_gemm_i8_dbg<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int mx = (int)cudaSharedmemCarveoutMaxShared;
+  CK(cudaFuncSetAttribute(emu::k_gram_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(emu::k_tgemm_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(emu::k_backward_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(emu::k_digits_rows<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute(emu::k_digits_cols<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   return SCFGP_OK;
 }
 
@@ -577,8 +638,10 @@ int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long lo
                     const double* rowmul, const double* rowinv, double ginv, const double* ginv_ptr, int permJ,
                     int8_t* dst, long long pitch, long long slice_stride, int col_off) {
   const long long total = (long long)rows * (cdiv(cols, 16) * 4);
+  trace_begin(h, "digits_rows", st);
   EMU_KS_SWITCH(h->ks, emu::k_digits_rows<KS><<<cdiv(total, 256), 256, 0, st>>>(
                            src, ld, rows, cols, rowmul, rowinv, ginv, ginv_ptr, permJ, dst, pitch, slice_stride, col_off));
+  trace_end(h, st);
   CKL();
   return SCFGP_OK;
 }
@@ -587,43 +650,65 @@ int emu_digits_cols(scfgp_handle* h, cudaStream_t st, const double* src, long lo
                     const double* rowmul, double ginv, const double* ginv_ptr, int8_t* dst, long long pitch,
                     long long slice_stride) {
   const dim3 grid(cdiv(cols, 32), cdiv(rows, 128));
+  trace_begin(h, "digits_cols", st);
   EMU_KS_SWITCH(h->ks, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
                                                                     pitch, slice_stride));
+  trace_end(h, st);
   CKL();
+  return SCFGP_OK;
+}
+
+// The GEMM kernels of a chunk stream run on its low-priority companion stream: enter = the
+// companion waits for everything queued on the chunk stream, leave = the chunk stream waits
+// for the GEMM.
+int gemm_enter(scfgp_handle* h, Ctx& c) {
+  CK(cudaEventRecord(c.ev_sg, c.st));
+  CK(cudaStreamWaitEvent(c.sg, c.ev_sg, 0));
+  return SCFGP_OK;
+}
+int gemm_leave(scfgp_handle* h, Ctx& c) {
+  CK(cudaEventRecord(c.ev_gs, c.sg));
+  CK(cudaStreamWaitEvent(c.st, c.ev_gs, 0));
   return SCFGP_OK;
 }
 
 // acc(lower tiles) += sc * digits(A)T . digits(Phi) over the rows of one chunk
 int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
   const int depth = (rows + umma::KB - 1) / umma::KB * umma::KB;
-  prof_begin(h, SCFGP_FAM_SYRK, c.st);
-  EMU_KS_SWITCH(h->ks, emu::k_gram_i8<KS><<<h->gram_count, umma::THREADS, umma::Geo<KS>::SMEM, c.st>>>(
+  int rc;
+  if ((rc = gemm_enter(h, c))) return rc;
+  prof_begin(h, SCFGP_FAM_SYRK, c.sg);
+  EMU_KS_SWITCH(h->ks, emu::k_gram_i8<KS><<<h->gram_count, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                            a_is_psi ? c.mapPsiT_A : c.mapPhiT_A, c.mapPhiT_B, depth, h->K, h->gram_items, c.acc, h->ldk,
                            h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
-  prof_end(h, SCFGP_FAM_SYRK, c.st);
+  prof_end(h, SCFGP_FAM_SYRK, c.sg);
   CKL();
-  return SCFGP_OK;
+  return gemm_leave(h, c);
 }
 
 int emu_tgemm(scfgp_handle* h, Ctx& c, int rows) {
   const dim3 grid(cdiv(h->K, umma::TN), cdiv(rows, umma::TM));
-  prof_begin(h, SCFGP_FAM_TGEMM, c.st);
-  EMU_KS_SWITCH(h->ks, emu::k_tgemm_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.st>>>(
+  int rc;
+  if ((rc = gemm_enter(h, c))) return rc;
+  prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
+  EMU_KS_SWITCH(h->ks, emu::k_tgemm_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                            c.mapRowsA, h->mapLiB, rows, h->K, h->liscale, h->s2, c.vpart, h->R));
-  prof_end(h, SCFGP_FAM_TGEMM, c.st);
+  prof_end(h, SCFGP_FAM_TGEMM, c.sg);
   CKL();
-  return SCFGP_OK;
+  return gemm_leave(h, c);
 }
 
 int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0) {
   const dim3 grid(cdiv(h->J, 32), cdiv(rows, umma::TM));
-  prof_begin(h, SCFGP_FAM_BACKWARD, c.st);
-  EMU_KS_SWITCH(h->ks, emu::k_backward_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.st>>>(
+  int rc;
+  if ((rc = gemm_enter(h, c))) return rc;
+  prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
+  EMU_KS_SWITCH(h->ks, emu::k_backward_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                            c.mapRowsA, h->mapCB, rows, h->J, (int)(h->Kp + h->K), h->cscale, h->s2, c.Phi, h->ldk,
                            h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj, c.slots));
-  prof_end(h, SCFGP_FAM_BACKWARD, c.st);
+  prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
-  return SCFGP_OK;
+  return gemm_leave(h, c);
 }
 
 // digits of Li with per-row power-of-two scales (B operand of Phi.LiT)
@@ -754,7 +839,10 @@ void free_all(scfgp_handle* h) {
     for (int8_t* p : {c.digR, c.digPhiT, c.digPsiT})
       if (p) cudaFree(p);
     if (c.done) cudaEventDestroy(c.done);
+    if (c.ev_sg) cudaEventDestroy(c.ev_sg);
+    if (c.ev_gs) cudaEventDestroy(c.ev_gs);
     if (c.st) cudaStreamDestroy(c.st);
+    if (c.sg) cudaStreamDestroy(c.sg);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   free_emu_static(h);
@@ -767,6 +855,7 @@ void free_all(scfgp_handle* h) {
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->prof_ev) cudaEventDestroy(e);
+  for (auto& r : h->trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
 }
 
 // penalty of SCFGP/SCFGP.py:94,114-117,127 and its adjoints (A.6), host
@@ -856,9 +945,18 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   if ((rc = dalloc(h, &h->colpart, (size_t)kColSplit * K))) return rc;
   if ((rc = dalloc(h, &h->slots, 1024))) return rc;
   if (const char* e = getenv("SCFGP_STREAMS")) h->ns = std::min(kMaxStreams, std::max(1, atoi(e)));
+  // The block scheduler hands out the CTAs of ready kernels in priority order, so the long
+  // tensor-core GEMM kernels go to low-priority streams: the short memory-bound kernels of the
+  // other chunk streams are then placed as soon as they are ready, next to the resident GEMM
+  // CTAs (which leave registers and shared memory free), instead of queueing behind them.
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int i = 0; i < kMaxStreams; ++i) {
-    CK(cudaStreamCreateWithFlags(&h->ctx[i].st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&h->ctx[i].st, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&h->ctx[i].sg, cudaStreamNonBlocking, prio_lo));
     CK(cudaEventCreateWithFlags(&h->ctx[i].done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ctx[i].ev_sg, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ctx[i].ev_gs, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   if ((rc = dalloc(h, &h->trslots, K))) return rc;
@@ -1009,7 +1107,9 @@ int scfgp_eval_pass1(scfgp_handle* h) {
     } else {
       if ((rc = run_syrk(h, c, false, rows))) return rc;
     }
+    trace_begin(h, "colsum", c.st);
     k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->dy + r0, c.colpart, K);
+    trace_end(h, c.st);
     CKL();
   }
   // yy on the main stream while the chunk streams drain
@@ -1109,14 +1209,18 @@ int scfgp_eval_pass2(scfgp_handle* h) {
     } else {
       if ((rc = run_tgemm(h, c, rows))) return rc;
     }
+    trace_begin(h, "seeds", c.st);
     k_seeds<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->dy + r0,
                                           h->tau, h->gmu + r0, h->gv + r0, c.Psi, c.slots,
                                           emu_on ? 0 : h->want_grad);
+    trace_end(h, c.st);
     CKL();
     if (h->want_grad && emu_on) {
       // H += (gv Phi)T Phi with the chunk's own power-of-two bound of |gv|
-      emu::k_absmax_pow2<<<1, 1024, 0, c.st>>>(h->gv + r0, rows, c.sig, h->gvmax);
-      CKL();
+      trace_begin(h, "absmax", c.st);
+    emu::k_absmax_pow2<<<1, 1024, 0, c.st>>>(h->gv + r0, rows, c.sig, h->gvmax);
+      trace_end(h, c.st);
+    CKL();
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
                                 (long long)K * h->R)))
         return rc;
@@ -1124,12 +1228,16 @@ int scfgp_eval_pass2(scfgp_handle* h) {
                                 (long long)K * h->R)))
         return rc;
       if ((rc = emu_gram(h, c, true, rows))) return rc;
-      k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
-      CKL();
+      trace_begin(h, "colsum", c.st);
+    k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
+      trace_end(h, c.st);
+    CKL();
     } else if (h->want_grad) {
       if ((rc = run_syrk(h, c, true, rows))) return rc;
-      k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
-      CKL();
+      trace_begin(h, "colsum", c.st);
+    k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
+      trace_end(h, c.st);
+    CKL();
     }
   }
   if ((rc = join_streams(h))) return rc;
@@ -1234,16 +1342,20 @@ int scfgp_eval_pass3(scfgp_handle* h) {
     {
       const int split_len = cdiv(cdiv(rows, kDwSplit), 16) * 16;
       const dim3 grid(h->dw.count, kDwSplit);
-      const size_t dsm = SmemSize<CfgWide, false, false>::BYTES;
+      const size_t dsm = SmemSize<CfgDw, false, false>::BYTES;
+      trace_begin(h, "dw", c.st);
       if (h->xvec == 2)
-        k_dw_splitk<2><<<grid, CfgWide::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
+        k_dw_splitk<2><<<grid, CfgDw::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
                                                          (long long)DJ, h->dw.d);
       else
-        k_dw_splitk<1><<<grid, CfgWide::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
+        k_dw_splitk<1><<<grid, CfgDw::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
                                                          (long long)DJ, h->dw.d);
+      trace_end(h, c.st);
       CKL();
     }
+    trace_begin(h, "colsum", c.st);
     k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, J, nullptr, c.colpart, K);
+    trace_end(h, c.st);
     CKL();
   }
   if ((rc = join_streams(h))) return rc;
@@ -1371,6 +1483,40 @@ int scfgp_device_factors(scfgp_handle* h, void** d_alpha, void** d_Li, long long
   return SCFGP_OK;
 }
 
+int scfgp_set_tracing(scfgp_handle* h, int on) {
+  if (!h) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  for (auto& r : h->trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  h->trace.clear();
+  h->tracing = on != 0;
+  return SCFGP_OK;
+}
+
+int scfgp_trace_dump(scfgp_handle* h, const char* path) {
+  if (!h || !path) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  FILE* f = fopen(path, "w");
+  if (!f) { h->err = std::string("cannot open ") + path; return SCFGP_ERR_ARG; }
+  fprintf(f, "{\"traceEvents\": [\n");
+  bool first = true;
+  for (size_t i = 0; i < h->trace.size(); ++i) {
+    float t0 = 0, dur = 0;
+    if (cudaEventElapsedTime(&t0, h->trace[0].e0, h->trace[i].e0) != cudaSuccess ||
+        cudaEventElapsedTime(&dur, h->trace[i].e0, h->trace[i].e1) != cudaSuccess) {
+      (void)cudaGetLastError();
+      continue;
+    }
+    fprintf(f, "%s{\"name\": \"%s\", \"ph\": \"X\", \"pid\": 0, \"tid\": %d, \"ts\": %.3f, \"dur\": %.3f}",
+            first ? "" : ",\n", h->trace[i].name, h->trace[i].lane, t0 * 1e3, dur * 1e3);
+    first = false;
+  }
+  fprintf(f, "\n]}\n");
+  fclose(f);
+  return SCFGP_OK;
+}
+
 int scfgp_set_profiling(scfgp_handle* h, int family) {
   if (!h || family < SCFGP_FAM_NONE || family > SCFGP_FAM_SYRK) return SCFGP_ERR_ARG;
   h->prof_family = family;
@@ -1419,8 +1565,10 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
         return rc;
       if ((rc = emu_tgemm(h, c, rows))) return rc;
     } else if ((rc = run_tgemm(h, c, rows))) return rc;
+    trace_begin(h, "pred_finish", c.st);
     k_pred_finish<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->tau,
                                                 dmu + r0, dstd + r0);
+    trace_end(h, c.st);
     CKL();
   }
   return join_streams(h);

@@ -22,7 +22,7 @@
 //   warp 1    : allocates TMEM, one lane issues the tcgen05.mma stream and commits each
 //               stage back to the producer (tcgen05.commit -> mbarrier)
 //   warps 2-9 : epilogue; tcgen05.ld the class accumulators, combine them in float64
-//               registers (2^-8q weights) and hand 32 columns of one row to a functor
+//               registers (2^-8q weights), 16 columns of one row at a time
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -41,6 +41,7 @@ constexpr double PROD_SCALE = 1.0 / 16384.0;  // 2^-14: product of the two leadi
 constexpr int THREADS = 320;
 constexpr int EPI_WARP0 = 2;
 constexpr int EPI_THREADS = 256;
+constexpr int MAX_REGS = 96;  // per thread: 320 x 96 leaves more than half of the register file to co-resident kernels
 
 template <int KS>
 struct Geo {
@@ -230,26 +231,51 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
   }
 }
 
-// epilogue role (warps 2..9): returns v[c] = sum_q 2^(-8q) acc_q[row][col0 + c], c < 32
-template <int KS>
-__device__ __forceinline__ void epilogue_collect(const Pipe& p, uint32_t tmem_base, uint32_t acc_parity, int& row,
-                                                 int& col0, double (&v)[32]) {
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// epilogue role (warps 2..9).  Each warp owns one TMEM lane quarter (32 tile rows, one per
+// lane) and one half (32 columns) of the tile, handled as two groups of 16 columns so that
+// the kernels stay within 96 registers per thread (side kernels of other streams can then
+// share the SM with a resident tensor-core CTA).
+struct EpiPos {
+  int row;    // tile row of this thread (0..127)
+  int col0;   // first of its 32 tile columns (0 or 32)
+  uint32_t lane_base;  // TMEM address of lane quarter, column 0
+};
+__device__ __forceinline__ EpiPos epilogue_wait(const Pipe& p, uint32_t tmem_base, uint32_t acc_parity) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-  const int half = (warp - EPI_WARP0) >> 2;     // which 32 of the 64 columns
-  row = quarter * 32 + lane;
-  col0 = half * 32;
+  const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
+  const int half = (warp - EPI_WARP0) >> 2;  // which 32 of the 64 columns
+  EpiPos e;
+  e.row = quarter * 32 + lane;
+  e.col0 = half * 32;
+  e.lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
   mbar_wait(p.acc_full, acc_parity);
   tc_fence_after();
+  return e;
+}
+// v[c] = sum_q 2^(-8q) acc_q[row][col + c], c < 16   (col = tile column, multiple of 16)
+template <int KS>
+__device__ __forceinline__ void epilogue_load16(const EpiPos& e, int col, double (&v)[16]) {
 #pragma unroll
-  for (int c = 0; c < 32; ++c) v[c] = 0.0;
+  for (int c = 0; c < 16; ++c) v[c] = 0.0;
 #pragma unroll
   for (int q = KS - 1; q >= 0; --q) {  // least significant class first
-    uint32_t r[32];
-    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * TN + col0), r);
+    uint32_t r[16];
+    tmem_ld16(e.lane_base + (uint32_t)(q * TN + col), r);
     const double w = __longlong_as_double((long long)(1023 - DIGIT_BITS * q) << 52);  // 2^(-8q)
 #pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)r[c], w, v[c]);
+    for (int c = 0; c < 16; ++c) v[c] = fma((double)(int)r[c], w, v[c]);
   }
 }
 

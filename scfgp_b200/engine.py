@@ -113,6 +113,13 @@ class Engine:
     def set_streams(self, n: int):
         self._check(self.lib.scfgp_set_streams(self._h, int(n)))
 
+    def set_tracing(self, on: bool):
+        self._check(self.lib.scfgp_set_tracing(self._h, int(bool(on))))
+
+    def trace_dump(self, path: str):
+        """Write the launch trace recorded since set_tracing(True) as Chrome-trace JSON."""
+        self._check(self.lib.scfgp_trace_dump(self._h, str(path).encode()))
+
     def set_profiling(self, family: int):
         self._check(self.lib.scfgp_set_profiling(self._h, int(family)))
 
