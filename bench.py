@@ -30,6 +30,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one 8192-row k_backward_i8 launch (ncu --set full), by digits
+TRAFFIC_BACKWARD_I8 = {5: 664.3e6}
+
 WORKLOAD = dict(name="cfg4: synthetic N=10M, D=64, rank=16, feature_size=1024", N=10_000_000, D=64, S=16, M=1024)
 
 
@@ -182,6 +185,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=WORKLOAD["N"], help="total training rows (default: the cfg4 workload)")
     ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--precision", default="emu5",
+                    help="arithmetic of the streaming products: 'emu<digits>' = float64 emulated on the int8 "
+                         "tensor cores (tcgen05, default 5 base-256 digits), 'fp64' = FP64 DMMA path")
+    ap.add_argument("--no-fp64-compare", action="store_true",
+                    help="skip the one-evaluation comparison run of the FP64 DMMA path (N = 1 GPU only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -228,8 +236,15 @@ def main():
     n_local = hi - lo
 
     Xd, yd, params0 = make_device_problem(n_local, D, S, M, seed=1000 + rank, device=device, dist=dist)
-    eng = Engine(D, S, M, device=local_rank, chunk_rows=args.chunk_rows or None)
+    eng = Engine(D, S, M, device=local_rank, chunk_rows=args.chunk_rows or None, precision=args.precision)
     eng.set_data_device(Xd, yd, n_global=N)
+    emulated = eng.precision.startswith("emu")
+    digits = int(eng.precision[3:]) if emulated else 0
+    config["precision"] = (f"float64 emulated on the int8 tensor cores: {digits} base-256 digits per operand "
+                           f"({8 * digits - 2} fractional bits of each row's power-of-two scale), "
+                           f"{digits * (digits + 1) // 2} digit products, exact int32 accumulation (tcgen05.mma kind::i8); "
+                           "feature map, Cholesky, inverse and small dense backward in true FP64"
+                           if emulated else "FP64 tensor path (DMMA.8x8x4)")
 
     def barrier():
         torch.cuda.synchronize()
@@ -279,8 +294,8 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(nrep):
-            eng.set_data(Xn, yn, n_global=N)          # H2D of this step's inputs
-            c2, g2, a2, L2 = eng.eval(params0)        # D2H of cost, grad, alpha, Li
+            eng.set_data(Xn, yn, n_global=N, overlap=True)   # H2D of this step's inputs (row blocks, consumed by pass 1 as they land)
+            c2, g2, a2, L2 = eng.eval(params0)               # D2H of cost, grad, alpha, Li
         barrier()
         sec = (time.perf_counter() - t0) / nrep
         tt = torch.tensor([sec], dtype=torch.float64, device=device)
@@ -291,7 +306,9 @@ def main():
         e2e = {"value": N / sec, "unit": "rows/s", "ms_per_step": sec * 1e3,
                "h2d_bytes_per_step": int(n_local * D * 8 + n_local * 8 + eng.P * 8) * world,
                "d2h_bytes_per_step": int(8 * (1 + eng.P + K + K * K)) * world,
-               "api": "Engine.set_data(X_host, y_host) + Engine.eval(params) == scfgp_set_data_host + scfgp_eval"}
+               "api": "Engine.set_data(X_host, y_host, overlap=True) + Engine.eval(params) == "
+                      "scfgp_set_data_host_async + scfgp_eval (pinned host X/y uploaded in row blocks inside the "
+                      "timed region, pass 1 starts on each block as it lands; cost, grad, alpha, Li read back)"}
         assert abs(c2 - cost) <= 1e-9 * abs(cost)
         eng.set_data_device(Xd, yd, n_global=N)
 
@@ -300,7 +317,7 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_backward: 4 N K^2 of the 7 N K^2 flops)
+    # ---- roofline of the dominant kernel (pass 3: 4 N K^2 of the 7 N K^2 flops)
     K = eng.K
     peak_burst = peak_sus = None
     try:
@@ -323,13 +340,14 @@ def main():
         del a, b
     except Exception as ex:  # pragma: no cover
         peak_burst = None
-    # (1) over the timed region: pass 3 = [features, k_backward_tma, dW contraction, column sums] on 4
-    #     overlapped streams, bracketed by CUDA events on the handle's main stream.  Its algorithmic
-    #     work is 4 N K^2 (Phi.(2Abar) + Psi.(2B)); helpers are charged to the kernel (conservative).
+    dgemm_peak = peak_sus or 35.4
+    # (1) over the timed region: pass 3 = [features, digits, backward GEMM, dW contraction, column sums] on
+    #     overlapped streams, bracketed by CUDA events on the handle's main stream.  Its algorithmic work is
+    #     4 N K^2 float64 flops (Phi.(2Abar) + Psi.(2B)); the helpers are charged to the kernel (conservative).
     p3_ms = sum(p[2] for p in pass_ms) / len(pass_ms)
     flops_p3 = 4.0 * K * K * n_local
-    achieved = flops_p3 / (p3_ms * 1e-3) * 1e-12
-    # (2) one launch in isolation (single stream, CUDA events around every k_backward_tma launch)
+    achieved_f64 = flops_p3 / (p3_ms * 1e-3) * 1e-12
+    # (2) one launch in isolation (single stream, CUDA events around every backward-GEMM launch)
     iso_ms, iso_n = 0.0, 0
     if world == 1:                      # (an evaluation is collective: rank 0 cannot run one alone)
         eng.set_streams(1)
@@ -337,28 +355,83 @@ def main():
         eng.eval(params0)
         iso_ms, iso_n = eng.get_profile()
         eng.set_profiling(_lib.FAM_NONE)
-    rows_per_launch = n_local / max(iso_n, 1) if iso_n else 4096
+        eng.set_streams(4)
+    rows_per_launch = n_local / max(iso_n, 1) if iso_n else (8192 if emulated else 4096)
     flops_per_launch = 4.0 * K * K * rows_per_launch
     iso_avg = iso_ms / max(iso_n, 1)
-    peak = peak_sus or 35.4
-    roofline = {"bound": "tensor", "kernel": "k_backward_tma (FP64 DMMA.8x8x4 fed by TMA)", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 562.2e6,
-                "traffic_note": "dram__bytes_read+write of one 4096-row launch from ncu --set full "
-                                "(profiles/r1_prof_backward_ncu_full_N8192.txt); algorithmic operand bytes per "
-                                "launch: Phi+Psi slabs 136 MB + 2Abar,2B 69 MB",
-                "how": "4 N K^2 algorithmic flops of pass 3 / pass-3 device time (CUDA events on the launching "
-                       "stream) averaged over the timed steps",
-                "avg_launch_ms_isolated": iso_avg, "launches_isolated": iso_n,
-                "algorithmic_flops_per_launch": flops_per_launch,
-                "achieved_isolated_launch": flops_per_launch / (iso_avg * 1e-3) * 1e-12 if iso_avg > 0 else None,
-                "overlapped_launch_ms_sum": bw_ms, "overlapped_launches": bw_launches,
-                "peak_source": "cublasDgemm 8192^3 sustained, measured in this run (MEASURED_PEAKS.json holds no "
-                               "fp64 entry; register-resident DMMA.8x8x4 issue peak measured 37.0 TFLOP/s, "
-                               "gpurun_out/microbench.log -> profiles/r1_fp64_pipe_microbench.txt)",
-                "peak_dgemm_burst": peak_burst, "peak_dgemm_sustained": peak_sus,
-                "whole_eval_tflops": fpr * N / (ms_step * 1e-3) * 1e-12 / max(world, 1),
-                "whole_eval_frac_of_peak": fpr * N / (ms_step * 1e-3) * 1e-12 / max(world, 1) / peak,
-                "pass_ms_last": dict(zip(["pass1", "pass2", "pass3", "dense"], pass_ms[-1]))}
+    whole_tf = fpr * N / (ms_step * 1e-3) * 1e-12 / max(world, 1)
+    common = {"avg_launch_ms_isolated": iso_avg, "launches_isolated": iso_n,
+              "overlapped_launch_ms_sum": bw_ms, "overlapped_launches": bw_launches,
+              "peak_dgemm_burst": peak_burst, "peak_dgemm_sustained": peak_sus,
+              "whole_eval_fp64_equivalent_tflops": whole_tf,
+              "whole_eval_vs_dgemm_peak": whole_tf / dgemm_peak,
+              "pass_ms_last": dict(zip(["pass1", "pass2", "pass3", "dense"], pass_ms[-1]))}
+    if emulated:
+        # digit-product operations actually asked of the int8 tensor cores: 2 * rows * K * 2K per digit product
+        nprod = digits * (digits + 1) // 2
+        int8_ops_p3 = flops_p3 * nprod
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16_sus = peaks.get("bf16_tflops_sustained") or 1400.0
+        bf16_burst = peaks.get("bf16_tflops") or 1590.0
+        peak_i8 = 2.0 * bf16_sus
+        achieved = int8_ops_p3 / (p3_ms * 1e-3) * 1e-12
+        roofline = dict(common, **{
+            "bound": "tensor", "kernel": "k_backward_i8 (tcgen05.mma kind::i8, int32 accumulators in TMEM, TMA-fed)",
+            "achieved": achieved, "peak": peak_i8, "unit": "TOP/s", "frac": achieved / peak_i8,
+            "traffic": TRAFFIC_BACKWARD_I8.get(digits),
+            "traffic_note": "dram__bytes_read+write of one 8192-row k_backward_i8 launch from ncu --set full "
+                            "(profiles/r1_prof_backward_i8_ncu_full.txt); algorithmic operand bytes per launch: "
+                            "A digits rows*2K*digits + C digits K*2K*digits + Phi slab read + Zbar write",
+            "how": f"int8 digit-product operations of pass 3 (4 N K^2 x {nprod} digit products) / pass-3 device time "
+                   "(CUDA events on the launching stream) averaged over the timed steps; the pass includes the feature "
+                   "map, digit extraction and dW kernels, so the GEMM kernel alone is faster than this",
+            "algorithmic_int8_ops_per_launch": flops_per_launch * nprod,
+            "algorithmic_flops_per_launch": flops_per_launch,
+            "achieved_isolated_launch": flops_per_launch * nprod / (iso_avg * 1e-3) * 1e-12 if iso_avg > 0 else None,
+            "peak_source": ("2 x the sustained dense bf16 rate of MEASURED_PEAKS.json (" + str(bf16_sus) + " TFLOP/s; "
+                            "int8 dense = 2 x bf16 dense on sm_100a; the file has no int8 entry; burst would be 2 x "
+                            + str(bf16_burst) + "); the evaluation runs for seconds at the 1 kW power cap, hence sustained"
+                            if peaks else "fallback 2 x 1.4 PFLOP/s sustained bf16 (MEASURED_PEAKS.json absent)"),
+            "fp64_equivalent_tflops_pass3": achieved_f64,
+            "fp64_equivalent_vs_dgemm_peak": achieved_f64 / dgemm_peak,
+        })
+    else:
+        roofline = dict(common, **{
+            "bound": "tensor", "kernel": "k_backward_tma (FP64 DMMA.8x8x4 fed by TMA)", "achieved": achieved_f64,
+            "peak": dgemm_peak, "unit": "TFLOP/s", "frac": achieved_f64 / dgemm_peak, "traffic": 562.2e6,
+            "traffic_note": "dram__bytes_read+write of one 4096-row launch from ncu --set full "
+                            "(profiles/r1_prof_backward_ncu_full_N8192.txt); algorithmic operand bytes per "
+                            "launch: Phi+Psi slabs 136 MB + 2Abar,2B 69 MB",
+            "how": "4 N K^2 algorithmic flops of pass 3 / pass-3 device time (CUDA events on the launching "
+                   "stream) averaged over the timed steps",
+            "algorithmic_flops_per_launch": flops_per_launch,
+            "achieved_isolated_launch": flops_per_launch / (iso_avg * 1e-3) * 1e-12 if iso_avg > 0 else None,
+            "peak_source": "cublasDgemm 8192^3 sustained, measured in this run (MEASURED_PEAKS.json holds no "
+                           "fp64 entry; register-resident DMMA.8x8x4 issue peak measured 37.0 TFLOP/s, "
+                           "profiles/r1_fp64_pipe_microbench.txt)",
+        })
+
+    # ---- the FP64 DMMA path on the same data: one evaluation, timing + parity of the emulated results
+    fp64_compare = None
+    if emulated and world == 1 and not args.no_fp64_compare:
+        eng.set_precision("fp64")
+        eng.eval(params0)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        c64, g64, a64, L64 = eng.eval(params0)
+        torch.cuda.synchronize(); sec64 = time.perf_counter() - t0
+        fp64_compare = {"ms_per_step": sec64 * 1e3, "rows_per_sec": N / sec64,
+                        "fp64_tflops": fpr * N / sec64 * 1e-12,
+                        "speedup_of_emulated": sec64 * 1e3 / ms_step,
+                        "parity_of_emulated": {
+                            "cost_rel": abs(cost - c64) / abs(c64),
+                            "grad_rel": float(np.linalg.norm(grad - g64) / np.linalg.norm(g64)),
+                            "alpha_abs": float(np.abs(alpha - a64).max()), "Li_abs": float(np.abs(Li - L64).max()),
+                            "tolerance": "cost 1e-6 relative; gradient, alpha, Li 1e-5 (north_star)"}}
+        eng.set_precision(args.precision)
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -368,8 +441,10 @@ def main():
     line = {"metric": "nlml_grad_rows_per_sec", "value": rows_per_s, "unit": "rows/s",
             "evals_per_sec": 1e3 / ms_step, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "dtype": "f64 emulated on int8 tensor cores (s8 x s8 -> s32 digit products)" if emulated else "f64",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "fp64_dmma_path": fp64_compare,
+            "cpu_baseline": cpu_baseline,
             "cost": cost, "grad_norm": float(np.linalg.norm(grad))}
     print(json.dumps(line))
     if dist is not None:

@@ -60,6 +60,12 @@ struct scfgp_handle {
   const double* dy = nullptr;
   double* ownX = nullptr;
   double* owny = nullptr;
+  long long own_cap = 0;                 // rows the owned buffers can hold
+  // host -> device upload in row blocks on a copy stream, overlapped with the first pass
+  cudaStream_t cstream = nullptr;
+  std::vector<cudaEvent_t> up_ev;        // one event per uploaded row block
+  long long up_block = 0;                // rows per block
+  bool upload_pending = false;
   int R = 4096;  // rows per chunk (8192 in the emulated mode unless set by the caller)
   bool R_user = false;
   int xvec = 2;
@@ -845,6 +851,8 @@ void free_all(scfgp_handle* h) {
     if (c.sg) cudaStreamDestroy(c.sg);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->cstream) cudaStreamDestroy(h->cstream);
+  for (auto& e : h->up_ev) cudaEventDestroy(e);
   free_emu_static(h);
   for (double* p : {h->acc_all, h->dW_all, h->colpart_all, h->slots_all, h->Wt, h->phi, h->red1, h->red2, h->red3, h->L,
                     h->Li, h->Bm, h->BH, h->BHB, h->A2, h->B2, h->Dinv, h->tmpS, h->alpha, h->beta, h->tvec,
@@ -959,6 +967,7 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
     CK(cudaEventCreateWithFlags(&h->ctx[i].ev_gs, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
   if ((rc = dalloc(h, &h->trslots, K))) return rc;
   if ((rc = dalloc(h, &h->info, 1))) return rc;
   if (const char* e = getenv("SCFGP_NO_TMA")) h->use_tma = atoi(e) ? 0 : 1;
@@ -1000,6 +1009,7 @@ int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
   if (!h || rows < 128 || rows % 128 != 0) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
+  h->upload_pending = false;  // (the device-wide sync above completed any upload)
   h->R = rows;
   h->R_user = true;
   return alloc_chunk_buffers(h);
@@ -1011,6 +1021,7 @@ int scfgp_set_precision(scfgp_handle* h, int mode, int digits) {
   if (digits < 4 || digits > 8) { h->err = "digits must be 4..8"; return SCFGP_ERR_ARG; }
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
+  h->upload_pending = false;  // (the device-wide sync above completed any upload)
   h->prec = mode;
   h->ks = digits;
   if (!h->R_user) h->R = mode == SCFGP_PREC_EMU_I8 ? 8192 : 4096;
@@ -1031,6 +1042,7 @@ int scfgp_set_streams(scfgp_handle* h, int n) {
   if (!h || n < 1 || n > kMaxStreams) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
+  h->upload_pending = false;  // (the device-wide sync above completed any upload)
   h->ns = n;
   return alloc_chunk_buffers(h);
 }
@@ -1043,25 +1055,65 @@ static int set_data_common(scfgp_handle* h, long long N, long long n_global) {
   return ensure_row_arrays(h, N);
 }
 
-int scfgp_set_data_host(scfgp_handle* h, const double* X, const double* y, long long N, long long n_global) {
+// wait (on the host) for an upload started by scfgp_set_data_host_async
+static int finish_upload(scfgp_handle* h) {
+  if (h->upload_pending) {
+    CK(cudaStreamSynchronize(h->cstream));
+    h->upload_pending = false;
+  }
+  return SCFGP_OK;
+}
+
+int scfgp_set_data_host_async(scfgp_handle* h, const double* X, const double* y, long long N, long long n_global) {
   if (!h || !X || !y || N <= 0) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
-  if (h->ownX) cudaFree(h->ownX);
-  if (h->owny) cudaFree(h->owny);
-  h->ownX = h->owny = nullptr;
-  CK(cudaMalloc((void**)&h->ownX, (size_t)N * h->D * sizeof(double)));
-  CK(cudaMalloc((void**)&h->owny, (size_t)N * sizeof(double)));
-  CK(cudaMemcpyAsync(h->ownX, X, (size_t)N * h->D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->owny, y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  int rc;
+  if ((rc = finish_upload(h))) return rc;
+  if (N > h->own_cap) {
+    CK(cudaDeviceSynchronize());
+    if (h->ownX) cudaFree(h->ownX);
+    if (h->owny) cudaFree(h->owny);
+    h->ownX = h->owny = nullptr;
+    h->own_cap = 0;
+    CK(cudaMalloc((void**)&h->ownX, (size_t)N * h->D * sizeof(double)));
+    CK(cudaMalloc((void**)&h->owny, (size_t)N * sizeof(double)));
+    h->own_cap = N;
+  } else {
+    // the previous evaluation may still be reading the buffers
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  // y first, then X in blocks of a few chunks; one event per block
+  CK(cudaMemcpyAsync(h->owny, y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->cstream));
+  h->up_block = (long long)h->R * 8;
+  const long long nblk = (N + h->up_block - 1) / h->up_block;
+  while ((long long)h->up_ev.size() < nblk) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->up_ev.push_back(e);
+  }
+  for (long long b = 0; b < nblk; ++b) {
+    const long long r0 = b * h->up_block, rows = std::min(h->up_block, N - r0);
+    CK(cudaMemcpyAsync(h->ownX + r0 * h->D, X + r0 * h->D, (size_t)rows * h->D * sizeof(double),
+                       cudaMemcpyHostToDevice, h->cstream));
+    CK(cudaEventRecord(h->up_ev[b], h->cstream));
+  }
+  h->upload_pending = true;
   h->dX = h->ownX;
   h->dy = h->owny;
   return set_data_common(h, N, n_global);
 }
 
+int scfgp_set_data_host(scfgp_handle* h, const double* X, const double* y, long long N, long long n_global) {
+  int rc = scfgp_set_data_host_async(h, X, y, N, n_global);
+  if (rc) return rc;
+  return finish_upload(h);
+}
+
 int scfgp_set_data_device(scfgp_handle* h, const double* dX, const double* dy, long long N, long long n_global) {
   if (!h || !dX || !dy || N <= 0) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
+  int rcu;
+  if ((rcu = finish_upload(h))) return rcu;
   h->dX = dX;
   h->dy = dy;
   return set_data_common(h, N, n_global);
@@ -1098,6 +1150,11 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   for (long long r0 = 0; r0 < h->N; r0 += h->R, ++ci) {
     Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
+    if (h->upload_pending) {
+      // rows of this chunk arrive with upload block b (blocks complete in order on the copy stream)
+      const long long b = (r0 + rows - 1) / h->up_block;
+      CK(cudaStreamWaitEvent(c.st, h->up_ev[b], 0));
+    }
     if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
     if (h->prec == SCFGP_PREC_EMU_I8) {
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
@@ -1113,12 +1170,14 @@ int scfgp_eval_pass1(scfgp_handle* h) {
     CKL();
   }
   // yy on the main stream while the chunk streams drain
+  if (h->upload_pending) CK(cudaStreamWaitEvent(h->stream, h->up_ev[0], 0));  // y is copied before X block 0
   CK(cudaMemsetAsync(h->slots, 0, 256 * sizeof(double), h->stream));
   k_sumsq_part<<<256, 256, 0, h->stream>>>(h->dy, h->N, h->slots);
   CKL();
   k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots, 256, 1, 1, yy);
   CKL();
   if ((rc = join_streams(h))) return rc;
+  h->upload_pending = false;  // everything queued after this point is ordered behind the whole upload
   k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns, (int)KK, G);
   CKL();
   k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, K, p);

@@ -129,6 +129,23 @@ __host__ __device__ constexpr uint32_t idesc_i8(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
+// wait that is expected to take tens of microseconds (the epilogue warps wait for the whole
+// mainloop): let the hardware suspend the thread instead of spinning on the issue slots
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
+        : "memory");
+  } while (!ok);
+}
+
 struct Tile {
   int m0;       // first row of the A tensor map (dimension 1)
   int n0;       // first row of the B tensor map (dimension 1)
@@ -260,7 +277,7 @@ __device__ __forceinline__ EpiPos epilogue_wait(const Pipe& p, uint32_t tmem_bas
   e.row = quarter * 32 + lane;
   e.col0 = half * 32;
   e.lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-  mbar_wait(p.acc_full, acc_parity);
+  mbar_wait_long(p.acc_full, acc_parity);
   tc_fence_after();
   return e;
 }

@@ -133,16 +133,20 @@ class Engine:
         self._check(self.lib.scfgp_set_stream(self._h, C.c_void_p(stream_ptr)))
 
     # ------------------------------------------------------------------ data
-    def set_data(self, X, y, n_global: int | None = None):
-        """X (N,D), y (N,) or (N,1) host arrays -> device copies owned by the handle."""
+    def set_data(self, X, y, n_global: int | None = None, overlap: bool = False):
+        """X (N,D), y (N,) or (N,1) host arrays -> device copies owned by the handle.
+
+        ``overlap=True`` queues the upload in row blocks and returns at once; the first pass of
+        the next ``eval`` consumes the blocks as they land (use pinned host memory).  The arrays
+        are kept alive by the engine and must not be modified until that ``eval`` returns."""
         X = _lib.as_f64(X)
         y = _lib.as_f64(np.asarray(y).reshape(-1))
         if X.ndim != 2 or X.shape[1] != self.D or y.shape[0] != X.shape[0]:
             raise ValueError(f"shape mismatch: X {X.shape}, y {y.shape}, D={self.D}")
         self.N = X.shape[0]
-        self._keep = None
-        self._check(self.lib.scfgp_set_data_host(self._h, _lib.dptr(X), _lib.dptr(y), self.N,
-                                                 int(n_global or self.N)))
+        fn = self.lib.scfgp_set_data_host_async if overlap else self.lib.scfgp_set_data_host
+        self._check(fn(self._h, _lib.dptr(X), _lib.dptr(y), self.N, int(n_global or self.N)))
+        self._keep = (X, y) if overlap else None
 
     def set_data_device(self, X_t, y_t, n_global: int | None = None):
         """Borrow float64 CUDA torch tensors (zero-copy)."""
