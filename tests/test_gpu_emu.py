@@ -261,3 +261,24 @@ def test_facade_fit_in_emulated_mode():
     assert model.get_compiled_funcs().engine.precision == "emu5"
     mu, sd = model.predict(X[te], yraw[te, None])
     assert np.all(np.isfinite(mu)) and np.all(sd > 0)
+
+
+def test_cfg5_geometry_reduced_rows_both_modes():
+    """cfg5's D = 256, rank 32, feature_size 2048 (K = 4160, P = 75 811) at a row count the
+    oracle finishes in seconds: FP64 DMMA path and emulated path against the oracle."""
+    N, D, S, M = 2500, 256, 32, 2048
+    X, y, h = synth.make_problem(N, D, S, M, seed=5)
+    c0, g0, al0, Li0 = O.streaming_eval(h, X, y, S, M, chunk=1250)
+    for prec, (ctol, gtol, atol) in (("fp64", (1e-10, 1e-8, 1e-8)), ("emu5", TOL["emu5"])):
+        eng = Engine(D, S, M, precision=prec)
+        eng.set_data(X, y)
+        c, g, al, Li = eng.eval(h)
+        assert abs(c - c0) <= ctol * abs(c0), (prec, c, c0)
+        for name, sl in grad_blocks(D, S, M).items():
+            if name == "phase":
+                assert np.abs(g[sl] - g0[sl]).max() <= gtol, (prec, name)
+            else:
+                assert rel(g[sl], g0[sl]) <= gtol, (prec, name, rel(g[sl], g0[sl]))
+        assert np.abs(al - al0).max() <= atol * max(1.0, np.abs(al0).max()), prec
+        assert np.abs(Li - Li0).max() <= atol * max(1.0, np.abs(Li0).max()), prec
+        eng.close()
