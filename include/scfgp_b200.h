@@ -178,6 +178,29 @@ enum {
 int scfgp_set_profiling(scfgp_handle* h, int family);
 int scfgp_get_profile(const scfgp_handle* h, double* total_ms, long long* launches);
 
+/* ---- data preprocessing on the device (SCFGP/Scaler.py:39-135).
+ * Stateless helpers on device-resident row-major float64 data (N x D, leading dimension ld);
+ * the Scaler object itself (fitted fields, algorithm names, SLSQP line search over the
+ * Box-Cox exponent) is host code: scfgp_b200/gpu_scaler.py.
+ *   colstats       : per-column min, max and "constant column" flags        Scaler.py:40-41,44-45
+ *   gather_column  : dcol[r] = (X[r][col] - shift) / range (contiguous copy of one column)
+ *   column_moments : mean, population variance and skewness g1 = m3 / m2^1.5 of
+ *                    boxcox(dcol, lambda) (lambda <= 0: of dcol itself)      Scaler.py:61-66,71-72
+ *   column_distinct: min(number of distinct values, cap + 1), cap <= 15      Scaler.py:63
+ *   forward        : Scaler.forward_transform on the columns `cols` (host int array); algo
+ *                    0 min-max, 1 normal, 2 inv-normal, 3 auto-normal, 4 auto-inv-normal; the
+ *                    per-column parameter arrays are host pointers (unused ones may be NULL) */
+int scfgp_scaler_colstats(int device, const double* dX, long long N, int D, long long ld, double* mn, double* mx,
+                          int* is_const);
+int scfgp_scaler_gather_column(int device, const double* dX, long long N, long long ld, int col, double shift,
+                               double range, double* dcol);
+int scfgp_scaler_column_moments(int device, const double* dcol, long long N, double lambda, double* mean,
+                                double* var, double* skew_g1);
+int scfgp_scaler_column_distinct(int device, const double* dcol, long long N, int cap, int* ndistinct);
+int scfgp_scaler_forward(int device, int algo, const double* dX, long long N, long long ld, const int* cols, int ncols,
+                         const double* mn, const double* mx, const double* lambda, const double* mu,
+                         const double* sd, double* dOut, long long ldo);
+
 /* ---- self-test hooks used by tests/ (each runs ONE kernel family on caller data so a
  * failing parity test names the kernel, not the pipeline).  Host pointers, row-major. */
 /* C (m x n) = op(A).op(B)^T-style products through the DMMA mainloop.

@@ -4,9 +4,10 @@
 """
 from .model import SCFGP, CompiledFuncs  # noqa: F401
 from .scaler import Scaler  # noqa: F401
+from .gpu_scaler import GpuScaler  # noqa: F401
 from .optimizer import Optimizer  # noqa: F401
 from .engine import Engine, ScfgpError  # noqa: F401
 from .sharding import shard_bounds, run_eval_phases  # noqa: F401
 
-__all__ = ["SCFGP", "Scaler", "Optimizer", "Engine", "ScfgpError", "CompiledFuncs", "shard_bounds",
+__all__ = ["SCFGP", "Scaler", "GpuScaler", "Optimizer", "Engine", "ScfgpError", "CompiledFuncs", "shard_bounds",
            "run_eval_phases"]

@@ -59,6 +59,13 @@ PROTOTYPES = {
     "scfgp_trace_dump": (C.c_int, [_h, C.c_char_p]),
     "scfgp_set_profiling": (C.c_int, [_h, C.c_int]),
     "scfgp_get_profile": (C.c_int, [_h, C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "scfgp_scaler_colstats": (C.c_int, [C.c_int, C.c_void_p, _ll, C.c_int, _ll, _dp, _dp, C.POINTER(C.c_int)]),
+    "scfgp_scaler_gather_column": (C.c_int, [C.c_int, C.c_void_p, _ll, _ll, C.c_int, C.c_double, C.c_double,
+                                             C.c_void_p]),
+    "scfgp_scaler_column_moments": (C.c_int, [C.c_int, C.c_void_p, _ll, C.c_double, _dp, _dp, _dp]),
+    "scfgp_scaler_column_distinct": (C.c_int, [C.c_int, C.c_void_p, _ll, C.c_int, C.POINTER(C.c_int)]),
+    "scfgp_scaler_forward": (C.c_int, [C.c_int, C.c_int, C.c_void_p, _ll, _ll, C.POINTER(C.c_int), C.c_int,
+                                       _dp, _dp, _dp, _dp, _dp, C.c_void_p, _ll]),
     "scfgp_dbg_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
     "scfgp_dbg_emu_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
     "scfgp_dbg_factor": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, C.POINTER(_ll)]),

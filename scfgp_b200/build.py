@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libscfgp_b200.so")
-SOURCES = ["scfgp_abi.cu"]
-DEPS = ["scfgp_abi.cu", "kernels.cuh", "gemm_dmma.cuh", "gemm_tma.cuh", "kernels_tma.cuh", "umma_i8.cuh",
+SOURCES = ["scfgp_abi.cu", "scaler_abi.cu"]
+DEPS = ["scfgp_abi.cu", "scaler_abi.cu", "kernels.cuh", "gemm_dmma.cuh", "gemm_tma.cuh", "kernels_tma.cuh", "umma_i8.cuh",
         "emu_kernels.cuh", os.path.join("..", "..", "include", "scfgp_b200.h")]
 
 NVCC_FLAGS = [

@@ -52,7 +52,7 @@ class SCFGP(object):
 
     def __init__(self, rank=None, feature_size=None, fftype=None, msg=None, *, sparsity=None, nfeats=None,
                  evals=None, X_scaling_method='auto-inv-normal', y_scaling_method='auto-normal',
-                 verbose=None, device=0, chunk_rows=None, precision=None):
+                 verbose=None, device=0, chunk_rows=None, precision=None, scaler_device='cpu'):
         # G2 spelling: SCFGP(sparsity=20, nfeats=18, ...) (SCFGP.py:33-35);
         # G1 spelling: SCFGP(rank, feature_size, fftype, msg) (README.md:47-50).
         S = sparsity if sparsity is not None else (rank if rank is not None else 20)
@@ -65,8 +65,18 @@ class SCFGP(object):
             raise ValueError(f"unknown fftype {fftype!r}; use 'phase' or 'non-phase'")
         self.fftype = _PHASE_NAMES[key]
         self.verbose = bool(verbose if verbose is not None else (msg if msg is not None else False))
-        self.X_scaler = Scaler(X_scaling_method)
-        self.y_scaler = Scaler(y_scaling_method)
+        # scaler_device='gpu': fit / apply the column scalers with the streaming kernels of
+        # gpu_scaler.py (same interface, fields and checkpoint format as the host Scaler); meant for
+        # N >= 1e6 rows where the reference's per-column host search dominates set_data
+        if scaler_device not in ('cpu', 'gpu'):
+            raise ValueError("scaler_device must be 'cpu' or 'gpu'")
+        if scaler_device == 'gpu':
+            from .gpu_scaler import GpuScaler
+            self.X_scaler = GpuScaler(X_scaling_method, device)
+            self.y_scaler = GpuScaler(y_scaling_method, device)
+        else:
+            self.X_scaler = Scaler(X_scaling_method)
+            self.y_scaler = Scaler(y_scaling_method)
         self.evals = _new_evals() if evals is None else evals
         self.device = device
         self.chunk_rows = chunk_rows

@@ -1,0 +1,124 @@
+"""Row f3 of SURVEY.md section 8: the column scalers of SCFGP/Scaler.py streamed on the GPU
+(scfgp_b200/gpu_scaler.py, C ABI scfgp_scaler_*) against the host restatement of the reference
+(scfgp_b200/scaler.py, itself pinned by tests/test_host.py)."""
+import numpy as np
+import pytest
+from scipy.stats import skew
+
+from scfgp_b200 import GpuScaler, Scaler, SCFGP
+from scfgp_b200.scaler import _boxcox
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = ["min-max", "normal", "inv-normal", "auto-normal", "auto-inv-normal"]
+
+
+def make_table(n=6000, seed=0):
+    rng = np.random.default_rng(seed)
+    cols = [
+        rng.lognormal(size=n),                          # right-skewed
+        rng.random(n),                                  # uniform
+        np.full(n, 3.25),                               # constant: dropped at fit time
+        rng.integers(0, 3, n).astype(float),            # 3 distinct values: lambda stays 1
+        rng.standard_normal(n) * 4 - 7,                 # negative values
+        -rng.gamma(2.0, size=n),                        # left-skewed
+        rng.standard_t(5, size=n),                      # heavy tails
+    ]
+    return np.stack(cols, 1)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_fit_matches_host_scaler(algo):
+    X = make_table()
+    host, gpu = Scaler(algo), GpuScaler(algo)
+    host.fit(X)
+    gpu.fit(X)
+    assert list(gpu.data["cols"]) == list(host.data["cols"]) == [0, 1, 3, 4, 5, 6]
+    for k in ("min", "max"):
+        if k in host.data:
+            np.testing.assert_array_equal(gpu.data[k], host.data[k])
+    if algo in ("normal", "inv-normal"):
+        np.testing.assert_allclose(gpu.data["mu"], host.data["mu"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(gpu.data["std"], host.data["std"], rtol=1e-12)
+    if algo.startswith("auto"):
+        lm_h, lm_g = host.data["boxcox"], gpu.data["boxcox"]
+        assert lm_g[2] == 1.0 and lm_h[2] == 1.0                    # the 3-valued column
+        # same SLSQP driver on (nearly) the same objective values: the exponents agree closely,
+        # and the GPU optimum is as good as the host one
+        np.testing.assert_allclose(lm_g, lm_h, rtol=0, atol=2e-3)
+        tX = (X[:, host.data["cols"]] - host.data["min"]) / (host.data["max"] - host.data["min"])
+        for j in range(tX.shape[1]):
+            if lm_h[j] == 1.0 and lm_g[j] == 1.0:
+                continue
+            oh = skew(_boxcox(tX[:, j], lm_h[j]), bias=False) ** 2
+            og = skew(_boxcox(tX[:, j], lm_g[j]), bias=False) ** 2
+            assert og <= oh + 1e-6, (j, og, oh)
+        np.testing.assert_allclose(gpu.data["mu"], host.data["mu"], rtol=0, atol=5e-3)
+        np.testing.assert_allclose(gpu.data["std"], host.data["std"], rtol=0, atol=5e-3)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_forward_transform_matches_host_with_same_parameters(algo):
+    """Elementwise parity of the transform kernel: both scalers hold the host-fitted fields."""
+    X = make_table(seed=1)
+    host = Scaler(algo)
+    host.fit(X)
+    gpu = GpuScaler.from_state_dict(host.state_dict())
+    assert isinstance(gpu, GpuScaler)
+    Xs = make_table(n=1234, seed=2)
+    ref = host.forward_transform(Xs)
+    out = gpu.forward_transform(Xs)
+    assert isinstance(out, np.ndarray) and out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-13)
+    # backward transform (host code shared with Scaler) inverts it where the reference's does
+    if algo != "inv-normal":
+        back = gpu.backward_transform(out)
+        np.testing.assert_allclose(back, Xs[:, host.data["cols"]], rtol=1e-6, atol=1e-7)
+
+
+def test_cuda_tensor_in_cuda_tensor_out():
+    import torch
+    X = make_table(n=3000, seed=3)
+    gpu = GpuScaler("auto-inv-normal")
+    Xt = torch.as_tensor(X, device="cuda")
+    gpu.fit(Xt)
+    out = gpu.forward_transform(Xt)
+    assert out.is_cuda and out.shape == (3000, 6)
+    o = out.cpu().numpy()
+    assert o.min() > 0 and o.max() < 1                       # normal CDF output
+    assert gpu.objective_evals > 0
+
+
+def test_moments_on_a_long_column():
+    """Size-independent property at a row count the host would crawl through: after
+    auto-normal scaling every column has mean 0, variance 1 and (near) zero skewness."""
+    import torch
+    n = 2_000_000
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    X = torch.exp(torch.randn((n, 3), dtype=torch.float64, device="cuda", generator=g))
+    sc = GpuScaler("auto-normal")
+    sc.fit(X)
+    Z = sc.forward_transform(X)
+    m = Z.mean(0).cpu().numpy(); v = Z.var(0, unbiased=False).cpu().numpy()
+    sk = ((Z - Z.mean(0)) ** 3).mean(0).cpu().numpy() / v ** 1.5
+    np.testing.assert_allclose(m, 0, atol=1e-9)
+    np.testing.assert_allclose(v, 1, rtol=1e-9)
+    assert np.abs(sk).max() < 2e-3
+
+
+def test_facade_with_gpu_scalers():
+    rng = np.random.default_rng(3)
+    N, D = 506, 13
+    X = rng.lognormal(size=(N, D))
+    yraw = np.tanh(X @ rng.standard_normal(D) / 5) * 10 + 22 + rng.standard_normal(N)
+    np.random.seed(7)
+    m_gpu = SCFGP(rank=5, feature_size=50, scaler_device="gpu")
+    m_gpu.set_data(X, yraw[:, None])
+    np.random.seed(7)
+    m_cpu = SCFGP(rank=5, feature_size=50)
+    m_cpu.set_data(X, yraw[:, None])
+    np.testing.assert_allclose(m_gpu.X, m_cpu.X, rtol=0, atol=2e-3)     # lambda search tolerance
+    np.testing.assert_allclose(m_gpu.y, m_cpu.y, rtol=0, atol=2e-3)
+    m_gpu.optimize(max_iter=15)
+    mu, sd = m_gpu.predict(X[:50])
+    assert mu.shape == (50, 1) and np.all(np.isfinite(mu)) and np.all(sd > 0)
