@@ -90,6 +90,12 @@ int scfgp_set_streams(scfgp_handle* h, int n);
 enum { SCFGP_PREC_FP64 = 0, SCFGP_PREC_EMU_I8 = 1 };
 int scfgp_set_precision(scfgp_handle* h, int mode, int digits);
 int scfgp_get_precision(const scfgp_handle* h, int* mode, int* digits);
+/* Two digit counts: `digits` for PhiT.Phi (pass 1: it feeds the Cholesky factor, alpha and Li, the
+ * results most sensitive to operand rounding) and `digits2` (0 = same) for Phi.LiT, PsiT.Phi and the
+ * backward product, whose rounding only reaches the cost through v_n and the gradient.
+ * Environment spelling: SCFGP_PRECISION=emu5/4. */
+int scfgp_set_precision2(scfgp_handle* h, int mode, int digits, int digits2);
+int scfgp_get_precision2(const scfgp_handle* h, int* mode, int* digits, int* digits2);
 
 /* Training data of train_func/train_iter_func (the X, y arguments at
  * SCFGP/SCFGP.py:230,237,265).  X is N x D row-major, y has N entries.

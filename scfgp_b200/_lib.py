@@ -37,6 +37,8 @@ PROTOTYPES = {
     "scfgp_set_streams": (C.c_int, [_h, C.c_int]),
     "scfgp_set_precision": (C.c_int, [_h, C.c_int, C.c_int]),
     "scfgp_get_precision": (C.c_int, [_h, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "scfgp_set_precision2": (C.c_int, [_h, C.c_int, C.c_int, C.c_int]),
+    "scfgp_get_precision2": (C.c_int, [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "scfgp_set_data_host": (C.c_int, [_h, _dp, _dp, _ll, _ll]),
     "scfgp_set_data_host_async": (C.c_int, [_h, _dp, _dp, _ll, _ll]),
     "scfgp_set_data_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, _ll, _ll]),

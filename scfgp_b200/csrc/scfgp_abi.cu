@@ -46,7 +46,8 @@ struct Ctx {
   int8_t *digPhiT = nullptr;  // [KS][K][R]     transposed digits of Phi
   int8_t *digPsiT = nullptr;  // [KS][K][R]     transposed digits of gv * Phi / sigma_chunk
   double *sig = nullptr;      // {sigma_chunk, 1/sigma_chunk}
-  CUtensorMap mapRowsA, mapPhiT_A, mapPhiT_B, mapPsiT_A;
+  CUtensorMap mapRowsA, mapPhiT_A, mapPhiT_B, mapPsiT_A;  // ks2 leading digit planes
+  CUtensorMap mapPhiT_A1, mapPhiT_B1;                     // ks digit planes (pass 1)
 };
 
 }  // namespace
@@ -97,7 +98,8 @@ struct scfgp_handle {
 
   // emulated-FP64 path: precision mode, digit count and the replicated digit operands
   int prec = SCFGP_PREC_FP64;
-  int ks = 5;
+  int ks = 5;                  // digits of the Phi^T Phi Gram (pass 1: feeds the Cholesky, the sensitive product)
+  int ks2 = 5;                 // digits of every other streaming product (Phi.LiT, PsiT.Phi, backward)
   long long Kp = 0;            // K rounded up to 16 (digit row pitch / offset of the Psi' half)
   double s2 = 1.0;             // power of two >= s: scale of the Phi digits
   int8_t *digLi = nullptr;     // [KS][K][Kp]
@@ -506,16 +508,20 @@ int alloc_chunk_buffers(scfgp_handle* h) {
       if ((rc = make_tmap(h, &c.mapPsi, c.Psi, K, R, h->ldk))) return rc;
     }
     if (emu_on) {
+      // The leading n digit planes of a digit array are a valid n-digit representation (balanced
+      // digits: dropping the tail rounds to nearest), so one array serves both digit counts.
       const long long Kp = h->Kp;
-      const int ks = h->ks;
-      if ((rc = dalloc(h, &c.digR, (size_t)ks * R * 2 * Kp))) return rc;
-      if ((rc = dalloc(h, &c.digPhiT, (size_t)ks * K * R))) return rc;
-      if ((rc = dalloc(h, &c.digPsiT, (size_t)ks * K * R))) return rc;
+      const int ks = h->ks, ks2 = h->ks2, ksm = std::max(ks, ks2);
+      if ((rc = dalloc(h, &c.digR, (size_t)ks2 * R * 2 * Kp))) return rc;
+      if ((rc = dalloc(h, &c.digPhiT, (size_t)ksm * K * R))) return rc;
+      if ((rc = dalloc(h, &c.digPsiT, (size_t)ks2 * K * R))) return rc;
       if ((rc = dalloc(h, &c.sig, 2))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapRowsA, c.digR, Kp + K, R, 2 * Kp, ks, umma::TM))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPhiT_A, c.digPhiT, R, K, R, ks, umma::TM))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPhiT_B, c.digPhiT, R, K, R, ks, umma::TN))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPsiT_A, c.digPsiT, R, K, R, ks, umma::TM))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapRowsA, c.digR, Kp + K, R, 2 * Kp, ks2, umma::TM))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPhiT_A, c.digPhiT, R, K, R, ks2, umma::TM))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPhiT_B, c.digPhiT, R, K, R, ks2, umma::TN))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPsiT_A, c.digPsiT, R, K, R, ks2, umma::TM))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPhiT_A1, c.digPhiT, R, K, R, ks, umma::TM))) return rc;
+      if ((rc = make_tmap_digits(h, &c.mapPhiT_B1, c.digPhiT, R, K, R, ks, umma::TN))) return rc;
     }
   }
   return SCFGP_OK;
@@ -541,7 +547,7 @@ void free_emu_static(scfgp_handle* h) {
 int alloc_emu_static(scfgp_handle* h) {
   free_emu_static(h);
   if (h->prec != SCFGP_PREC_EMU_I8) return SCFGP_OK;
-  const int K = h->K, ks = h->ks;
+  const int K = h->K, ks = h->ks2;
   const long long Kp = h->Kp;
   int rc;
   if ((rc = dalloc(h, &h->digLi, (size_t)ks * K * Kp))) return rc;
@@ -559,7 +565,8 @@ int alloc_emu_static(scfgp_handle* h) {
   h->gram_count = (int)v.size();
   CK(cudaMalloc((void**)&h->gram_items, v.size() * sizeof(int2)));
   CK(cudaMemcpy(h->gram_items, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice));
-  EMU_KS_SWITCH(ks, if ((rc = set_emu_attrs<KS>(h))) return rc);
+  EMU_KS_SWITCH(h->ks, if ((rc = set_emu_attrs<KS>(h))) return rc);
+  EMU_KS_SWITCH(h->ks2, if ((rc = set_emu_attrs<KS>(h))) return rc);
   return SCFGP_OK;
 }
 
@@ -642,10 +649,11 @@ int run_tgemm(scfgp_handle* h, Ctx& c, int rows) {
 // ---------------------------------------------------------------------------------
 int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
                     const double* rowmul, const double* rowinv, double ginv, const double* ginv_ptr, int permJ,
-                    int8_t* dst, long long pitch, long long slice_stride, int col_off) {
+                    int8_t* dst, long long pitch, long long slice_stride, int col_off, int nd = 0) {
+  if (nd == 0) nd = h->ks2;
   const long long total = (long long)rows * (cdiv(cols, 16) * 4);
   trace_begin(h, "digits_rows", st);
-  EMU_KS_SWITCH(h->ks, emu::k_digits_rows<KS><<<cdiv(total, 256), 256, 0, st>>>(
+  EMU_KS_SWITCH(nd, emu::k_digits_rows<KS><<<cdiv(total, 256), 256, 0, st>>>(
                            src, ld, rows, cols, rowmul, rowinv, ginv, ginv_ptr, permJ, dst, pitch, slice_stride, col_off));
   trace_end(h, st);
   CKL();
@@ -654,10 +662,10 @@ int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long lo
 
 int emu_digits_cols(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
                     const double* rowmul, double ginv, const double* ginv_ptr, int8_t* dst, long long pitch,
-                    long long slice_stride) {
+                    long long slice_stride, int nd) {
   const dim3 grid(cdiv(cols, 32), cdiv(rows, 128));
   trace_begin(h, "digits_cols", st);
-  EMU_KS_SWITCH(h->ks, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
+  EMU_KS_SWITCH(nd, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
                                                                     pitch, slice_stride));
   trace_end(h, st);
   CKL();
@@ -684,9 +692,11 @@ int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_SYRK, c.sg);
-  EMU_KS_SWITCH(h->ks, emu::k_gram_i8<KS><<<h->gram_count, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           a_is_psi ? c.mapPsiT_A : c.mapPhiT_A, c.mapPhiT_B, depth, h->K, h->gram_items, c.acc, h->ldk,
-                           h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
+  // pass 1 (G, feeds the Cholesky): ks digits; pass 2 (H): ks2 leading digits
+  EMU_KS_SWITCH(a_is_psi ? h->ks2 : h->ks,
+                emu::k_gram_i8<KS><<<h->gram_count, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                    a_is_psi ? c.mapPsiT_A : c.mapPhiT_A1, a_is_psi ? c.mapPhiT_B : c.mapPhiT_B1, depth, h->K,
+                    h->gram_items, c.acc, h->ldk, h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
   prof_end(h, SCFGP_FAM_SYRK, c.sg);
   CKL();
   return gemm_leave(h, c);
@@ -697,7 +707,7 @@ int emu_tgemm(scfgp_handle* h, Ctx& c, int rows) {
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
-  EMU_KS_SWITCH(h->ks, emu::k_tgemm_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+  EMU_KS_SWITCH(h->ks2, emu::k_tgemm_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                            c.mapRowsA, h->mapLiB, rows, h->K, h->liscale, h->s2, c.vpart, h->R));
   prof_end(h, SCFGP_FAM_TGEMM, c.sg);
   CKL();
@@ -709,7 +719,7 @@ int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0) {
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
-  EMU_KS_SWITCH(h->ks, emu::k_backward_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+  EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                            c.mapRowsA, h->mapCB, rows, h->J, (int)(h->Kp + h->K), h->cscale, h->s2, c.Phi, h->ldk,
                            h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj, c.slots));
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
@@ -928,6 +938,11 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
       h->prec = SCFGP_PREC_EMU_I8;
       const int d = atoi(e + 3);
       h->ks = (d >= 4 && d <= 8) ? d : 5;
+      h->ks2 = h->ks;
+      if (const char* sl = strchr(e, '/')) {
+        const int d2 = atoi(sl + 1);
+        if (d2 >= 4 && d2 <= 8) h->ks2 = d2;
+      }
       h->R = 8192;
     }
   }
@@ -1015,15 +1030,19 @@ int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
   return alloc_chunk_buffers(h);
 }
 
-int scfgp_set_precision(scfgp_handle* h, int mode, int digits) {
+int scfgp_set_precision(scfgp_handle* h, int mode, int digits) { return scfgp_set_precision2(h, mode, digits, digits); }
+
+int scfgp_set_precision2(scfgp_handle* h, int mode, int digits, int digits2) {
   if (!h || (mode != SCFGP_PREC_FP64 && mode != SCFGP_PREC_EMU_I8)) return SCFGP_ERR_ARG;
   if (digits == 0) digits = 5;
-  if (digits < 4 || digits > 8) { h->err = "digits must be 4..8"; return SCFGP_ERR_ARG; }
+  if (digits2 == 0) digits2 = digits;
+  if (digits < 4 || digits > 8 || digits2 < 4 || digits2 > 8) { h->err = "digits must be 4..8"; return SCFGP_ERR_ARG; }
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
   h->upload_pending = false;  // (the device-wide sync above completed any upload)
   h->prec = mode;
   h->ks = digits;
+  h->ks2 = digits2;
   if (!h->R_user) h->R = mode == SCFGP_PREC_EMU_I8 ? 8192 : 4096;
   h->have_factors = false;
   int rc;
@@ -1035,6 +1054,14 @@ int scfgp_get_precision(const scfgp_handle* h, int* mode, int* digits) {
   if (!h) return SCFGP_ERR_ARG;
   if (mode) *mode = h->prec;
   if (digits) *digits = h->ks;
+  return SCFGP_OK;
+}
+
+int scfgp_get_precision2(const scfgp_handle* h, int* mode, int* digits, int* digits2) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (mode) *mode = h->prec;
+  if (digits) *digits = h->ks;
+  if (digits2) *digits2 = h->ks2;
   return SCFGP_OK;
 }
 
@@ -1158,7 +1185,7 @@ int scfgp_eval_pass1(scfgp_handle* h) {
     if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
     if (h->prec == SCFGP_PREC_EMU_I8) {
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
-                                (long long)K * h->R)))
+                                (long long)K * h->R, h->ks)))
         return rc;
       if ((rc = emu_gram(h, c, false, rows))) return rc;
     } else {
@@ -1281,10 +1308,10 @@ int scfgp_eval_pass2(scfgp_handle* h) {
       trace_end(h, c.st);
     CKL();
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
-                                (long long)K * h->R)))
+                                (long long)K * h->R, h->ks2)))
         return rc;
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, h->gv + r0, 1.0 / h->s2, c.sig + 1, c.digPsiT, h->R,
-                                (long long)K * h->R)))
+                                (long long)K * h->R, h->ks2)))
         return rc;
       if ((rc = emu_gram(h, c, true, rows))) return rc;
       trace_begin(h, "colsum", c.st);
@@ -1730,7 +1757,7 @@ int scfgp_dbg_emu_gemm(int device, int digits, int m, int n, int k, const double
   scfgp_handle tmp;
   scfgp_handle* h = &tmp;
   h->device = device;
-  h->ks = digits;
+  h->ks = h->ks2 = digits;
   CK(cudaSetDevice(device));
   const long long kp = (k + 15) / 16 * 16;
   double *dA = nullptr, *dB = nullptr, *dC = nullptr, *sc = nullptr;

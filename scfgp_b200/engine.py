@@ -97,18 +97,25 @@ class Engine:
         tensor cores with 4..8 base-256 digits; 'emu' = 5)."""
         p = str(precision).lower()
         if p == "fp64":
-            mode, digits = _lib.PREC_FP64, 0
+            mode, digits, digits2 = _lib.PREC_FP64, 0, 0
         elif p.startswith("emu"):
-            mode, digits = _lib.PREC_EMU_I8, int(p[3:] or 0)
+            # 'emu5/4': 5 digits for the Gram that feeds the Cholesky, 4 for the other products
+            a, _, b = p[3:].partition("/")
+            try:
+                mode, digits, digits2 = _lib.PREC_EMU_I8, int(a or 0), int(b or 0)
+            except ValueError:
+                raise ValueError(f"unknown precision {precision!r}") from None
         else:
             raise ValueError(f"unknown precision {precision!r}")
-        self._check(self.lib.scfgp_set_precision(self._h, mode, digits))
+        self._check(self.lib.scfgp_set_precision2(self._h, mode, digits, digits2))
 
     @property
     def precision(self) -> str:
-        m, d = C.c_int(), C.c_int()
-        self.lib.scfgp_get_precision(self._h, C.byref(m), C.byref(d))
-        return "fp64" if m.value == _lib.PREC_FP64 else f"emu{d.value}"
+        m, d, d2 = C.c_int(), C.c_int(), C.c_int()
+        self.lib.scfgp_get_precision2(self._h, C.byref(m), C.byref(d), C.byref(d2))
+        if m.value == _lib.PREC_FP64:
+            return "fp64"
+        return f"emu{d.value}" if d2.value == d.value else f"emu{d.value}/{d2.value}"
 
     def set_streams(self, n: int):
         self._check(self.lib.scfgp_set_streams(self._h, int(n)))
