@@ -226,28 +226,36 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
 k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int depth, int K,
-          const int2* __restrict__ items, double* __restrict__ C, long long ldc, double scale,
+          const int2* __restrict__ items, int ntiles, double* __restrict__ C, long long ldc, double scale,
           const double* __restrict__ scale_ptr) {
   extern __shared__ uint8_t smem_raw[];
   umma::Pipe p = umma::pipe_init<KS>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
-  const int2 it = items[blockIdx.x];
-  umma::Tile t;
-  t.m0 = it.x * TM;
-  t.n0 = it.y * TN;
-  t.c_begin = 0;
-  t.c_end = depth;
-  if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
-    umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, 0);
-  } else {
-    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, 0);
+  const bool front = (threadIdx.x >> 5) < umma::EPI_WARP0;
+  int it0 = 0, seq = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
+    const int2 it = items[tile];
+    umma::Tile t;
+    t.m0 = it.x * TM;
+    t.n0 = it.y * TN;
+    t.c_begin = 0;
+    t.c_end = depth;
+    if (front) {
+      umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, it0, seq);
+      it0 += umma::tile_stages(t);
+      continue;
+    }
+    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, seq & 1);
     const int a = t.m0 + e.row;
     const double sc = scale * (scale_ptr ? *scale_ptr : 1.0) * umma::PROD_SCALE;
-#pragma unroll 1
-    for (int h16 = 0; h16 < 2; ++h16) {
-      double v[16];
-      umma::epilogue_load16<KS>(e, e.col0 + 16 * h16, v);   // warp-collective: before any row guard
-      if (a < K) {
+    double v0[16], v1[16];
+    umma::epilogue_load16<KS>(e, e.col0, v0);       // warp-collective: before any row guard
+    umma::epilogue_load16<KS>(e, e.col0 + 16, v1);
+    umma::epilogue_release(p);                      // TMEM is free: the next tile's MMAs may start
+    if (a < K) {
+#pragma unroll
+      for (int h16 = 0; h16 < 2; ++h16) {
+        const double* v = h16 ? v1 : v0;
         const int b0 = t.n0 + e.col0 + 16 * h16;
         double* crow = C + (long long)a * ldc + b0;
         const int nvalid = K - b0;
@@ -276,26 +284,32 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
 k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int rows, int K,
-           const double* __restrict__ liscale, double sA, double* __restrict__ vpart, long long ldv) {
+           int ntiles, const double* __restrict__ liscale, double sA, double* __restrict__ vpart, long long ldv) {
   extern __shared__ uint8_t smem_raw[];
-  const int nb = (int)gridDim.x - 1 - (int)blockIdx.x;
-  umma::Tile t;
-  t.m0 = blockIdx.y * TM;
-  t.n0 = nb * TN;
-  t.c_begin = 0;
-  t.c_end = min(K, t.n0 + TN);  // Li is lower triangular
-  if (t.m0 >= rows) return;     // short last chunk: the whole CTA leaves before any barrier
   umma::Pipe p = umma::pipe_init<KS>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
-  if ((threadIdx.x >> 5) < umma::EPI_WARP0) {
-    umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapLi, t, 0);
-  } else {
-    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, 0);
+  const bool front = (threadIdx.x >> 5) < umma::EPI_WARP0;
+  const int nnb = (K + TN - 1) / TN;
+  int it0 = 0, seq = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
+    const int nb = nnb - 1 - tile % nnb;   // deepest reduction first within a row block
+    umma::Tile t;
+    t.m0 = (tile / nnb) * TM;
+    t.n0 = nb * TN;
+    t.c_begin = 0;
+    t.c_end = min(K, t.n0 + TN);  // Li is lower triangular
+    if (front) {
+      umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapLi, t, it0, seq);
+      it0 += umma::tile_stages(t);
+      continue;
+    }
+    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, seq & 1);
     double sq = 0;
 #pragma unroll 1
     for (int h16 = 0; h16 < 2; ++h16) {
       double v[16];
       umma::epilogue_load16<KS>(e, e.col0 + 16 * h16, v);
+      if (h16 == 1) umma::epilogue_release(p);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int j = t.n0 + e.col0 + 16 * h16 + c;
@@ -319,25 +333,30 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
 k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, int rows, int J,
-              int depth2, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
+              int depth2, int ntiles, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
               long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
               const double* __restrict__ pbar, const double* __restrict__ alpha, double* __restrict__ Zbar,
               long long ldz, double* __restrict__ slots) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ double sh[8];
-  umma::Tile t;
-  t.m0 = blockIdx.y * TM;
-  t.n0 = blockIdx.x * TN;
-  t.c_begin = 0;
-  t.c_end = depth2;
-  if (t.m0 >= rows) return;
   umma::Pipe p = umma::pipe_init<KS>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < umma::EPI_WARP0) {
-    umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapC, t, 0);
-  } else {
-    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, 0);
+  const bool front = warp < umma::EPI_WARP0;
+  const int nfb = (J + 31) / 32;
+  int it0 = 0, seq = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
+    umma::Tile t;
+    t.m0 = (tile / nfb) * TM;     // row-block major: consecutive tiles share the A operand in L2
+    t.n0 = (tile % nfb) * TN;
+    t.c_begin = 0;
+    t.c_end = depth2;
+    if (front) {
+      umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapC, t, it0, seq);
+      it0 += umma::tile_stages(t);
+      continue;
+    }
+    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, seq & 1);
     const int r = t.m0 + e.row;
     const bool rvalid = r < rows;
     const double sc = sA * umma::PROD_SCALE;
@@ -349,6 +368,7 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       double v[16];
       const int pcol = e.col0 + 16 * h16;                 // permuted tile column of v[0]
       umma::epilogue_load16<KS>(e, pcol, v);
+      if (h16 == 1) umma::epilogue_release(p);
       if (rvalid) {
         const int f0 = (t.n0 + pcol) >> 1;
 #pragma unroll
@@ -366,12 +386,13 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       }
     }
     sacc = warp_sum(sacc);
+    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");   // sh[] of the previous tile consumed
     if (lane == 0) sh[warp - umma::EPI_WARP0] = sacc;
     asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");
     if (warp == umma::EPI_WARP0 && lane == 0) {
-      double s = 0;
-      for (int w = 0; w < 8; ++w) s += sh[w];
-      slots[blockIdx.y * gridDim.x + blockIdx.x] += s;
+      double sum = 0;
+      for (int w = 0; w < 8; ++w) sum += sh[w];
+      slots[tile] += sum;
     }
   }
   umma::pipe_teardown<KS>(p, tmem_base);

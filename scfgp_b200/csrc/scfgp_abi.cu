@@ -98,6 +98,7 @@ struct scfgp_handle {
 
   // emulated-FP64 path: precision mode, digit count and the replicated digit operands
   int prec = SCFGP_PREC_FP64;
+  int num_sms = 148;
   int ks = 5;                  // digits of the Phi^T Phi Gram (pass 1: feeds the Cholesky, the sensitive product)
   int ks2 = 5;                 // digits of every other streaming product (Phi.LiT, PsiT.Phi, backward)
   long long Kp = 0;            // K rounded up to 16 (digit row pitch / offset of the Psi' half)
@@ -694,33 +695,33 @@ int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
   prof_begin(h, SCFGP_FAM_SYRK, c.sg);
   // pass 1 (G, feeds the Cholesky): ks digits; pass 2 (H): ks2 leading digits
   EMU_KS_SWITCH(a_is_psi ? h->ks2 : h->ks,
-                emu::k_gram_i8<KS><<<h->gram_count, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                emu::k_gram_i8<KS><<<std::min(h->gram_count, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                     a_is_psi ? c.mapPsiT_A : c.mapPhiT_A1, a_is_psi ? c.mapPhiT_B : c.mapPhiT_B1, depth, h->K,
-                    h->gram_items, c.acc, h->ldk, h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
+                    h->gram_items, h->gram_count, c.acc, h->ldk, h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
   prof_end(h, SCFGP_FAM_SYRK, c.sg);
   CKL();
   return gemm_leave(h, c);
 }
 
 int emu_tgemm(scfgp_handle* h, Ctx& c, int rows) {
-  const dim3 grid(cdiv(h->K, umma::TN), cdiv(rows, umma::TM));
+  const int ntiles = cdiv(h->K, umma::TN) * cdiv(rows, umma::TM);
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
-  EMU_KS_SWITCH(h->ks2, emu::k_tgemm_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           c.mapRowsA, h->mapLiB, rows, h->K, h->liscale, h->s2, c.vpart, h->R));
+  EMU_KS_SWITCH(h->ks2, emu::k_tgemm_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                           c.mapRowsA, h->mapLiB, rows, h->K, ntiles, h->liscale, h->s2, c.vpart, h->R));
   prof_end(h, SCFGP_FAM_TGEMM, c.sg);
   CKL();
   return gemm_leave(h, c);
 }
 
 int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0) {
-  const dim3 grid(cdiv(h->J, 32), cdiv(rows, umma::TM));
+  const int ntiles = cdiv(h->J, 32) * cdiv(rows, umma::TM);
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
-  EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           c.mapRowsA, h->mapCB, rows, h->J, (int)(h->Kp + h->K), h->cscale, h->s2, c.Phi, h->ldk,
+  EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                           c.mapRowsA, h->mapCB, rows, h->J, (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk,
                            h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj, c.slots));
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
@@ -950,6 +951,7 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) { h->err = "no such CUDA device"; return SCFGP_ERR_CUDA; }
   CK(cudaSetDevice(device));
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   int rc;
   if ((rc = set_kernel_attrs(h))) return rc;
   const size_t K = h->K, KK = K * h->ldk;

@@ -157,7 +157,8 @@ struct Pipe {
   uint8_t* stages;
   uint64_t* full;
   uint64_t* empty;
-  uint64_t* acc_full;
+  uint64_t* acc_full;   // MMA -> epilogue: the tile's accumulators are complete
+  uint64_t* acc_empty;  // epilogue -> MMA: the accumulators have been read, the next tile may overwrite them
   uint32_t* tmem_slot;
 };
 
@@ -170,13 +171,15 @@ __device__ __forceinline__ Pipe pipe_init(uint8_t* smem_raw) {
   p.full = reinterpret_cast<uint64_t*>(p.stages + (size_t)G::STAGES * G::STAGE_BYTES);
   p.empty = p.full + G::STAGES;
   p.acc_full = p.empty + G::STAGES;
-  p.tmem_slot = reinterpret_cast<uint32_t*>(p.acc_full + 1);
+  p.acc_empty = p.acc_full + 1;
+  p.tmem_slot = reinterpret_cast<uint32_t*>(p.acc_empty + 1);
   if (threadIdx.x == 0) {
     for (int s = 0; s < G::STAGES; ++s) {
       mbar_init(&p.full[s], 1);
       mbar_init(&p.empty[s], 1);
     }
     mbar_init(p.acc_full, 1);
+    mbar_init(p.acc_empty, EPI_THREADS / 32);
     mbar_fence_init();
   }
   if ((threadIdx.x >> 5) == 1) tmem_alloc(p.tmem_slot, G::TMEM_COLS);
@@ -196,11 +199,17 @@ __device__ __forceinline__ void pipe_teardown(const Pipe& p, uint32_t tmem_base)
   }
 }
 
-// producer + MMA roles of one tile (warps 0 and 1).  `it0` = pipeline iterations already
-// consumed by earlier tiles of this CTA (keeps the barrier phases running).
+// Persistent CTAs: every CTA walks the tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (`seq` =
+// 0, 1, 2, ... counts the tiles of this CTA).  The producer keeps streaming stages across tile
+// boundaries (the ring's phases simply continue: `it0` = stages consumed by earlier tiles), so
+// the next tile's operands are already in flight while the epilogue drains the accumulators;
+// the MMA warp only has to wait for the epilogue to release TMEM (acc_empty).
+__device__ __forceinline__ int tile_stages(const Tile& t) { return (t.c_end - t.c_begin + KB - 1) / KB; }
+
+// producer + MMA roles of one tile (warps 0 and 1)
 template <int KS>
 __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, const CUtensorMap* mapA,
-                                             const CUtensorMap* mapB, const Tile& t, int it0) {
+                                             const CUtensorMap* mapB, const Tile& t, int it0, int seq = 0) {
   using G = Geo<KS>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (t.c_end - t.c_begin + KB - 1) / KB;
@@ -219,6 +228,10 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      if (seq > 0) {
+        mbar_wait(p.acc_empty, (uint32_t)(seq - 1) & 1u);
+        tc_fence_after();
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         const int it = it0 + kb;
         const int st = it % G::STAGES;
@@ -280,6 +293,12 @@ __device__ __forceinline__ EpiPos epilogue_wait(const Pipe& p, uint32_t tmem_bas
   mbar_wait_long(p.acc_full, acc_parity);
   tc_fence_after();
   return e;
+}
+// after the last epilogue_load16 of a tile: hand the accumulators back to the MMA warp
+__device__ __forceinline__ void epilogue_release(const Pipe& p) {
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(p.acc_empty);
 }
 // v[c] = sum_q 2^(-8q) acc_q[row][col + c], c < 16   (col = tile column, multiple of 16)
 template <int KS>
