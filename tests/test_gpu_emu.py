@@ -282,3 +282,49 @@ def test_cfg5_geometry_reduced_rows_both_modes():
         assert np.abs(al - al0).max() <= atol * max(1.0, np.abs(al0).max()), prec
         assert np.abs(Li - Li0).max() <= atol * max(1.0, np.abs(Li0).max()), prec
         eng.close()
+
+
+def test_errors_surface_in_emulated_mode():
+    """The digit extraction would turn NaN / Inf into finite integers; the float64 side paths
+    (Phi^T y, Phi alpha) still carry them into the cost, and the factorisation reports a
+    non-positive-definite A exactly as in FP64 mode."""
+    eng = Engine(4, 2, 8, precision="emu5")
+    X = np.random.default_rng(0).random((300, 4)); y = np.random.default_rng(1).standard_normal(300)
+    h = synth.draw_params(4, 2, 8, np.random.default_rng(1))
+    eng.set_data(X, y)
+    c, g, _, _ = eng.eval(h)
+    assert np.isfinite(c) and np.all(np.isfinite(g))
+    Xbad = X.copy(); Xbad[17, 2] = np.nan
+    eng.set_data(Xbad, y)
+    with pytest.raises((FloatingPointError, np.linalg.LinAlgError)):
+        eng.eval(h)
+    Xbad[17, 2] = np.inf
+    eng.set_data(Xbad, y)
+    with pytest.raises((FloatingPointError, np.linalg.LinAlgError)):
+        eng.eval(h)
+    eng.set_data(X, y)
+    hb = h.copy(); hb[0] = -400.0; hb[1] = 200.0          # sig2_n -> 0, sig_f huge
+    with pytest.raises((np.linalg.LinAlgError, FloatingPointError)):
+        eng.eval(hb)
+    c2, _, _, _ = eng.eval(h)                              # the handle stays usable
+    assert c2 == c
+    eng.close()
+
+
+def test_async_upload_matches_synchronous():
+    """scfgp_set_data_host_async: row blocks land while pass 1 runs; same bits as the blocking copy."""
+    N, D, S, M = 70000, 8, 4, 60
+    X, y, h = synth.make_problem(N, D, S, M, seed=31)
+    eng = Engine(D, S, M, precision="emu5", chunk_rows=1024)
+    eng.set_data(X, y)
+    r1 = eng.eval(h)
+    for _ in range(2):
+        eng.set_data(X, y, overlap=True)
+        r2 = eng.eval(h)
+        assert r1[0] == r2[0]
+        np.testing.assert_array_equal(r1[1], r2[1])
+    X2 = X[::-1].copy(); y2 = y[::-1].copy()               # new data through the same buffers
+    eng.set_data(X2, y2, overlap=True)
+    r3 = eng.eval(h)
+    assert abs(r3[0] - r1[0]) <= 1e-9 * abs(r1[0])         # a row permutation only reorders the sums
+    eng.close()
