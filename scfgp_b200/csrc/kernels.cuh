@@ -134,29 +134,37 @@ k_features(const double* __restrict__ X, long long ldx, int rows, int D,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+  // A thread's two accumulators of a fragment are neighbouring features (2t, 2t+1): they leave
+  // as one 16-byte store where the addresses allow it (ldp even; sin half needs J even).
+  const bool vec_c = (ldp & 1) == 0 && (reinterpret_cast<uintptr_t>(Phi) & 15) == 0 &&
+                     (Psi == nullptr || (reinterpret_cast<uintptr_t>(Psi) & 15) == 0);
+  const bool vec_s = vec_c && (J & 1) == 0;
 #pragma unroll
   for (int j = 0; j < Cfg::NI; ++j) {
+    const int f = n0 + wn0 + 8 * j + 2 * t;   // even
+    if (f >= J) continue;
+    const bool two = f + 1 < J;
+    const double ph0 = phi[f], ph1 = two ? phi[f + 1] : 0.0;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int f = n0 + wn0 + 8 * j + 2 * t + e;
-      if (f >= J) continue;
-      const double ph = phi[f];
-#pragma unroll
-      for (int i = 0; i < Cfg::MI; ++i) {
-        const int r = m0 + wm0 + 8 * i + g;
-        if (r >= rows) continue;
-        double sn, cs;
-        sincos(acc[i][j][e] + ph, &sn, &cs);
-        cs *= s; sn *= s;
-        double* row = Phi + (long long)r * ldp;
-        row[f] = cs;
-        row[J + f] = sn;
-        if (Psi != nullptr) {
-          const double w = rowscale[r];
-          double* prow = Psi + (long long)r * ldp;
-          prow[f] = w * cs;
-          prow[J + f] = w * sn;
-        }
+    for (int i = 0; i < Cfg::MI; ++i) {
+      const int r = m0 + wm0 + 8 * i + g;
+      if (r >= rows) continue;
+      double sn0, cs0, sn1 = 0.0, cs1 = 0.0;
+      sincos(acc[i][j][0] + ph0, &sn0, &cs0);
+      if (two) sincos(acc[i][j][1] + ph1, &sn1, &cs1);
+      cs0 *= s; sn0 *= s; cs1 *= s; sn1 *= s;
+      double* row = Phi + (long long)r * ldp;
+      if (two && vec_c) *reinterpret_cast<double2*>(row + f) = make_double2(cs0, cs1);
+      else { row[f] = cs0; if (two) row[f + 1] = cs1; }
+      if (two && vec_s) *reinterpret_cast<double2*>(row + J + f) = make_double2(sn0, sn1);
+      else { row[J + f] = sn0; if (two) row[J + f + 1] = sn1; }
+      if (Psi != nullptr) {
+        const double w = rowscale[r];
+        double* prow = Psi + (long long)r * ldp;
+        if (two && vec_c) *reinterpret_cast<double2*>(prow + f) = make_double2(w * cs0, w * cs1);
+        else { prow[f] = w * cs0; if (two) prow[f + 1] = w * cs1; }
+        if (two && vec_s) *reinterpret_cast<double2*>(prow + J + f) = make_double2(w * sn0, w * sn1);
+        else { prow[J + f] = w * sn0; if (two) prow[J + f + 1] = w * sn1; }
       }
     }
   }
