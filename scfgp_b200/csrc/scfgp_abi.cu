@@ -444,6 +444,27 @@ int ensure_row_arrays(scfgp_handle* h, long long n) {
   return SCFGP_OK;
 }
 
+// Exactness of the emulated path: every class sum must fit int32.  With the leading digit within
+// +-64 and the others within +-128 the largest class (q = ks - 1) is bounded by
+// depth * 16384 * (ks - 1), so reduction depths (rows per chunk for the Gram products, Kp + K for
+// the backward product) are limited to (2^31 - 1) / (16384 (ks - 1)).
+inline long long emu_max_depth(int ks) { return 2147483647ll / (16384ll * (ks - 1)); }
+int emu_check_depths(scfgp_handle* h) {
+  if (h->prec != SCFGP_PREC_EMU_I8) return SCFGP_OK;
+  const long long lim = emu_max_depth(std::max(h->ks, h->ks2));
+  if (h->R > lim) {
+    h->err = "chunk_rows " + std::to_string(h->R) + " exceeds the exact-int32 depth limit " + std::to_string(lim) +
+             " of the emulated mode at this digit count";
+    return SCFGP_ERR_ARG;
+  }
+  if (h->Kp + h->K > lim) {
+    h->err = "2K = " + std::to_string(2 * h->K) + " features exceed the exact-int32 depth limit " +
+             std::to_string(lim) + " of the emulated mode at this digit count";
+    return SCFGP_ERR_ARG;
+  }
+  return SCFGP_OK;
+}
+
 // (re)allocate everything that depends on the chunk size R / number of streams
 int alloc_chunk_buffers(scfgp_handle* h) {
   for (int i = 0; i < kMaxStreams; ++i) {
@@ -994,6 +1015,7 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
     if ((rc = make_tmap(h, &h->mapB2, h->B2, K, K, h->ldk))) return rc;
   }
   if ((rc = build_static_lists(h))) return rc;
+  if ((rc = emu_check_depths(h))) return rc;
   if ((rc = alloc_emu_static(h))) return rc;
   if ((rc = alloc_chunk_buffers(h))) return rc;
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -1027,7 +1049,10 @@ int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
   h->upload_pending = false;  // (the device-wide sync above completed any upload)
+  const int old_R = h->R;
   h->R = rows;
+  int rc;
+  if ((rc = emu_check_depths(h))) { h->R = old_R; return rc; }
   h->R_user = true;
   return alloc_chunk_buffers(h);
 }
@@ -1042,12 +1067,14 @@ int scfgp_set_precision2(scfgp_handle* h, int mode, int digits, int digits2) {
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
   h->upload_pending = false;  // (the device-wide sync above completed any upload)
+  const int o_prec = h->prec, o_ks = h->ks, o_ks2 = h->ks2, o_R = h->R;
   h->prec = mode;
   h->ks = digits;
   h->ks2 = digits2;
   if (!h->R_user) h->R = mode == SCFGP_PREC_EMU_I8 ? 8192 : 4096;
-  h->have_factors = false;
   int rc;
+  if ((rc = emu_check_depths(h))) { h->prec = o_prec; h->ks = o_ks; h->ks2 = o_ks2; h->R = o_R; return rc; }
+  h->have_factors = false;
   if ((rc = alloc_emu_static(h))) return rc;
   return alloc_chunk_buffers(h);
 }

@@ -7,8 +7,9 @@
 // keeps the balanced representation inside int8).  A product  sum_c X[m,c] Y[n,c]  is then
 //     sum_{i,j} 2^(-8(i+j)) * ( sum_c dX_i[m,c] dY_j[n,c] )   * scaleX scaleY 2^-14 ,
 // truncated to the "classes"  i + j = q < KS  (the dropped terms are below the digit
-// quantisation error).  Every class sum is an exact int32 (depth * (q+1) * 2^14 < 2^31, i.e.
-// reduction depths up to 16384 at 8 digits).
+// quantisation error).  Every class sum is an exact int32: |class q| <= depth * 16384 * (KS - 1)
+// (leading digit within +-64), so the host refuses reduction depths beyond
+// (2^31 - 1) / (16384 (KS - 1)) = 32767 at 5 digits, 18724 at 8.
 //
 // Tile = 128 rows (TMEM lanes) x 64 columns.  Class q owns TMEM columns [64 q, 64 q + 64):
 // all KS classes are resident, so one pass over the contraction does every digit product.

@@ -328,3 +328,29 @@ def test_async_upload_matches_synchronous():
     r3 = eng.eval(h)
     assert abs(r3[0] - r1[0]) <= 1e-9 * abs(r1[0])         # a row permutation only reorders the sums
     eng.close()
+
+
+def test_depth_limit_is_enforced():
+    """Reduction depths that could overflow an int32 class sum are refused, not silently wrong."""
+    eng = Engine(4, 2, 8, precision="emu5")
+    with pytest.raises(ValueError):
+        eng._check(eng.lib.scfgp_set_chunk_rows(eng._h, 32768))       # limit at 5 digits: 32767
+    eng._check(eng.lib.scfgp_set_chunk_rows(eng._h, 16384))
+    with pytest.raises(ValueError):
+        eng.set_precision("emu8")                                     # 16384 rows < 18724: fine ...
+        eng._check(eng.lib.scfgp_set_chunk_rows(eng._h, 18816))       # ... but not 18816
+    eng.close()
+
+
+@pytest.mark.parametrize("digits", [4, 5, 6])
+@pytest.mark.parametrize("mnk", [(130, 70, 33), (257, 129, 500), (128, 64, 2080)])
+def test_digit_gemm_bit_exact_against_cpu_restatement(digits, mnk):
+    """Scales, digit extraction, int32 class sums (tcgen05.mma kind::i8) and the float64
+    recombination reproduce oracle/emu_digits.py (NumPy int64) bit for bit."""
+    from oracle import emu_digits as ED
+    m, n, k = mnk
+    rng = np.random.default_rng(11 * m + n + k + digits)
+    A = rng.standard_normal((m, k)) * np.exp(2 * rng.standard_normal((m, 1)))
+    B = rng.standard_normal((n, k)) * np.exp(2 * rng.standard_normal((n, 1)))
+    A[5] = 0.0                                              # an all-zero row (scale 2)
+    np.testing.assert_array_equal(E.dbg_emu_gemm(A, B, digits), ED.emu_gemm(A, B, digits))
