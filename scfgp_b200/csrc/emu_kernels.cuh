@@ -126,7 +126,10 @@ template <int KS>
 __global__ void __launch_bounds__(256)
 k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols, const double* __restrict__ rowmul,
               const double* __restrict__ rowinv, double ginv, const double* __restrict__ ginv_ptr, int perm_J,
-              int8_t* __restrict__ dst, long long pitch, long long slice_stride, int col_off) {
+              int8_t* __restrict__ dst, long long pitch, long long slice_stride, int col_off,
+              const double* __restrict__ rowmul2, const double* __restrict__ ginv_ptr2, int col_off2) {
+  // optional second output from the same read of src (pass 3: [Phi | (gv / sigma) Phi]):
+  //   dst[s][r][col_off2 + c] = digit s of src[r][c] * rowmul2[r] * ginv * *ginv_ptr2
   const int ngroups = (cols + 15) / 16 * 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)rows * ngroups) return;
@@ -159,6 +162,21 @@ k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols, 
   *reinterpret_cast<uint32_t*>(o) = packed[0];
 #pragma unroll
   for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * slice_stride) = fix_bytes(packed[s]);
+  if (rowmul2) {
+    const double mult2 = digit_mult<KS>() * ginv * (ginv_ptr2 ? *ginv_ptr2 : 1.0) * rowmul2[r];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) packed[s] = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long qp = biased_q<KS>(x[e] * mult2);
+#pragma unroll
+      for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
+    }
+    int8_t* o2 = dst + (long long)orow * pitch + col_off2 + g * 4;
+    *reinterpret_cast<uint32_t*>(o2) = packed[0];
+#pragma unroll
+    for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o2 + (long long)s * slice_stride) = fix_bytes(packed[s]);
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -174,7 +192,12 @@ template <int KS>
 __global__ void __launch_bounds__(256)
 k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, const double* __restrict__ rowmul,
               double ginv, const double* __restrict__ ginv_ptr, int8_t* __restrict__ dst, long long pitch,
-              long long slice_stride) {
+              long long slice_stride, const double* __restrict__ wsum, double* __restrict__ cpart,
+              long long ldpart) {
+  // optional by-product (saves a separate pass over the slab): weighted column sums of the RAW
+  // source, cpart[blockIdx.y][c] += sum over this block's 128 rows of wsum[r] * src[r][c]
+  // (p = PhiT.y in pass 1, q = PhiT.gmu in pass 2); fixed summation order
+  __shared__ double csum[8][32];
   __shared__ uint32_t sm[KS][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 128;
@@ -185,6 +208,15 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
   for (int e = 0; e < 16; ++e) {
     const int r = r0 + warp * 16 + e;
     x[e] = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.0;
+  }
+  if (wsum) {
+    double a = 0.0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int r = r0 + warp * 16 + e;
+      if (r < rows) a = fma(wsum[r], x[e], a);
+    }
+    csum[warp][lane] = a;
   }
   if (rowmul) {
 #pragma unroll
@@ -209,6 +241,12 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
     for (int s = 1; s < KS; ++s) sm[s][lane][warp * 4 + k] = fix_bytes(packed[s]);
   }
   __syncthreads();
+  if (wsum && warp == 0 && c < cols) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += csum[w][lane];
+    cpart[(long long)blockIdx.y * ldpart + c] += a;
+  }
   for (int p = warp; p < KS * 32; p += 8) {
     const int s = p >> 5, cc = p & 31;
     if (c0 + cc < cols)
@@ -336,9 +374,11 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               int depth2, int ntiles, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
               long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
               const double* __restrict__ pbar, const double* __restrict__ alpha, double* __restrict__ Zbar,
-              long long ldz, double* __restrict__ slots) {
+              long long ldz, double* __restrict__ slots, double* __restrict__ dphi_part, long long ldpart) {
+  // dphi_part[row block][f] += column sums of the tile's Zbar (dphi = colsum(Zbar), A.5)
   extern __shared__ uint8_t smem_raw[];
   __shared__ double sh[8];
+  __shared__ double shcol[8][16];
   umma::Pipe p = umma::pipe_init<KS>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -363,36 +403,54 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const double yn = rvalid ? y[r] : 0.0, gm = rvalid ? gmu[r] : 0.0;
     const double* prow = Phi + (long long)(rvalid ? r : 0) * ldp;
     double sacc = 0;
+    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");   // sh[], shcol[] of the previous tile consumed
 #pragma unroll 1
     for (int h16 = 0; h16 < 2; ++h16) {
       double v[16];
       const int pcol = e.col0 + 16 * h16;                 // permuted tile column of v[0]
       umma::epilogue_load16<KS>(e, pcol, v);
       if (h16 == 1) umma::epilogue_release(p);
-      if (rvalid) {
-        const int f0 = (t.n0 + pcol) >> 1;
+      double zb[8];
+      const int f0 = (t.n0 + pcol) >> 1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int f = f0 + i;
-          if (f < J) {
-            const int pj = t.n0 + pcol + 2 * i;
-            const double pc = v[2 * i] * (cscale[pj] * sc) + yn * pbar[f] + gm * alpha[f];
-            const double ps = v[2 * i + 1] * (cscale[pj + 1] * sc) + yn * pbar[J + f] + gm * alpha[J + f];
-            const double phc = prow[f], phs = prow[J + f];
-            Zbar[(long long)r * ldz + f] = -pc * phs + ps * phc;
-            sacc += pc * phc + ps * phs;
-          }
+      for (int i = 0; i < 8; ++i) {
+        const int f = f0 + i;
+        zb[i] = 0.0;
+        if (rvalid && f < J) {
+          const int pj = t.n0 + pcol + 2 * i;
+          const double pc = v[2 * i] * (cscale[pj] * sc) + yn * pbar[f] + gm * alpha[f];
+          const double ps = v[2 * i + 1] * (cscale[pj + 1] * sc) + yn * pbar[J + f] + gm * alpha[J + f];
+          const double phc = prow[f], phs = prow[J + f];
+          zb[i] = -pc * phs + ps * phc;
+          Zbar[(long long)r * ldz + f] = zb[i];
+          sacc += pc * phc + ps * phs;
         }
+      }
+      // column sums over this warp's 32 rows: features f0 .. f0+7
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double cs = warp_sum(zb[i]);
+        if (lane == 0) shcol[warp - umma::EPI_WARP0][h16 * 8 + i] = cs;
       }
     }
     sacc = warp_sum(sacc);
-    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");   // sh[] of the previous tile consumed
     if (lane == 0) sh[warp - umma::EPI_WARP0] = sacc;
     asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");
-    if (warp == umma::EPI_WARP0 && lane == 0) {
-      double sum = 0;
-      for (int w = 0; w < 8; ++w) sum += sh[w];
-      slots[tile] += sum;
+    if (warp == umma::EPI_WARP0) {
+      if (lane == 0) {
+        double sum = 0;
+        for (int w = 0; w < 8; ++w) sum += sh[w];
+        slots[tile] += sum;
+      }
+      // warps w and w+4 hold column halves 0 / 1; their 4 lane quarters are the 4 row groups
+      const int half = lane >> 4, k = lane & 15;          // 32 features of the tile: half*16 + k
+      const int f = (t.n0 >> 1) + half * 16 + k;
+      if (f < J) {
+        double cs = 0;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) cs += shcol[half * 4 + qd][k];   // the 4 row quarters, fixed order
+        dphi_part[(long long)(tile / nfb) * ldpart + f] += cs;
+      }
     }
   }
   umma::pipe_teardown<KS>(p, tmem_base);

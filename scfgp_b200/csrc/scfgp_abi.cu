@@ -111,6 +111,7 @@ struct scfgp_handle {
   int2* gram_items = nullptr;
   int gram_count = 0;
   int vparts = 0;              // partial rows of vpart per chunk
+  int csplit = kColSplit;      // partial rows of the column-sum buffers per chunk stream (>= R/128)
 
   // work lists
   ItemList lowerK, syrkK, fullK, tgemm, bwd, dw;
@@ -513,7 +514,8 @@ int alloc_chunk_buffers(scfgp_handle* h) {
   const size_t KK = (size_t)K * h->ldk, DJ = (size_t)h->D * h->ldj;
   if ((rc = dalloc(h, &h->acc_all, KK * h->ns))) return rc;
   if ((rc = dalloc(h, &h->dW_all, DJ * kDwSplit * h->ns))) return rc;
-  if ((rc = dalloc(h, &h->colpart_all, (size_t)kColSplit * K * h->ns))) return rc;
+  h->csplit = std::max(kColSplit, R / 128);
+  if ((rc = dalloc(h, &h->colpart_all, (size_t)h->csplit * K * h->ns))) return rc;
   if ((rc = dalloc(h, &h->slots_all, (size_t)h->slot_stride * h->ns))) return rc;
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
@@ -523,7 +525,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
     if ((rc = dalloc(h, &c.vpart, (size_t)std::max(nkb, h->vparts) * R))) return rc;
     c.acc = h->acc_all + KK * i;
     c.dW = h->dW_all + DJ * kDwSplit * i;
-    c.colpart = h->colpart_all + (size_t)kColSplit * K * i;
+    c.colpart = h->colpart_all + (size_t)h->csplit * K * i;
     c.slots = h->slots_all + (size_t)h->slot_stride * i;
     if (h->use_tma) {
       if ((rc = make_tmap(h, &c.mapPhi, c.Phi, K, R, h->ldk))) return rc;
@@ -671,12 +673,14 @@ int run_tgemm(scfgp_handle* h, Ctx& c, int rows) {
 // ---------------------------------------------------------------------------------
 int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
                     const double* rowmul, const double* rowinv, double ginv, const double* ginv_ptr, int permJ,
-                    int8_t* dst, long long pitch, long long slice_stride, int col_off, int nd = 0) {
+                    int8_t* dst, long long pitch, long long slice_stride, int col_off, int nd = 0,
+                    const double* rowmul2 = nullptr, const double* ginv_ptr2 = nullptr, int col_off2 = 0) {
   if (nd == 0) nd = h->ks2;
   const long long total = (long long)rows * (cdiv(cols, 16) * 4);
   trace_begin(h, "digits_rows", st);
   EMU_KS_SWITCH(nd, emu::k_digits_rows<KS><<<cdiv(total, 256), 256, 0, st>>>(
-                           src, ld, rows, cols, rowmul, rowinv, ginv, ginv_ptr, permJ, dst, pitch, slice_stride, col_off));
+                           src, ld, rows, cols, rowmul, rowinv, ginv, ginv_ptr, permJ, dst, pitch, slice_stride, col_off,
+                           rowmul2, ginv_ptr2, col_off2));
   trace_end(h, st);
   CKL();
   return SCFGP_OK;
@@ -684,11 +688,11 @@ int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long lo
 
 int emu_digits_cols(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
                     const double* rowmul, double ginv, const double* ginv_ptr, int8_t* dst, long long pitch,
-                    long long slice_stride, int nd) {
+                    long long slice_stride, int nd, const double* wsum = nullptr, double* cpart = nullptr) {
   const dim3 grid(cdiv(cols, 32), cdiv(rows, 128));
   trace_begin(h, "digits_cols", st);
   EMU_KS_SWITCH(nd, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
-                                                                    pitch, slice_stride));
+                                                                pitch, slice_stride, wsum, cpart, (long long)cols));
   trace_end(h, st);
   CKL();
   return SCFGP_OK;
@@ -743,7 +747,8 @@ int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0) {
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
   EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                            c.mapRowsA, h->mapCB, rows, h->J, (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk,
-                           h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj, c.slots));
+                           h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj, c.slots, c.colpart,
+                           (long long)h->K));
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
   return gemm_leave(h, c);
@@ -1200,7 +1205,7 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
     CK(cudaMemsetAsync(c.acc, 0, KK * sizeof(double), c.st));
-    CK(cudaMemsetAsync(c.colpart, 0, (size_t)kColSplit * K * sizeof(double), c.st));
+    CK(cudaMemsetAsync(c.colpart, 0, (size_t)h->csplit * K * sizeof(double), c.st));
   }
   long long ci = 0;
   for (long long r0 = 0; r0 < h->N; r0 += h->R, ++ci) {
@@ -1213,17 +1218,18 @@ int scfgp_eval_pass1(scfgp_handle* h) {
     }
     if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
     if (h->prec == SCFGP_PREC_EMU_I8) {
+      // digits of PhiT for the Gram; p = PhiT.y comes out of the same pass over the slab
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
-                                (long long)K * h->R, h->ks)))
+                                (long long)K * h->R, h->ks, h->dy + r0, c.colpart)))
         return rc;
       if ((rc = emu_gram(h, c, false, rows))) return rc;
     } else {
       if ((rc = run_syrk(h, c, false, rows))) return rc;
+      trace_begin(h, "colsum", c.st);
+      k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->dy + r0, c.colpart, K);
+      trace_end(h, c.st);
+      CKL();
     }
-    trace_begin(h, "colsum", c.st);
-    k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->dy + r0, c.colpart, K);
-    trace_end(h, c.st);
-    CKL();
   }
   // yy on the main stream while the chunk streams drain
   if (h->upload_pending) CK(cudaStreamWaitEvent(h->stream, h->up_ev[0], 0));  // y is copied before X block 0
@@ -1236,7 +1242,7 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   h->upload_pending = false;  // everything queued after this point is ordered behind the whole upload
   k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns, (int)KK, G);
   CKL();
-  k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, K, p);
+  k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, h->csplit * h->ns, K, p);
   CKL();
   CK(cudaEventRecord(h->ev[1], h->stream));
   return SCFGP_OK;
@@ -1307,7 +1313,7 @@ int scfgp_eval_pass2(scfgp_handle* h) {
     Ctx& c = h->ctx[i];
     if (h->want_grad) {
       CK(cudaMemsetAsync(c.acc, 0, KK * sizeof(double), c.st));
-      CK(cudaMemsetAsync(c.colpart, 0, (size_t)kColSplit * K * sizeof(double), c.st));
+      CK(cudaMemsetAsync(c.colpart, 0, (size_t)h->csplit * K * sizeof(double), c.st));
     }
     CK(cudaMemsetAsync(c.slots, 0, (size_t)h->slot_stride * sizeof(double), c.st));
   }
@@ -1337,16 +1343,12 @@ int scfgp_eval_pass2(scfgp_handle* h) {
       trace_end(h, c.st);
     CKL();
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
-                                (long long)K * h->R, h->ks2)))
+                                (long long)K * h->R, h->ks2, h->gmu + r0, c.colpart)))   // + q = PhiT.gmu
         return rc;
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, h->gv + r0, 1.0 / h->s2, c.sig + 1, c.digPsiT, h->R,
                                 (long long)K * h->R, h->ks2)))
         return rc;
       if ((rc = emu_gram(h, c, true, rows))) return rc;
-      trace_begin(h, "colsum", c.st);
-    k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->gmu + r0, c.colpart, K);
-      trace_end(h, c.st);
-    CKL();
     } else if (h->want_grad) {
       if ((rc = run_syrk(h, c, true, rows))) return rc;
       trace_begin(h, "colsum", c.st);
@@ -1359,7 +1361,7 @@ int scfgp_eval_pass2(scfgp_handle* h) {
   if (h->want_grad) {
     k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns, (int)KK, H);
     CKL();
-    k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, K, q);
+    k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, h->csplit * h->ns, K, q);
     CKL();
   } else {
     CK(cudaMemsetAsync(h->red2, 0, (KK + K) * sizeof(double), h->stream));
@@ -1418,7 +1420,7 @@ int scfgp_eval_pass3(scfgp_handle* h) {
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
     CK(cudaMemsetAsync(c.dW, 0, DJ * kDwSplit * sizeof(double), c.st));
-    CK(cudaMemsetAsync(c.colpart, 0, (size_t)kColSplit * K * sizeof(double), c.st));
+    CK(cudaMemsetAsync(c.colpart, 0, (size_t)h->csplit * K * sizeof(double), c.st));
     CK(cudaMemsetAsync(c.slots, 0, (size_t)h->slot_stride * sizeof(double), c.st));
   }
   long long ci = 0;
@@ -1431,10 +1433,7 @@ int scfgp_eval_pass3(scfgp_handle* h) {
       if ((rc = run_features(h, c, Xc, h->xvec, rows, nullptr, nullptr))) return rc;
       // A operand digits: [Phi | (gv / sigma) Phi], both against the scale s2
       if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, nullptr, nullptr, 1.0 / h->s2, nullptr, 0, c.digR,
-                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0)))
-        return rc;
-      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, h->gv + r0, nullptr, 1.0 / h->s2, h->sigg + 1, 0,
-                                c.digR, 2 * h->Kp, (long long)h->R * 2 * h->Kp, (int)h->Kp)))
+                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0, 0, h->gv + r0, h->sigg + 1, (int)h->Kp)))
         return rc;
       if ((rc = emu_backward(h, c, rows, r0))) return rc;
     } else if ((rc = run_features(h, c, Xc, h->xvec, rows, h->gv + r0, c.Psi))) return rc;
@@ -1468,15 +1467,17 @@ int scfgp_eval_pass3(scfgp_handle* h) {
       trace_end(h, c.st);
       CKL();
     }
-    trace_begin(h, "colsum", c.st);
-    k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, J, nullptr, c.colpart, K);
-    trace_end(h, c.st);
-    CKL();
+    if (!emu_on) {   // (the emulated backward kernel leaves dphi = colsum(Zbar) in c.colpart itself)
+      trace_begin(h, "colsum", c.st);
+      k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, J, nullptr, c.colpart, K);
+      trace_end(h, c.st);
+      CKL();
+    }
   }
   if ((rc = join_streams(h))) return rc;
   k_sum_parts<<<cdiv((long long)DJ, 256), 256, 0, h->stream>>>(h->dW_all, (long long)DJ, h->ns * kDwSplit, (int)DJ, dW);
   CKL();
-  k_sum_parts<<<cdiv(J, 256), 256, 0, h->stream>>>(h->colpart_all, K, kColSplit * h->ns, J, dphi);
+  k_sum_parts<<<cdiv(J, 256), 256, 0, h->stream>>>(h->colpart_all, K, h->csplit * h->ns, J, dphi);
   CKL();
   k_reduce_slots<<<1, 256, 0, h->stream>>>(h->slots_all, (int)h->slot_stride * h->ns, 1, 1, sbar);
   CKL();
