@@ -193,7 +193,10 @@ __global__ void __launch_bounds__(256)
 k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, const double* __restrict__ rowmul,
               double ginv, const double* __restrict__ ginv_ptr, int8_t* __restrict__ dst, long long pitch,
               long long slice_stride, const double* __restrict__ wsum, double* __restrict__ cpart,
-              long long ldpart) {
+              long long ldpart, const double* __restrict__ rowmul2, const double* __restrict__ ginv_ptr2,
+              int8_t* __restrict__ dst2) {
+  // optional second output from the same read (pass 2: PhiT and (gv / sigma_chunk) PhiT):
+  //   dst2[s][c][r] = digit s of src[r][c] * rowmul2[r] * ginv * *ginv_ptr2
   // optional by-product (saves a separate pass over the slab): weighted column sums of the RAW
   // source, cpart[blockIdx.y][c] += sum over this block's 128 rows of wsum[r] * src[r][c]
   // (p = PhiT.y in pass 1, q = PhiT.gmu in pass 2); fixed summation order
@@ -251,6 +254,38 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
     const int s = p >> 5, cc = p & 31;
     if (c0 + cc < cols)
       *reinterpret_cast<uint32_t*>(dst + (long long)s * slice_stride + (long long)(c0 + cc) * pitch + r0 + 4 * lane) =
+          sm[s][cc][lane];
+  }
+  if (dst2 == nullptr) return;
+  __syncthreads();   // sm[] is reused
+  const double base2 = digit_mult<KS>() * ginv * (ginv_ptr2 ? *ginv_ptr2 : 1.0);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int r = r0 + warp * 16 + e;
+    // x[] holds src * rowmul (if any); the second output starts again from the raw value
+    double raw = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.0;
+    x[e] = (r < rows) ? raw * rowmul2[r] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t packed[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) packed[s] = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long qp = biased_q<KS>(x[4 * k + e] * base2);
+#pragma unroll
+      for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
+    }
+    sm[0][lane][warp * 4 + k] = packed[0];
+#pragma unroll
+    for (int s = 1; s < KS; ++s) sm[s][lane][warp * 4 + k] = fix_bytes(packed[s]);
+  }
+  __syncthreads();
+  for (int p = warp; p < KS * 32; p += 8) {
+    const int s = p >> 5, cc = p & 31;
+    if (c0 + cc < cols)
+      *reinterpret_cast<uint32_t*>(dst2 + (long long)s * slice_stride + (long long)(c0 + cc) * pitch + r0 + 4 * lane) =
           sm[s][cc][lane];
   }
 }
@@ -322,12 +357,15 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
 k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int rows, int K,
-           int ntiles, const double* __restrict__ liscale, double sA, double* __restrict__ vpart, long long ldv) {
+           int ntiles, const double* __restrict__ liscale, double sA, double* __restrict__ vpart, long long ldv,
+           double* __restrict__ mu) {
+  // The B operand has K + 1 rows: rows 0..K-1 are Li, row K is alpha, so column K of the product is
+  // mu_n = Phi_n . alpha (SCFGP.py:111) and never enters the sum of squares.
   extern __shared__ uint8_t smem_raw[];
   umma::Pipe p = umma::pipe_init<KS>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
   const bool front = (threadIdx.x >> 5) < umma::EPI_WARP0;
-  const int nnb = (K + TN - 1) / TN;
+  const int nnb = (K + 1 + TN - 1) / TN;
   int it0 = 0, seq = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
     const int nb = nnb - 1 - tile % nnb;   // deepest reduction first within a row block
@@ -342,6 +380,8 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       continue;
     }
     const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, seq & 1);
+    const double sc = sA * umma::PROD_SCALE;
+    const int r = t.m0 + e.row;
     double sq = 0;
 #pragma unroll 1
     for (int h16 = 0; h16 < 2; ++h16) {
@@ -351,12 +391,11 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int j = t.n0 + e.col0 + 16 * h16 + c;
-        const double tv = j < K ? v[c] * liscale[j] : 0.0;
-        sq = fma(tv, tv, sq);
+        const double tv = j <= K ? v[c] * liscale[j] : 0.0;
+        if (j == K) { if (r < rows) mu[r] = tv * sc; }
+        else sq = fma(tv, tv, sq);
       }
     }
-    const double sc = sA * umma::PROD_SCALE;
-    const int r = t.m0 + e.row;
     if (r < rows) vpart[(long long)(2 * nb + (e.col0 >> 5)) * ldv + r] = sq * sc * sc;
   }
   umma::pipe_teardown<KS>(p, tmem_base);

@@ -313,14 +313,19 @@ __global__ void k_seeds(const double* __restrict__ Phi, long long ldp, int rows,
                         const double* __restrict__ alpha, const double* __restrict__ vpart,
                         long long ldv, int nkb, const double* __restrict__ y, double tau,
                         double* __restrict__ gmu, double* __restrict__ gv,
-                        double* __restrict__ Psi, double* __restrict__ slots, int want_grad) {
+                        double* __restrict__ Psi, double* __restrict__ slots, int want_grad,
+                        const double* __restrict__ mu_in) {
+  // mu_in != nullptr: mu_n = Phi_n.alpha was produced by the Phi.LiT kernel (emulated mode)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   double Eacc = 0, Tacc = 0;
   for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
     const double* row = Phi + (long long)r * ldp;
     double mu = 0;
-    for (int k = lane; k < K; k += 32) mu += row[k] * alpha[k];
-    mu = warp_sum(mu);
+    if (mu_in) mu = mu_in[r];
+    else {
+      for (int k = lane; k < K; k += 32) mu += row[k] * alpha[k];
+      mu = warp_sum(mu);
+    }
     double v = 0;
     for (int b = 0; b < nkb; ++b) v += vpart[(long long)b * ldv + r];
     const double res = mu - y[r];
@@ -430,13 +435,16 @@ k_backward(const double* __restrict__ Phi, const double* __restrict__ Psi, long 
 __global__ void k_pred_finish(const double* __restrict__ Phi, long long ldp, int rows, int K,
                               const double* __restrict__ alpha, const double* __restrict__ vpart,
                               long long ldv, int nkb, double tau, double* __restrict__ mu,
-                              double* __restrict__ sd) {
+                              double* __restrict__ sd, const double* __restrict__ mu_in) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
     const double* row = Phi + (long long)r * ldp;
     double m = 0;
-    for (int k = lane; k < K; k += 32) m += row[k] * alpha[k];
-    m = warp_sum(m);
+    if (mu_in) m = mu_in[r];
+    else {
+      for (int k = lane; k < K; k += 32) m += row[k] * alpha[k];
+      m = warp_sum(m);
+    }
     if (lane == 0) {
       double v = 0;
       for (int b = 0; b < nkb; ++b) v += vpart[(long long)b * ldv + r];

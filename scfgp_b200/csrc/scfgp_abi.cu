@@ -46,6 +46,7 @@ struct Ctx {
   int8_t *digPhiT = nullptr;  // [KS][K][R]     transposed digits of Phi
   int8_t *digPsiT = nullptr;  // [KS][K][R]     transposed digits of gv * Phi / sigma_chunk
   double *sig = nullptr;      // {sigma_chunk, 1/sigma_chunk}
+  double *mu = nullptr;       // mu_n = Phi_n.alpha of the chunk (column K of the Phi.[Li; alpha]T product)
   CUtensorMap mapRowsA, mapPhiT_A, mapPhiT_B, mapPsiT_A;  // ks2 leading digit planes
   CUtensorMap mapPhiT_A1, mapPhiT_B1;                     // ks digit planes (pass 1)
 };
@@ -470,7 +471,7 @@ int emu_check_depths(scfgp_handle* h) {
 int alloc_chunk_buffers(scfgp_handle* h) {
   for (int i = 0; i < kMaxStreams; ++i) {
     Ctx& c = h->ctx[i];
-    for (double** p : {&c.Phi, &c.Psi, &c.Zbar, &c.vpart, &c.sig}) {
+    for (double** p : {&c.Phi, &c.Psi, &c.Zbar, &c.vpart, &c.sig, &c.mu}) {
       if (*p) cudaFree(*p);
       *p = nullptr;
     }
@@ -508,7 +509,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
   if ((rc = upload_items(h, bw, &h->bwd))) return rc;
   const bool emu_on = h->prec == SCFGP_PREC_EMU_I8;
   const int emu_bwd_ctas = emu_on ? nrb * cdiv(h->J, 32) : 0;
-  h->vparts = emu_on ? 2 * cdiv(K, umma::TN) : nkb;
+  h->vparts = emu_on ? 2 * cdiv(K + 1, umma::TN) : nkb;
   h->slot_stride =
       (std::max<long long>(std::max(std::max(2 * kSeedBlocks, (int)bw.size()), emu_bwd_ctas), 256) + 1) / 2 * 2;
   const size_t KK = (size_t)K * h->ldk, DJ = (size_t)h->D * h->ldj;
@@ -540,6 +541,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
       if ((rc = dalloc(h, &c.digPhiT, (size_t)ksm * K * R))) return rc;
       if ((rc = dalloc(h, &c.digPsiT, (size_t)ks2 * K * R))) return rc;
       if ((rc = dalloc(h, &c.sig, 2))) return rc;
+      if ((rc = dalloc(h, &c.mu, (size_t)R))) return rc;
       if ((rc = make_tmap_digits(h, &c.mapRowsA, c.digR, Kp + K, R, 2 * Kp, ks2, umma::TM))) return rc;
       if ((rc = make_tmap_digits(h, &c.mapPhiT_A, c.digPhiT, R, K, R, ks2, umma::TM))) return rc;
       if ((rc = make_tmap_digits(h, &c.mapPhiT_B, c.digPhiT, R, K, R, ks2, umma::TN))) return rc;
@@ -574,13 +576,13 @@ int alloc_emu_static(scfgp_handle* h) {
   const int K = h->K, ks = h->ks2;
   const long long Kp = h->Kp;
   int rc;
-  if ((rc = dalloc(h, &h->digLi, (size_t)ks * K * Kp))) return rc;
+  if ((rc = dalloc(h, &h->digLi, (size_t)ks * (K + 1) * Kp))) return rc;   // rows 0..K-1: Li, row K: alpha
   if ((rc = dalloc(h, &h->digC, (size_t)ks * K * 2 * Kp))) return rc;
   for (double** p : {&h->liscale, &h->liinv, &h->cscale, &h->cinv})
-    if ((rc = dalloc(h, p, K))) return rc;
+    if ((rc = dalloc(h, p, K + 1))) return rc;
   if ((rc = dalloc(h, &h->sigg, 2))) return rc;
   if ((rc = dalloc(h, &h->gvmax, 1))) return rc;
-  if ((rc = make_tmap_digits(h, &h->mapLiB, h->digLi, K, K, Kp, ks, umma::TN))) return rc;
+  if ((rc = make_tmap_digits(h, &h->mapLiB, h->digLi, K, K + 1, Kp, ks, umma::TN))) return rc;
   if ((rc = make_tmap_digits(h, &h->mapCB, h->digC, Kp + K, K, 2 * Kp, ks, umma::TN))) return rc;
   std::vector<int2> v;
   for (int mt = 0; mt < cdiv(K, umma::TM); ++mt)
@@ -688,11 +690,13 @@ int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long lo
 
 int emu_digits_cols(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
                     const double* rowmul, double ginv, const double* ginv_ptr, int8_t* dst, long long pitch,
-                    long long slice_stride, int nd, const double* wsum = nullptr, double* cpart = nullptr) {
+                    long long slice_stride, int nd, const double* wsum = nullptr, double* cpart = nullptr,
+                    const double* rowmul2 = nullptr, const double* ginv_ptr2 = nullptr, int8_t* dst2 = nullptr) {
   const dim3 grid(cdiv(cols, 32), cdiv(rows, 128));
   trace_begin(h, "digits_cols", st);
   EMU_KS_SWITCH(nd, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
-                                                                pitch, slice_stride, wsum, cpart, (long long)cols));
+                                                                pitch, slice_stride, wsum, cpart, (long long)cols,
+                                                                rowmul2, ginv_ptr2, dst2));
   trace_end(h, st);
   CKL();
   return SCFGP_OK;
@@ -729,12 +733,12 @@ int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
 }
 
 int emu_tgemm(scfgp_handle* h, Ctx& c, int rows) {
-  const int ntiles = cdiv(h->K, umma::TN) * cdiv(rows, umma::TM);
+  const int ntiles = cdiv(h->K + 1, umma::TN) * cdiv(rows, umma::TM);
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
   EMU_KS_SWITCH(h->ks2, emu::k_tgemm_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           c.mapRowsA, h->mapLiB, rows, h->K, ntiles, h->liscale, h->s2, c.vpart, h->R));
+                           c.mapRowsA, h->mapLiB, rows, h->K, ntiles, h->liscale, h->s2, c.vpart, h->R, c.mu));
   prof_end(h, SCFGP_FAM_TGEMM, c.sg);
   CKL();
   return gemm_leave(h, c);
@@ -759,8 +763,16 @@ int emu_prepare_li(scfgp_handle* h) {
   const int K = h->K;
   emu::k_rowscale<<<K, 128, 0, h->stream>>>(h->Li, h->ldk, nullptr, 0, nullptr, K, K, 0, h->liscale, h->liinv);
   CKL();
-  return emu_digits_rows(h, h->stream, h->Li, h->ldk, K, K, nullptr, h->liinv, 1.0, nullptr, 0, h->digLi, h->Kp,
-                         (long long)K * h->Kp, 0);
+  const long long plane = (long long)(K + 1) * h->Kp;
+  int rc;
+  if ((rc = emu_digits_rows(h, h->stream, h->Li, h->ldk, K, K, nullptr, h->liinv, 1.0, nullptr, 0, h->digLi, h->Kp,
+                            plane, 0)))
+    return rc;
+  // row K = alpha (its own power-of-two scale): the product's column K is mu = Phi.alpha
+  emu::k_rowscale<<<1, 128, 0, h->stream>>>(h->alpha, K, nullptr, 0, nullptr, 1, K, 0, h->liscale + K, h->liinv + K);
+  CKL();
+  return emu_digits_rows(h, h->stream, h->alpha, K, 1, K, nullptr, h->liinv + K, 1.0, nullptr, 0,
+                         h->digLi + (long long)K * h->Kp, h->Kp, plane, 0);
 }
 
 // digits of Cmat = [2 Abar | 2 sigma B] (rows permuted cos/sin-interleaved, per-row scales);
@@ -877,7 +889,7 @@ int build_static_lists(scfgp_handle* h) {
 void free_all(scfgp_handle* h) {
   for (int i = 0; i < kMaxStreams; ++i) {
     Ctx& c = h->ctx[i];
-    for (double* p : {c.Phi, c.Psi, c.Zbar, c.vpart, c.sig})
+    for (double* p : {c.Phi, c.Psi, c.Zbar, c.vpart, c.sig, c.mu})
       if (p) cudaFree(p);
     for (int8_t* p : {c.digR, c.digPhiT, c.digPsiT})
       if (p) cudaFree(p);
@@ -1262,7 +1274,6 @@ int scfgp_eval_factor(scfgp_handle* h) {
   k_add_diag<<<cdiv(K, 256), 256, 0, h->stream>>>(h->L, h->ldk, K, h->sig2n + kEps);
   CKL();
   if ((rc = factor_device(h, h->L, h->Li, K, h->ldk))) return rc;
-  if (h->prec == SCFGP_PREC_EMU_I8 && (rc = emu_prepare_li(h))) return rc;
   // beta = Li p ; alpha = LiT beta                           SCFGP/SCFGP.py:108-110
   k_gemv_n<<<cdiv(K, 8), 256, 0, h->stream>>>(h->Li, h->ldk, K, K, p, h->beta);
   CKL();
@@ -1273,6 +1284,7 @@ int scfgp_eval_factor(scfgp_handle* h) {
   CKL();
   k_factor_scalars<<<1, 256, 0, h->stream>>>(h->L, h->ldk, K, h->beta, p, h->alpha, h->scal);
   CKL();
+  if (h->prec == SCFGP_PREC_EMU_I8 && (rc = emu_prepare_li(h))) return rc;   // digits of [Li; alpha]
   if (h->want_grad) {
     // B = LiT Li = A^-1 (lower tiles; rows r < m0 of Li[:, m-block] are zero), then mirror
     if ((rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->Li, h->ldk, K, h->Li, h->ldk, K, h->Bm, h->ldk,
@@ -1333,7 +1345,7 @@ int scfgp_eval_pass2(scfgp_handle* h) {
     trace_begin(h, "seeds", c.st);
     k_seeds<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->dy + r0,
                                           h->tau, h->gmu + r0, h->gv + r0, c.Psi, c.slots,
-                                          emu_on ? 0 : h->want_grad);
+                                          emu_on ? 0 : h->want_grad, emu_on ? c.mu : nullptr);
     trace_end(h, c.st);
     CKL();
     if (h->want_grad && emu_on) {
@@ -1342,11 +1354,10 @@ int scfgp_eval_pass2(scfgp_handle* h) {
     emu::k_absmax_pow2<<<1, 1024, 0, c.st>>>(h->gv + r0, rows, c.sig, h->gvmax);
       trace_end(h, c.st);
     CKL();
+      // one pass over the slab: digits of PhiT and of (gv / sigma_chunk) PhiT, and q = PhiT.gmu
       if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
-                                (long long)K * h->R, h->ks2, h->gmu + r0, c.colpart)))   // + q = PhiT.gmu
-        return rc;
-      if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, h->gv + r0, 1.0 / h->s2, c.sig + 1, c.digPsiT, h->R,
-                                (long long)K * h->R, h->ks2)))
+                                (long long)K * h->R, h->ks2, h->gmu + r0, c.colpart, h->gv + r0, c.sig + 1,
+                                c.digPsiT)))
         return rc;
       if ((rc = emu_gram(h, c, true, rows))) return rc;
     } else if (h->want_grad) {
@@ -1683,7 +1694,8 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
     } else if ((rc = run_tgemm(h, c, rows))) return rc;
     trace_begin(h, "pred_finish", c.st);
     k_pred_finish<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->tau,
-                                                dmu + r0, dstd + r0);
+                                                dmu + r0, dstd + r0,
+                                                h->prec == SCFGP_PREC_EMU_I8 ? c.mu : nullptr);
     trace_end(h, c.st);
     CKL();
   }
