@@ -298,21 +298,26 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
-k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int depth, int K,
-          const int2* __restrict__ items, int ntiles, double* __restrict__ C, long long ldc, double scale,
-          const double* __restrict__ scale_ptr) {
+k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int depth,
+          int split_len, int K, const int2* __restrict__ items, int ngram, int ntiles, double* __restrict__ Call,
+          long long ldc, long long split_stride, double scale, const double* __restrict__ scale_ptr) {
+  // work item = (row split, Gram tile): split sp reduces rows [sp split_len, (sp+1) split_len) of the
+  // chunk into its own accumulator Call + sp * split_stride (tile-major order keeps the operands of a
+  // split together in L2)
   extern __shared__ uint8_t smem_raw[];
   umma::Pipe p = umma::pipe_init<KS>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
   const bool front = (threadIdx.x >> 5) < umma::EPI_WARP0;
   int it0 = 0, seq = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
-    const int2 it = items[tile];
+    const int sp = tile / ngram;
+    const int2 it = items[tile - sp * ngram];
+    double* __restrict__ C = Call + (long long)sp * split_stride;
     umma::Tile t;
     t.m0 = it.x * TM;
     t.n0 = it.y * TN;
-    t.c_begin = 0;
-    t.c_end = depth;
+    t.c_begin = sp * split_len;
+    t.c_end = min(depth, t.c_begin + split_len);
     if (front) {
       umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, it0, seq);
       it0 += umma::tile_stages(t);

@@ -22,6 +22,7 @@ namespace {
 constexpr double kEps = 1e-6;  // jitter, SCFGP/SCFGP.py:93
 constexpr int kColSplit = 64;  // row splits of the column-sum kernels (parallelism: ceil(K/256) x 64 CTAs)
 constexpr int kSeedBlocks = 296;
+constexpr int kGramSplit = 1;  // row splits of one chunk's Gram tiles in the emulated mode (work items = tiles x splits)
 constexpr int kDwSplit = 16;   // row splits of the dW = XT.Zbar contraction (partial buffers per chunk stream)
 
 struct ItemList {
@@ -112,6 +113,7 @@ struct scfgp_handle {
   int2* gram_items = nullptr;
   int gram_count = 0;
   int vparts = 0;              // partial rows of vpart per chunk
+  int gsplit = 1;              // partial Gram accumulators per chunk stream (kGramSplit in the emulated mode)
   int csplit = kColSplit;      // partial rows of the column-sum buffers per chunk stream (>= R/128)
 
   // work lists
@@ -513,7 +515,14 @@ int alloc_chunk_buffers(scfgp_handle* h) {
   h->slot_stride =
       (std::max<long long>(std::max(std::max(2 * kSeedBlocks, (int)bw.size()), emu_bwd_ctas), 256) + 1) / 2 * 2;
   const size_t KK = (size_t)K * h->ldk, DJ = (size_t)h->D * h->ldj;
-  if ((rc = dalloc(h, &h->acc_all, KK * h->ns))) return rc;
+  // Emulated mode: the ~300 Gram tiles do not divide evenly over 148 persistent CTAs (2.07 rounds
+  // cost 3).  Each tile's row reduction can be cut into gsplit work items with their own partial
+  // accumulator (summed in fixed order afterwards); measured at cfg4 (SCFGP_GRAM_SPLIT=1/2/3/4:
+  // 0.556 / 0.561 / 0.569 / 0.568 s per 2M rows) the better balance does not pay, because the
+  // evaluation is power-limited and idle SMs let the busy ones clock higher -- default 1.
+  h->gsplit = emu_on ? kGramSplit : 1;
+  if (const char* e = getenv("SCFGP_GRAM_SPLIT")) h->gsplit = emu_on ? std::max(1, std::min(16, atoi(e))) : 1;
+  if ((rc = dalloc(h, &h->acc_all, KK * h->ns * h->gsplit))) return rc;
   if ((rc = dalloc(h, &h->dW_all, DJ * kDwSplit * h->ns))) return rc;
   h->csplit = std::max(kColSplit, R / 128);
   if ((rc = dalloc(h, &h->colpart_all, (size_t)h->csplit * K * h->ns))) return rc;
@@ -524,7 +533,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
     if ((rc = dalloc(h, &c.Psi, (size_t)R * h->ldk))) return rc;
     if ((rc = dalloc(h, &c.Zbar, (size_t)R * h->ldj))) return rc;
     if ((rc = dalloc(h, &c.vpart, (size_t)std::max(nkb, h->vparts) * R))) return rc;
-    c.acc = h->acc_all + KK * i;
+    c.acc = h->acc_all + KK * h->gsplit * i;
     c.dW = h->dW_all + DJ * kDwSplit * i;
     c.colpart = h->colpart_all + (size_t)h->csplit * K * i;
     c.slots = h->slots_all + (size_t)h->slot_stride * i;
@@ -719,14 +728,19 @@ int gemm_leave(scfgp_handle* h, Ctx& c) {
 // acc(lower tiles) += sc * digits(A)T . digits(Phi) over the rows of one chunk
 int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
   const int depth = (rows + umma::KB - 1) / umma::KB * umma::KB;
+  // rows per split: a multiple of the stage depth; short chunks use fewer splits
+  const int split_len = cdiv(cdiv(depth, h->gsplit), umma::KB) * umma::KB;
+  const int nsplit = cdiv(depth, split_len);
+  const int nitems = h->gram_count * nsplit;
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_SYRK, c.sg);
   // pass 1 (G, feeds the Cholesky): ks digits; pass 2 (H): ks2 leading digits
   EMU_KS_SWITCH(a_is_psi ? h->ks2 : h->ks,
-                emu::k_gram_i8<KS><<<std::min(h->gram_count, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                    a_is_psi ? c.mapPsiT_A : c.mapPhiT_A1, a_is_psi ? c.mapPhiT_B : c.mapPhiT_B1, depth, h->K,
-                    h->gram_items, h->gram_count, c.acc, h->ldk, h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
+                emu::k_gram_i8<KS><<<std::min(nitems, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                    a_is_psi ? c.mapPsiT_A : c.mapPhiT_A1, a_is_psi ? c.mapPhiT_B : c.mapPhiT_B1, depth, split_len,
+                    h->K, h->gram_items, h->gram_count, nitems, c.acc, h->ldk, (long long)h->K * h->ldk,
+                    h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
   prof_end(h, SCFGP_FAM_SYRK, c.sg);
   CKL();
   return gemm_leave(h, c);
@@ -1216,7 +1230,7 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   if ((rc = fork_streams(h))) return rc;
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
-    CK(cudaMemsetAsync(c.acc, 0, KK * sizeof(double), c.st));
+    CK(cudaMemsetAsync(c.acc, 0, KK * h->gsplit * sizeof(double), c.st));
     CK(cudaMemsetAsync(c.colpart, 0, (size_t)h->csplit * K * sizeof(double), c.st));
   }
   long long ci = 0;
@@ -1252,7 +1266,7 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   CKL();
   if ((rc = join_streams(h))) return rc;
   h->upload_pending = false;  // everything queued after this point is ordered behind the whole upload
-  k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns, (int)KK, G);
+  k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns * h->gsplit, (int)KK, G);
   CKL();
   k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, h->csplit * h->ns, K, p);
   CKL();
@@ -1324,7 +1338,7 @@ int scfgp_eval_pass2(scfgp_handle* h) {
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
     if (h->want_grad) {
-      CK(cudaMemsetAsync(c.acc, 0, KK * sizeof(double), c.st));
+      CK(cudaMemsetAsync(c.acc, 0, KK * h->gsplit * sizeof(double), c.st));
       CK(cudaMemsetAsync(c.colpart, 0, (size_t)h->csplit * K * sizeof(double), c.st));
     }
     CK(cudaMemsetAsync(c.slots, 0, (size_t)h->slot_stride * sizeof(double), c.st));
@@ -1370,7 +1384,7 @@ int scfgp_eval_pass2(scfgp_handle* h) {
   }
   if ((rc = join_streams(h))) return rc;
   if (h->want_grad) {
-    k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns, (int)KK, H);
+    k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns * h->gsplit, (int)KK, H);
     CKL();
     k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, h->csplit * h->ns, K, q);
     CKL();
