@@ -207,6 +207,13 @@ __device__ __forceinline__ void pipe_teardown(const Pipe& p, uint32_t tmem_base)
 // the MMA warp only has to wait for the epilogue to release TMEM (acc_empty).
 __device__ __forceinline__ int tile_stages(const Tile& t) { return (t.c_end - t.c_begin + KB - 1) / KB; }
 
+// Bottleneck probe (tools/umma_probe.cu only): UMMA_PROBE_MODE 1 = the loads run but no MMA is
+// issued (pure TMA pipeline time), 2 = only the first ring of stages is loaded and the MMAs re-read
+// it (pure MMA + shared-memory-read time).  Results are garbage in both modes.
+#ifndef UMMA_PROBE_MODE
+#define UMMA_PROBE_MODE 0
+#endif
+
 // producer + MMA roles of one tile (warps 0 and 1)
 template <int KS>
 __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, const CUtensorMap* mapA,
@@ -222,6 +229,9 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         const uint32_t use = it / G::STAGES;
         mbar_wait(&p.empty[st], (use & 1) ^ 1);
         uint8_t* sa = p.stages + (size_t)st * G::STAGE_BYTES;
+#if UMMA_PROBE_MODE == 2
+        if (it >= G::STAGES) { mbar_arrive(&p.full[st]); continue; }
+#endif
         mbar_arrive_expect_tx(&p.full[st], G::STAGE_BYTES);
         tma_load_3d(sa, mapA, t.c_begin + kb * KB, t.m0, 0, &p.full[st]);
         tma_load_3d(sa + G::A_BYTES, mapB, t.c_begin + kb * KB, t.n0, 0, &p.full[st]);
@@ -243,6 +253,21 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         const uint32_t sb = sa + G::A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < KB / 32; ++ks) {
+#if UMMA_PROBE_MODE == 3 || UMMA_PROBE_MODE == 4
+          // probe: the same number of output columns, but as uniform N = 256 (mode 3) or N = 64 (mode 4)
+          // instructions -- separates the per-instruction overhead from the shared-memory read volume
+          {
+            constexpr int COLS = TN * KS * (KS + 1) / 2;
+            constexpr int NI = UMMA_PROBE_MODE == 3 ? 256 : 64;
+#pragma unroll
+            for (int m = 0; m < (COLS + NI - 1) / NI; ++m) {
+              const uint64_t adesc = smem_desc_sw64(sa + (m % KS) * (TM * KB) + ks * 32);
+              const uint64_t bdesc = smem_desc_sw64(sb + ks * 32);
+              mma_i8(tmem_base, adesc, bdesc, idesc_i8(NI), (kb | ks | m) ? 1u : 0u);
+            }
+          }
+          continue;
+#endif
 #pragma unroll
           for (int i = 0; i < KS; ++i) {
             const uint64_t adesc = smem_desc_sw64(sa + i * (TM * KB) + ks * 32);
@@ -251,7 +276,11 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
               const int cnt = (KS - i - j0) < 4 ? (KS - i - j0) : 4;
               const uint64_t bdesc = smem_desc_sw64(sb + j0 * (TN * KB) + ks * 32);
               const uint32_t acc = (kb == 0 && ks == 0 && i == 0) ? 0u : 1u;
+#if UMMA_PROBE_MODE != 1
               mma_i8(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc, idesc_i8(TN * cnt), acc);
+#else
+              (void)adesc; (void)bdesc; (void)acc;
+#endif
             }
           }
         }
