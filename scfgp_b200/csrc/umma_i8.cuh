@@ -125,6 +125,26 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t byte_addr) {
   d |= (uint64_t)4 << 61;                       // layout type SWIZZLE_64B
   return d;
 }
+// MN-major ("transposed") operands: the tile lies in shared memory as [contraction row][M or N bytes],
+// i.e. straight out of a row-major digit array whose rows are the contraction index.
+//   A: 128 M-bytes per row, 128-byte swizzle; 8-row groups 1024 bytes apart (SBO); one 128-byte
+//      chunk covers M = 128, so LBO is unused.
+//   B: 64 N-bytes per row per digit, 64-byte swizzle; 8-row groups 512 bytes apart (SBO); the next
+//      64 N-bytes (= the next digit's block, N = 64 cnt) are `lbo` bytes further (LBO).
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t byte_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                 uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((byte_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_i8_mn(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TM >> 4) << 24);
+}
 // instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_i8(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -215,7 +235,10 @@ __device__ __forceinline__ int tile_stages(const Tile& t) { return (t.c_end - t.
 #endif
 
 // producer + MMA roles of one tile (warps 0 and 1)
-template <int KS>
+// TR = false: K-major operands (tensor maps (contraction, row, digit), tile rows m0 / n0);
+// TR = true : MN-major operands (tensor maps (M-or-N index, contraction row, digit)): m0 / n0 are
+//             coordinates of dimension 0, the contraction range [c_begin, c_end) of dimension 1.
+template <int KS, bool TR = false>
 __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, const CUtensorMap* mapA,
                                              const CUtensorMap* mapB, const Tile& t, int it0, int seq = 0) {
   using G = Geo<KS>;
@@ -233,8 +256,13 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         if (it >= G::STAGES) { mbar_arrive(&p.full[st]); continue; }
 #endif
         mbar_arrive_expect_tx(&p.full[st], G::STAGE_BYTES);
-        tma_load_3d(sa, mapA, t.c_begin + kb * KB, t.m0, 0, &p.full[st]);
-        tma_load_3d(sa + G::A_BYTES, mapB, t.c_begin + kb * KB, t.n0, 0, &p.full[st]);
+        if (TR) {
+          tma_load_3d(sa, mapA, t.m0, t.c_begin + kb * KB, 0, &p.full[st]);
+          tma_load_3d(sa + G::A_BYTES, mapB, t.n0, t.c_begin + kb * KB, 0, &p.full[st]);
+        } else {
+          tma_load_3d(sa, mapA, t.c_begin + kb * KB, t.m0, 0, &p.full[st]);
+          tma_load_3d(sa + G::A_BYTES, mapB, t.c_begin + kb * KB, t.n0, 0, &p.full[st]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -270,14 +298,19 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
 #endif
 #pragma unroll
           for (int i = 0; i < KS; ++i) {
-            const uint64_t adesc = smem_desc_sw64(sa + i * (TM * KB) + ks * 32);
+            // one digit block is TM x KB = KB x TM bytes in either layout
+            const uint64_t adesc = TR ? smem_desc_mn(sa + i * (TM * KB) + ks * 32 * TM, 0, 8 * TM, 2 /*SWIZZLE_128B*/)
+                                      : smem_desc_sw64(sa + i * (TM * KB) + ks * 32);
 #pragma unroll
             for (int j0 = 0; j0 < KS - i; j0 += 4) {
               const int cnt = (KS - i - j0) < 4 ? (KS - i - j0) : 4;
-              const uint64_t bdesc = smem_desc_sw64(sb + j0 * (TN * KB) + ks * 32);
+              const uint64_t bdesc =
+                  TR ? smem_desc_mn(sb + j0 * (TN * KB) + ks * 32 * TN, TN * KB, 8 * TN, 4 /*SWIZZLE_64B*/)
+                     : smem_desc_sw64(sb + j0 * (TN * KB) + ks * 32);
               const uint32_t acc = (kb == 0 && ks == 0 && i == 0) ? 0u : 1u;
 #if UMMA_PROBE_MODE != 1
-              mma_i8(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc, idesc_i8(TN * cnt), acc);
+              mma_i8(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
+                     TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
 #else
               (void)adesc; (void)bdesc; (void)acc;
 #endif
