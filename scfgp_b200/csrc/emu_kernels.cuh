@@ -180,6 +180,123 @@ k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols, 
 }
 
 // ------------------------------------------------------------------------------------
+// digits of a streaming row slab (the Phi chunk), all its by-products in ONE pass over the data:
+//   source  : the float64 slab (FROM_DIGITS = false) or the digit cache (true: x = recon * sum_i d_i 256^(KS-1-i))
+//   out1    : digit s of x * ginv * rowmul1[r] * *gptr1  -> dst1[s][r][4 tx ..]   (absent factors = 1)
+//   out2    : the same with rowmul2 / gptr2 -> dst2                                   (optional)
+//   cpart   : cpart[blockIdx.y][c] += sum over the block's 128 rows of wsum[r] * x[r][c]   (optional; p, q)
+// Rows [rows, next multiple of 128) are written as zeros: they lie inside the Gram reduction.
+// grid = (ceil(ceil16(cols) / 256), ceil(rows / 128)); 256 threads = 64 column groups x 4 row lanes.
+// ------------------------------------------------------------------------------------
+template <int KS, bool FROM_DIGITS>
+__global__ void __launch_bounds__(256)
+k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __restrict__ dsrc, long long dpitch,
+              long long dplane, double recon, int rows, int cols, double ginv,
+              const double* __restrict__ rowmul1, const double* __restrict__ gptr1, int8_t* __restrict__ dst1,
+              const double* __restrict__ rowmul2, const double* __restrict__ gptr2, int8_t* __restrict__ dst2,
+              long long pitch, long long plane, const double* __restrict__ wsum, double* __restrict__ cpart,
+              long long ldpart, double* __restrict__ xout, long long ldx) {
+  // xout (optional): the source values themselves as a float64 slab (from the cache: the reconstructed
+  // Phi the backward epilogue reads -- a coalesced write here instead of strided byte loads there)
+  __shared__ double csum[4][256];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = (blockIdx.x * 64 + tx) * 4;
+  const int cpad = (cols + 15) / 16 * 16;
+  const int r0 = blockIdx.y * 128;
+  const double m1 = digit_mult<KS>() * ginv * (gptr1 ? *gptr1 : 1.0);
+  const double m2 = digit_mult<KS>() * ginv * (gptr2 ? *gptr2 : 1.0);
+  const bool vec = !FROM_DIGITS && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < cpad) {
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+      const int r = r0 + ty + 4 * it;
+      double x[4] = {0.0, 0.0, 0.0, 0.0};
+      if (r < rows) {
+        if (FROM_DIGITS) {
+          long long q[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int s = 0; s < KS; ++s) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(dsrc + (long long)s * dplane + (long long)r * dpitch + c);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q[e] = q[e] * 256 + (long long)(int8_t)(w >> (8 * e));
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = (c + e < cols) ? (double)q[e] * recon : 0.0;
+        } else {
+          const double* p = src + (long long)r * ld + c;
+          if (vec && c + 3 < cols) {
+            const double2 a = *reinterpret_cast<const double2*>(p);
+            const double2 b = *reinterpret_cast<const double2*>(p + 2);
+            x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = (c + e < cols) ? p[e] : 0.0;
+          }
+        }
+        if (wsum) {
+          const double w = wsum[r];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] = fma(w, x[e], acc[e]);
+        }
+        if (xout) {
+          double* o = xout + (long long)r * ldx + c;
+          if ((ldx & 1) == 0 && c + 3 < cols) {
+            *reinterpret_cast<double2*>(o) = make_double2(x[0], x[1]);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(x[2], x[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c + e < cols) o[e] = x[e];
+          }
+        }
+      }
+      if (dst1) {
+        const double mm = (r < rows && rowmul1) ? m1 * rowmul1[r] : m1;
+        uint32_t packed[KS];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) packed[s] = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long qp = biased_q<KS>(x[e] * mm);
+#pragma unroll
+          for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
+        }
+        int8_t* o = dst1 + (long long)r * pitch + c;
+        *reinterpret_cast<uint32_t*>(o) = packed[0];
+#pragma unroll
+        for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * plane) = fix_bytes(packed[s]);
+      }
+      if (dst2) {
+        const double mm = (r < rows && rowmul2) ? m2 * rowmul2[r] : m2;
+        uint32_t packed[KS];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) packed[s] = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long qp = biased_q<KS>(x[e] * mm);
+#pragma unroll
+          for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
+        }
+        int8_t* o = dst2 + (long long)r * pitch + c;
+        *reinterpret_cast<uint32_t*>(o) = packed[0];
+#pragma unroll
+        for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * plane) = fix_bytes(packed[s]);
+      }
+    }
+  }
+  if (wsum) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) csum[ty][tx * 4 + e] = acc[e];
+    __syncthreads();
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < cols)
+      cpart[(long long)blockIdx.y * ldpart + cc] +=
+          (csum[0][threadIdx.x] + csum[1][threadIdx.x]) + (csum[2][threadIdx.x] + csum[3][threadIdx.x]);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // digits of the TRANSPOSE of a row slab, contraction index = row (Gram operands)
 //   dst[s][c][r] = digit s of src[r][c] * rowmul[r] * ginv * *ginv_ptr ; rows beyond `rows`
 //   up to the 128-row tile boundary are written as zeros (they are inside the reduction)
@@ -298,9 +415,12 @@ k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, 
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
-k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int depth,
-          int split_len, int K, const int2* __restrict__ items, int ngram, int ntiles, double* __restrict__ Call,
-          long long ldc, long long split_stride, double scale, const double* __restrict__ scale_ptr) {
+k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int row0_a,
+          int row0_b, int depth, int split_len, int K, const int2* __restrict__ items, int ngram, int ntiles,
+          double* __restrict__ Call, long long ldc, long long split_stride, double scale,
+          const double* __restrict__ scale_ptr) {
+  // MN-major operands: both maps are row-major digit arrays (feature index contiguous) whose ROWS are
+  // the contraction index; the chunk's rows start at row0_a / row0_b of the respective array.
   // work item = (row split, Gram tile): split sp reduces rows [sp split_len, (sp+1) split_len) of the
   // chunk into its own accumulator Call + sp * split_stride (tile-major order keeps the operands of a
   // split together in L2)
@@ -316,10 +436,11 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     umma::Tile t;
     t.m0 = it.x * TM;
     t.n0 = it.y * TN;
-    t.c_begin = sp * split_len;
-    t.c_end = min(depth, t.c_begin + split_len);
+    t.c_begin = row0_a + sp * split_len;
+    t.c_end = row0_a + min(depth, (sp + 1) * split_len);
+    t.c_off_b = row0_b - row0_a;
     if (front) {
-      umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapB, t, it0, seq);
+      umma::run_mainloop<KS, true>(p, tmem_base, &mapA, &mapB, t, it0, seq);
       it0 += umma::tile_stages(t);
       continue;
     }
@@ -361,9 +482,10 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
-k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int rows, int K,
-           int ntiles, const double* __restrict__ liscale, double sA, double* __restrict__ vpart, long long ldv,
-           double* __restrict__ mu) {
+k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int row0, int rows,
+           int K, int ntiles, const double* __restrict__ liscale, double sA, double* __restrict__ vpart,
+           long long ldv, double* __restrict__ mu) {
+  // row0: first row of this chunk inside the A array (0 for the chunk buffer, r0 for the digit cache)
   // The B operand has K + 1 rows: rows 0..K-1 are Li, row K is alpha, so column K of the product is
   // mu_n = Phi_n . alpha (SCFGP.py:111) and never enters the sum of squares.
   extern __shared__ uint8_t smem_raw[];
@@ -375,7 +497,8 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
     const int nb = nnb - 1 - tile % nnb;   // deepest reduction first within a row block
     umma::Tile t;
-    t.m0 = (tile / nnb) * TM;
+    const int rb0 = (tile / nnb) * TM;   // chunk-local first row of the tile
+    t.m0 = row0 + rb0;
     t.n0 = nb * TN;
     t.c_begin = 0;
     t.c_end = min(K, t.n0 + TN);  // Li is lower triangular
@@ -386,7 +509,7 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     }
     const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, seq & 1);
     const double sc = sA * umma::PROD_SCALE;
-    const int r = t.m0 + e.row;
+    const int r = rb0 + e.row;
     double sq = 0;
 #pragma unroll 1
     for (int h16 = 0; h16 < 2; ++h16) {
@@ -414,7 +537,8 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
-k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, int rows, int J,
+k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
+              const __grid_constant__ CUtensorMap mapC, int seg1_stages, int row0, int rows, int J,
               int depth2, int ntiles, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
               long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
               const double* __restrict__ pbar, const double* __restrict__ alpha, double* __restrict__ Zbar,
@@ -435,6 +559,11 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     t.n0 = (tile % nfb) * TN;
     t.c_begin = 0;
     t.c_end = depth2;
+    // digit cache: the Phi half of [Phi | Psi'] (the first seg1_stages stages) comes from the cache
+    // (rows row0 + ...), the Psi' half from the chunk buffer; seg1_stages == 0: both from mapA
+    t.mapA1 = &mapA1;
+    t.seg1_stages = seg1_stages;
+    t.seg1_row_off = row0;
     if (front) {
       umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapC, t, it0, seq);
       it0 += umma::tile_stages(t);

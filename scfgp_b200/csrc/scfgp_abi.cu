@@ -43,13 +43,13 @@ struct Ctx {
   double *slots = nullptr;    // slot_stride scalars
   CUtensorMap mapPhi, mapPsi; // 16x16-box TMA views of the slabs
   // emulated-FP64 path (int8 digits, see emu_kernels.cuh)
-  int8_t *digR = nullptr;     // [KS][R][2 Kp]  row digits of [Phi | Psi']
-  int8_t *digPhiT = nullptr;  // [KS][K][R]     transposed digits of Phi
-  int8_t *digPsiT = nullptr;  // [KS][K][R]     transposed digits of gv * Phi / sigma_chunk
+  int8_t *digR = nullptr;     // [KS][R][2 Kp]  row digits of [Phi | Psi] (Psi = gv Phi / sigma; feature index contiguous)
   double *sig = nullptr;      // {sigma_chunk, 1/sigma_chunk}
   double *mu = nullptr;       // mu_n = Phi_n.alpha of the chunk (column K of the Phi.[Li; alpha]T product)
-  CUtensorMap mapRowsA, mapPhiT_A, mapPhiT_B, mapPsiT_A;  // ks2 leading digit planes
-  CUtensorMap mapPhiT_A1, mapPhiT_B1;                     // ks digit planes (pass 1)
+  CUtensorMap mapRowsA;                                   // K-major view of digR (contraction = feature), ks2 planes
+  // MN-major views of digR (contraction = chunk row) for the Gram products
+  CUtensorMap mapPhiMN_A1, mapPhiMN_B1;                   // Phi half, ks planes (pass 1: G)
+  CUtensorMap mapPhiMN_B, mapPsiMN_A;                     // Phi / Psi halves, ks2 planes (pass 2: H)
 };
 
 }  // namespace
@@ -103,13 +103,20 @@ struct scfgp_handle {
   int num_sms = 148;
   int ks = 5;                  // digits of the Phi^T Phi Gram (pass 1: feeds the Cholesky, the sensitive product)
   int ks2 = 5;                 // digits of every other streaming product (Phi.LiT, PsiT.Phi, backward)
-  long long Kp = 0;            // K rounded up to 16 (digit row pitch / offset of the Psi' half)
+  long long Kp = 0;            // K rounded up to 64 (digit row pitch / offset of the Psi half)
   double s2 = 1.0;             // power of two >= s: scale of the Phi digits
   int8_t *digLi = nullptr;     // [KS][K][Kp]
   int8_t *digC = nullptr;      // [KS][K][2 Kp]   rows permuted (cos/sin interleaved): [2Abar | 2 sigma B]
   double *liscale = nullptr, *liinv = nullptr, *cscale = nullptr, *cinv = nullptr, *sigg = nullptr;
   unsigned long long* gvmax = nullptr;
   CUtensorMap mapLiB, mapCB;
+  // optional cache of Phi's row digits for ALL rows ([ks][cache_rows][Kc]; 104 GB at cfg4): passes 2 and 3
+  // then read Phi from it instead of recomputing features + digits
+  int8_t* phi_cache = nullptr;
+  long long cache_rows = 0, Kc = 0;
+  int cache_ks = 0;
+  int want_cache = 1;          // SCFGP_PHI_CACHE=0 disables
+  CUtensorMap mapCacheK, mapCacheMN_A, mapCacheMN_B;
   int2* gram_items = nullptr;
   int gram_count = 0;
   int vparts = 0;              // partial rows of vpart per chunk
@@ -213,6 +220,24 @@ int make_tmap_digits(scfgp_handle* h, CUtensorMap* out, const int8_t* base, long
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(digits) failed: " + std::to_string((int)r); return SCFGP_ERR_CUDA; }
+  return SCFGP_OK;
+}
+
+// MN-major view of a row-major digit array [ks][rows][pitch]: dimension 0 = the (feature) index that is
+// contiguous in memory, dimension 1 = the array's rows = the contraction index of the Gram products;
+// boxes of box_w (128: A operand, 128-byte swizzle; 64: B operand, 64-byte swizzle) bytes x 64 rows x ks digits
+int make_tmap_digits_mn(scfgp_handle* h, CUtensorMap* out, const int8_t* base, long long width, long long rows,
+                        long long pitch, int ks, int box_w) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { h->err = "cuTensorMapEncodeTiled not available"; return SCFGP_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)ks};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)umma::KB, (cuuint32_t)ks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_w == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(digits, MN) failed: " + std::to_string((int)r); return SCFGP_ERR_CUDA; }
   return SCFGP_OK;
 }
 
@@ -377,7 +402,8 @@ int set_emu_attrs(scfgp_handle* h) {
   CK(cudaFuncSetAttribute(emu::k_tgemm_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CK(cudaFuncSetAttribute(emu::k_backward_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CK(cudaFuncSetAttribute(emu::k_digits_rows<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-  CK(cudaFuncSetAttribute(emu::k_digits_cols<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute((emu::k_digits_slab<KS, false>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CK(cudaFuncSetAttribute((emu::k_digits_slab<KS, true>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   return SCFGP_OK;
 }
 
@@ -477,10 +503,8 @@ int alloc_chunk_buffers(scfgp_handle* h) {
       if (*p) cudaFree(*p);
       *p = nullptr;
     }
-    for (int8_t** p : {&c.digR, &c.digPhiT, &c.digPsiT}) {
-      if (*p) cudaFree(*p);
-      *p = nullptr;
-    }
+    if (c.digR) cudaFree(c.digR);
+    c.digR = nullptr;
   }
   for (double** p : {&h->acc_all, &h->dW_all, &h->colpart_all, &h->slots_all}) {
     if (*p) cudaFree(*p);
@@ -546,17 +570,15 @@ int alloc_chunk_buffers(scfgp_handle* h) {
       // digits: dropping the tail rounds to nearest), so one array serves both digit counts.
       const long long Kp = h->Kp;
       const int ks = h->ks, ks2 = h->ks2, ksm = std::max(ks, ks2);
-      if ((rc = dalloc(h, &c.digR, (size_t)ks2 * R * 2 * Kp))) return rc;
-      if ((rc = dalloc(h, &c.digPhiT, (size_t)ksm * K * R))) return rc;
-      if ((rc = dalloc(h, &c.digPsiT, (size_t)ks2 * K * R))) return rc;
+      // (dalloc zero-fills: columns [ceil16(K), Kp) and [Kp + ceil16(K), 2 Kp) are never written and stay 0)
+      if ((rc = dalloc(h, &c.digR, (size_t)ksm * R * 2 * Kp))) return rc;
       if ((rc = dalloc(h, &c.sig, 2))) return rc;
       if ((rc = dalloc(h, &c.mu, (size_t)R))) return rc;
       if ((rc = make_tmap_digits(h, &c.mapRowsA, c.digR, Kp + K, R, 2 * Kp, ks2, umma::TM))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPhiT_A, c.digPhiT, R, K, R, ks2, umma::TM))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPhiT_B, c.digPhiT, R, K, R, ks2, umma::TN))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPsiT_A, c.digPsiT, R, K, R, ks2, umma::TM))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPhiT_A1, c.digPhiT, R, K, R, ks, umma::TM))) return rc;
-      if ((rc = make_tmap_digits(h, &c.mapPhiT_B1, c.digPhiT, R, K, R, ks, umma::TN))) return rc;
+      if ((rc = make_tmap_digits_mn(h, &c.mapPhiMN_A1, c.digR, K, R, 2 * Kp, ks, umma::TM))) return rc;
+      if ((rc = make_tmap_digits_mn(h, &c.mapPhiMN_B1, c.digR, K, R, 2 * Kp, ks, umma::TN))) return rc;
+      if ((rc = make_tmap_digits_mn(h, &c.mapPhiMN_B, c.digR, K, R, 2 * Kp, ks2, umma::TN))) return rc;
+      if ((rc = make_tmap_digits_mn(h, &c.mapPsiMN_A, c.digR + Kp, K, R, 2 * Kp, ks2, umma::TM))) return rc;
     }
   }
   return SCFGP_OK;
@@ -697,16 +719,26 @@ int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long lo
   return SCFGP_OK;
 }
 
-int emu_digits_cols(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
-                    const double* rowmul, double ginv, const double* ginv_ptr, int8_t* dst, long long pitch,
-                    long long slice_stride, int nd, const double* wsum = nullptr, double* cpart = nullptr,
-                    const double* rowmul2 = nullptr, const double* ginv_ptr2 = nullptr, int8_t* dst2 = nullptr) {
-  const dim3 grid(cdiv(cols, 32), cdiv(rows, 128));
-  trace_begin(h, "digits_cols", st);
-  EMU_KS_SWITCH(nd, emu::k_digits_cols<KS><<<grid, 256, 0, st>>>(src, ld, rows, cols, rowmul, ginv, ginv_ptr, dst,
-                                                                pitch, slice_stride, wsum, cpart, (long long)cols,
-                                                                rowmul2, ginv_ptr2, dst2));
-  trace_end(h, st);
+// digits of one Phi chunk and their by-products (k_digits_slab): source = the float64 slab of the chunk
+// stream, or (from_cache) the digit cache rows r0..; dst1 / dst2 = digit arrays with row pitch `pitch`
+int emu_digits_slab(scfgp_handle* h, Ctx& c, int nd, bool from_cache, long long r0, int rows, const double* rowmul1,
+                    const double* gptr1, int8_t* dst1, const double* rowmul2, const double* gptr2, int8_t* dst2,
+                    long long pitch, long long plane, const double* wsum, double* cpart, bool write_slab = false) {
+  const int K = h->K;
+  const dim3 grid(cdiv((K + 15) / 16 * 16, 256), cdiv(rows, 128));
+  const double recon = h->s2 * std::ldexp(1.0, -(8 * h->cache_ks - 1));
+  trace_begin(h, from_cache ? "digits(cache)" : "digits(slab)", c.st);
+  if (from_cache) {
+    EMU_KS_SWITCH(nd, emu::k_digits_slab<KS, true><<<grid, 256, 0, c.st>>>(
+                          nullptr, 0, h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon, rows, K,
+                          1.0 / h->s2, rowmul1, gptr1, dst1, rowmul2, gptr2, dst2, pitch, plane, wsum, cpart,
+                          (long long)K, write_slab ? c.Phi : nullptr, h->ldk));
+  } else {
+    EMU_KS_SWITCH(nd, emu::k_digits_slab<KS, false><<<grid, 256, 0, c.st>>>(
+                          c.Phi, h->ldk, nullptr, 0, 0, 0.0, rows, K, 1.0 / h->s2, rowmul1, gptr1, dst1, rowmul2,
+                          gptr2, dst2, pitch, plane, wsum, cpart, (long long)K, nullptr, 0));
+  }
+  trace_end(h, c.st);
   CKL();
   return SCFGP_OK;
 }
@@ -725,51 +757,90 @@ int gemm_leave(scfgp_handle* h, Ctx& c) {
   return SCFGP_OK;
 }
 
-// acc(lower tiles) += sc * digits(A)T . digits(Phi) over the rows of one chunk
-int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows) {
+// acc(lower tiles) += sc * digits(A)T . digits(Phi) over the rows of one chunk; both operands are
+// row-major digit arrays read MN-major (no transposed copies).  Pass 1: A = B = Phi (chunk buffer, or
+// the cache rows r0..); pass 2: A = Psi (chunk buffer), B = Phi (chunk buffer or cache).
+int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows, long long r0, bool use_cache) {
   const int depth = (rows + umma::KB - 1) / umma::KB * umma::KB;
   // rows per split: a multiple of the stage depth; short chunks use fewer splits
   const int split_len = cdiv(cdiv(depth, h->gsplit), umma::KB) * umma::KB;
   const int nsplit = cdiv(depth, split_len);
   const int nitems = h->gram_count * nsplit;
+  const int row0_b = use_cache ? (int)r0 : 0;
+  const int row0_a = (use_cache && !a_is_psi) ? (int)r0 : 0;
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_SYRK, c.sg);
   // pass 1 (G, feeds the Cholesky): ks digits; pass 2 (H): ks2 leading digits
   EMU_KS_SWITCH(a_is_psi ? h->ks2 : h->ks,
                 emu::k_gram_i8<KS><<<std::min(nitems, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                    a_is_psi ? c.mapPsiT_A : c.mapPhiT_A1, a_is_psi ? c.mapPhiT_B : c.mapPhiT_B1, depth, split_len,
-                    h->K, h->gram_items, h->gram_count, nitems, c.acc, h->ldk, (long long)h->K * h->ldk,
+                    a_is_psi ? c.mapPsiMN_A : (use_cache ? h->mapCacheMN_A : c.mapPhiMN_A1),
+                    use_cache ? h->mapCacheMN_B : (a_is_psi ? c.mapPhiMN_B : c.mapPhiMN_B1), row0_a, row0_b, depth,
+                    split_len, h->K, h->gram_items, h->gram_count, nitems, c.acc, h->ldk, (long long)h->K * h->ldk,
                     h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
   prof_end(h, SCFGP_FAM_SYRK, c.sg);
   CKL();
   return gemm_leave(h, c);
 }
 
-int emu_tgemm(scfgp_handle* h, Ctx& c, int rows) {
+int emu_tgemm(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
   const int ntiles = cdiv(h->K + 1, umma::TN) * cdiv(rows, umma::TM);
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
   EMU_KS_SWITCH(h->ks2, emu::k_tgemm_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           c.mapRowsA, h->mapLiB, rows, h->K, ntiles, h->liscale, h->s2, c.vpart, h->R, c.mu));
+                           use_cache ? h->mapCacheK : c.mapRowsA, h->mapLiB, use_cache ? (int)r0 : 0, rows, h->K, ntiles,
+                           h->liscale, h->s2, c.vpart, h->R, c.mu));
   prof_end(h, SCFGP_FAM_TGEMM, c.sg);
   CKL();
   return gemm_leave(h, c);
 }
 
-int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0) {
+int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
   const int ntiles = cdiv(h->J, 32) * cdiv(rows, umma::TM);
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
   EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           c.mapRowsA, h->mapCB, rows, h->J, (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk,
-                           h->dy + r0, h->gmu + r0, h->pbar, h->alpha, c.Zbar, h->ldj, c.slots, c.colpart,
-                           (long long)h->K));
+                           c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA, h->mapCB,
+                           use_cache ? (int)(h->Kp / umma::KB) : 0, use_cache ? (int)r0 : 0, rows, h->J,
+                           (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0,
+                           h->pbar, h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K));
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
   return gemm_leave(h, c);
+}
+
+// (re)allocate the digit cache for the current data set if it is wanted and fits; otherwise run without
+void free_phi_cache(scfgp_handle* h) {
+  if (h->phi_cache) cudaFree(h->phi_cache);
+  h->phi_cache = nullptr;
+  h->cache_rows = 0;
+  h->cache_ks = 0;
+}
+int ensure_phi_cache(scfgp_handle* h) {
+  const bool want = h->prec == SCFGP_PREC_EMU_I8 && h->want_cache && h->ks == h->ks2 && h->N > 0;
+  const long long rows = (h->N + 127) / 128 * 128;
+  if (want && h->phi_cache && h->cache_rows >= rows && h->cache_ks == h->ks) return SCFGP_OK;
+  free_phi_cache(h);
+  if (!want) return SCFGP_OK;
+  h->Kc = (h->K + 15) / 16 * 16;
+  const size_t bytes = (size_t)h->ks * rows * h->Kc;
+  size_t fr = 0, tot = 0;
+  CK(cudaMemGetInfo(&fr, &tot));
+  if (bytes + ((size_t)6 << 30) > fr) return SCFGP_OK;   // keep 6 GB of head room for the caller
+  if (cudaMalloc((void**)&h->phi_cache, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    h->phi_cache = nullptr;
+    return SCFGP_OK;
+  }
+  h->cache_rows = rows;
+  h->cache_ks = h->ks;
+  int rc;
+  if ((rc = make_tmap_digits(h, &h->mapCacheK, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TM))) return rc;
+  if ((rc = make_tmap_digits_mn(h, &h->mapCacheMN_A, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TM))) return rc;
+  if ((rc = make_tmap_digits_mn(h, &h->mapCacheMN_B, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TN))) return rc;
+  return SCFGP_OK;
 }
 
 // digits of Li with per-row power-of-two scales (B operand of Phi.LiT)
@@ -905,8 +976,7 @@ void free_all(scfgp_handle* h) {
     Ctx& c = h->ctx[i];
     for (double* p : {c.Phi, c.Psi, c.Zbar, c.vpart, c.sig, c.mu})
       if (p) cudaFree(p);
-    for (int8_t* p : {c.digR, c.digPhiT, c.digPsiT})
-      if (p) cudaFree(p);
+    if (c.digR) cudaFree(c.digR);
     if (c.done) cudaEventDestroy(c.done);
     if (c.ev_sg) cudaEventDestroy(c.ev_sg);
     if (c.ev_gs) cudaEventDestroy(c.ev_gs);
@@ -914,6 +984,7 @@ void free_all(scfgp_handle* h) {
     if (c.sg) cudaStreamDestroy(c.sg);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  free_phi_cache(h);
   if (h->cstream) cudaStreamDestroy(h->cstream);
   for (auto& e : h->up_ev) cudaEventDestroy(e);
   free_emu_static(h);
@@ -985,7 +1056,8 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   h->ldk = h->K;                       // K = 2J is even: 16-byte row alignment holds
   h->ldj = (h->J + 1) / 2 * 2;
   h->ldw = (D + 1) / 2 * 2;
-  h->Kp = (h->K + 15) / 16 * 16;
+  h->Kp = (h->K + 63) / 64 * 64;   // stage-aligned: the Psi half of [Phi | Psi] starts on a pipeline-stage boundary
+  if (const char* e = getenv("SCFGP_PHI_CACHE")) h->want_cache = atoi(e) != 0;
   if (const char* e = getenv("SCFGP_PRECISION")) {
     if (!strncmp(e, "emu", 3)) {
       h->prec = SCFGP_PREC_EMU_I8;
@@ -1106,6 +1178,7 @@ int scfgp_set_precision2(scfgp_handle* h, int mode, int digits, int digits2) {
   int rc;
   if ((rc = emu_check_depths(h))) { h->prec = o_prec; h->ks = o_ks; h->ks2 = o_ks2; h->R = o_R; return rc; }
   h->have_factors = false;
+  free_phi_cache(h);   // rebuilt (if it fits) by the next evaluation
   if ((rc = alloc_emu_static(h))) return rc;
   return alloc_chunk_buffers(h);
 }
@@ -1214,6 +1287,8 @@ int scfgp_eval_begin(scfgp_handle* h, const double* params, int want_grad) {
   h->want_grad = want_grad;
   h->have_factors = false;
   h->pivot = -1;
+  int rcc;
+  if ((rcc = ensure_phi_cache(h))) return rcc;
   return unpack_and_upload(h, params);
 }
 
@@ -1244,11 +1319,16 @@ int scfgp_eval_pass1(scfgp_handle* h) {
     }
     if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
     if (h->prec == SCFGP_PREC_EMU_I8) {
-      // digits of PhiT for the Gram; p = PhiT.y comes out of the same pass over the slab
-      if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
-                                (long long)K * h->R, h->ks, h->dy + r0, c.colpart)))
+      // row digits of Phi -- into the cache (all rows stay resident for passes 2 and 3) or the chunk
+      // buffer; p = PhiT.y comes out of the same pass over the slab; the Gram reads them MN-major
+      const bool cached = h->phi_cache != nullptr;
+      int8_t* dst = cached ? h->phi_cache + r0 * h->Kc : c.digR;
+      const long long pitch = cached ? h->Kc : 2 * h->Kp;
+      const long long plane = cached ? h->cache_rows * h->Kc : (long long)h->R * 2 * h->Kp;
+      if ((rc = emu_digits_slab(h, c, h->ks, false, r0, rows, nullptr, nullptr, dst, nullptr, nullptr, nullptr,
+                                pitch, plane, h->dy + r0, c.colpart)))
         return rc;
-      if ((rc = emu_gram(h, c, false, rows))) return rc;
+      if ((rc = emu_gram(h, c, false, rows, r0, cached))) return rc;
     } else {
       if ((rc = run_syrk(h, c, false, rows))) return rc;
       trace_begin(h, "colsum", c.st);
@@ -1347,12 +1427,14 @@ int scfgp_eval_pass2(scfgp_handle* h) {
   for (long long r0 = 0; r0 < h->N; r0 += h->R, ++ci) {
     Ctx& c = h->ctx[ci % h->ns];
     const int rows = (int)std::min<long long>(h->R, h->N - r0);
-    if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
+    const bool cached = emu_on && h->phi_cache != nullptr;   // Phi's digits of every row are resident since pass 1
+    const long long rpitch = 2 * h->Kp, rplane = (long long)h->R * 2 * h->Kp;
+    if (!cached && (rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
     if (emu_on) {
-      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, nullptr, nullptr, 1.0 / h->s2, nullptr, 0, c.digR,
-                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0)))
+      if (!cached && (rc = emu_digits_slab(h, c, h->ks2, false, r0, rows, nullptr, nullptr, c.digR, nullptr, nullptr,
+                                           nullptr, rpitch, rplane, nullptr, nullptr)))
         return rc;
-      if ((rc = emu_tgemm(h, c, rows))) return rc;
+      if ((rc = emu_tgemm(h, c, rows, r0, cached))) return rc;
     } else {
       if ((rc = run_tgemm(h, c, rows))) return rc;
     }
@@ -1368,12 +1450,12 @@ int scfgp_eval_pass2(scfgp_handle* h) {
     emu::k_absmax_pow2<<<1, 1024, 0, c.st>>>(h->gv + r0, rows, c.sig, h->gvmax);
       trace_end(h, c.st);
     CKL();
-      // one pass over the slab: digits of PhiT and of (gv / sigma_chunk) PhiT, and q = PhiT.gmu
-      if ((rc = emu_digits_cols(h, c.st, c.Phi, h->ldk, rows, K, nullptr, 1.0 / h->s2, nullptr, c.digPhiT, h->R,
-                                (long long)K * h->R, h->ks2, h->gmu + r0, c.colpart, h->gv + r0, c.sig + 1,
-                                c.digPsiT)))
+      // row digits of Psi = (gv / sigma_chunk) Phi into the second half of the chunk buffer, and q = PhiT.gmu,
+      // from one pass over Phi (slab or cache); H = PsiT.Phi reads both halves MN-major
+      if ((rc = emu_digits_slab(h, c, h->ks2, cached, r0, rows, h->gv + r0, c.sig + 1, c.digR + h->Kp, nullptr, nullptr,
+                                nullptr, rpitch, rplane, h->gmu + r0, c.colpart)))
         return rc;
-      if ((rc = emu_gram(h, c, true, rows))) return rc;
+      if ((rc = emu_gram(h, c, true, rows, r0, cached))) return rc;
     } else if (h->want_grad) {
       if ((rc = run_syrk(h, c, true, rows))) return rc;
       trace_begin(h, "colsum", c.st);
@@ -1455,12 +1537,22 @@ int scfgp_eval_pass3(scfgp_handle* h) {
     const double* Xc = h->dX + r0 * D;
     const bool emu_on = h->prec == SCFGP_PREC_EMU_I8;
     if (emu_on) {
-      if ((rc = run_features(h, c, Xc, h->xvec, rows, nullptr, nullptr))) return rc;
-      // A operand digits: [Phi | (gv / sigma) Phi], both against the scale s2
-      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, nullptr, nullptr, 1.0 / h->s2, nullptr, 0, c.digR,
-                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0, 0, h->gv + r0, h->sigg + 1, (int)h->Kp)))
-        return rc;
-      if ((rc = emu_backward(h, c, rows, r0))) return rc;
+      const bool cached = h->phi_cache != nullptr;
+      const long long rpitch = 2 * h->Kp, rplane = (long long)h->R * 2 * h->Kp;
+      // A operand digits [Phi | (gv / sigma) Phi], both against the scale s2: with the cache only the Psi
+      // half is made (from the cached digits), the Phi half is read from the cache itself
+      if (cached) {
+        // (also rewrites the float64 Phi slab from the cached digits: the backward epilogue reads it)
+        if ((rc = emu_digits_slab(h, c, h->ks2, true, r0, rows, h->gv + r0, h->sigg + 1, c.digR + h->Kp, nullptr,
+                                  nullptr, nullptr, rpitch, rplane, nullptr, nullptr, true)))
+          return rc;
+      } else {
+        if ((rc = run_features(h, c, Xc, h->xvec, rows, nullptr, nullptr))) return rc;
+        if ((rc = emu_digits_slab(h, c, h->ks2, false, r0, rows, nullptr, nullptr, c.digR, h->gv + r0, h->sigg + 1,
+                                  c.digR + h->Kp, rpitch, rplane, nullptr, nullptr)))
+          return rc;
+      }
+      if ((rc = emu_backward(h, c, rows, r0, cached))) return rc;
     } else if ((rc = run_features(h, c, Xc, h->xvec, rows, h->gv + r0, c.Psi))) return rc;
     const int nitems = cdiv(rows, 128) * nfb;  // items are rb-major
     if (!emu_on) {
@@ -1701,10 +1793,10 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
     const int rows = (int)std::min<long long>(h->R, T - r0);
     if ((rc = run_features(h, c, dXs + r0 * h->D, xvec, rows, nullptr, nullptr))) return rc;
     if (h->prec == SCFGP_PREC_EMU_I8) {
-      if ((rc = emu_digits_rows(h, c.st, c.Phi, h->ldk, rows, K, nullptr, nullptr, 1.0 / h->s2, nullptr, 0, c.digR,
-                                2 * h->Kp, (long long)h->R * 2 * h->Kp, 0)))
+      if ((rc = emu_digits_slab(h, c, h->ks2, false, r0, rows, nullptr, nullptr, c.digR, nullptr, nullptr, nullptr,
+                                2 * h->Kp, (long long)h->R * 2 * h->Kp, nullptr, nullptr)))
         return rc;
-      if ((rc = emu_tgemm(h, c, rows))) return rc;
+      if ((rc = emu_tgemm(h, c, rows, 0, false))) return rc;
     } else if ((rc = run_tgemm(h, c, rows))) return rc;
     trace_begin(h, "pred_finish", c.st);
     k_pred_finish<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->tau,

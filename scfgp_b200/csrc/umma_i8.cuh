@@ -172,6 +172,12 @@ struct Tile {
   int n0;       // first row of the B tensor map (dimension 1)
   int c_begin;  // contraction range in bytes = elements; c_begin multiple of 64
   int c_end;
+  int c_off_b = 0;  // the B map's contraction coordinate is c + c_off_b (operands living in different arrays)
+  // optional first segment of the A operand from another array (same column layout): stages
+  // kb < seg1_stages read map `mapA1` at rows m0 + seg1_row_off instead of mapA
+  const CUtensorMap* mapA1 = nullptr;
+  int seg1_stages = 0;
+  int seg1_row_off = 0;
 };
 
 struct Pipe {
@@ -256,12 +262,14 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         if (it >= G::STAGES) { mbar_arrive(&p.full[st]); continue; }
 #endif
         mbar_arrive_expect_tx(&p.full[st], G::STAGE_BYTES);
+        const int c = t.c_begin + kb * KB;
         if (TR) {
-          tma_load_3d(sa, mapA, t.m0, t.c_begin + kb * KB, 0, &p.full[st]);
-          tma_load_3d(sa + G::A_BYTES, mapB, t.n0, t.c_begin + kb * KB, 0, &p.full[st]);
+          tma_load_3d(sa, mapA, t.m0, c, 0, &p.full[st]);
+          tma_load_3d(sa + G::A_BYTES, mapB, t.n0, c + t.c_off_b, 0, &p.full[st]);
         } else {
-          tma_load_3d(sa, mapA, t.c_begin + kb * KB, t.m0, 0, &p.full[st]);
-          tma_load_3d(sa + G::A_BYTES, mapB, t.c_begin + kb * KB, t.n0, 0, &p.full[st]);
+          if (kb < t.seg1_stages) tma_load_3d(sa, t.mapA1, c, t.m0 + t.seg1_row_off, 0, &p.full[st]);
+          else tma_load_3d(sa, mapA, c, t.m0, 0, &p.full[st]);
+          tma_load_3d(sa + G::A_BYTES, mapB, c + t.c_off_b, t.n0, 0, &p.full[st]);
         }
       }
     }
