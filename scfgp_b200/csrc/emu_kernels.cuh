@@ -1,7 +1,8 @@
 // Emulated-FP64 versions of the three hot products on the int8 tensor cores (tcgen05.mma
 // kind::i8, see umma_i8.cuh for the number format and the pipeline), plus the digit
 // extraction kernels that feed them.  Same math as kernels_tma.cuh:
-//   k_gram_i8      G += PhiT.Phi, H += PsiT.Phi          SCFGP.py:103-105, A.3
+//   k_gram_i8      G += PhiT.Phi, H += PsiT.Phi          SCFGP.py:103-105, A.3  (MN-major operands: straight
+//                                                        from the row-major digits, contraction = rows)
 //   k_tgemm_i8     v_n = |Phi_n LiT|^2                   SCFGP.py:112
 //   k_backward_i8  Phibar = [Phi | Psi'].[2Abar | 2 sigma B]T, fused trig derivative   A.5
 // All scales are powers of two, so scaling is exact; the only approximation is the
@@ -297,121 +298,10 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
 }
 
 // ------------------------------------------------------------------------------------
-// digits of the TRANSPOSE of a row slab, contraction index = row (Gram operands)
-//   dst[s][c][r] = digit s of src[r][c] * rowmul[r] * ginv * *ginv_ptr ; rows beyond `rows`
-//   up to the 128-row tile boundary are written as zeros (they are inside the reduction)
-//   grid = (ceil(cols/32), ceil(rows/128)), 256 threads.  Phase 1: lane = column, warp = 16
-//   rows (coalesced 256-byte reads, 16 independent loads per thread); the digit bytes are
-//   transposed through shared memory (row pitch 33 words: conflict-free both ways).
-//   Phase 2: lane = 4 rows, one (digit, column) per warp iteration: 128-byte coalesced writes.
-// ------------------------------------------------------------------------------------
-template <int KS>
-__global__ void __launch_bounds__(256)
-k_digits_cols(const double* __restrict__ src, long long ld, int rows, int cols, const double* __restrict__ rowmul,
-              double ginv, const double* __restrict__ ginv_ptr, int8_t* __restrict__ dst, long long pitch,
-              long long slice_stride, const double* __restrict__ wsum, double* __restrict__ cpart,
-              long long ldpart, const double* __restrict__ rowmul2, const double* __restrict__ ginv_ptr2,
-              int8_t* __restrict__ dst2) {
-  // optional second output from the same read (pass 2: PhiT and (gv / sigma_chunk) PhiT):
-  //   dst2[s][c][r] = digit s of src[r][c] * rowmul2[r] * ginv * *ginv_ptr2
-  // optional by-product (saves a separate pass over the slab): weighted column sums of the RAW
-  // source, cpart[blockIdx.y][c] += sum over this block's 128 rows of wsum[r] * src[r][c]
-  // (p = PhiT.y in pass 1, q = PhiT.gmu in pass 2); fixed summation order
-  __shared__ double csum[8][32];
-  __shared__ uint32_t sm[KS][32][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 128;
-  const int c = c0 + lane;
-  const double base = digit_mult<KS>() * ginv * (ginv_ptr ? *ginv_ptr : 1.0);
-  double x[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const int r = r0 + warp * 16 + e;
-    x[e] = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.0;
-  }
-  if (wsum) {
-    double a = 0.0;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int r = r0 + warp * 16 + e;
-      if (r < rows) a = fma(wsum[r], x[e], a);
-    }
-    csum[warp][lane] = a;
-  }
-  if (rowmul) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int r = r0 + warp * 16 + e;
-      if (r < rows) x[e] *= rowmul[r];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t packed[KS];
-#pragma unroll
-    for (int s = 0; s < KS; ++s) packed[s] = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const long long qp = biased_q<KS>(x[4 * k + e] * base);
-#pragma unroll
-      for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
-    }
-    sm[0][lane][warp * 4 + k] = packed[0];
-#pragma unroll
-    for (int s = 1; s < KS; ++s) sm[s][lane][warp * 4 + k] = fix_bytes(packed[s]);
-  }
-  __syncthreads();
-  if (wsum && warp == 0 && c < cols) {
-    double a = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) a += csum[w][lane];
-    cpart[(long long)blockIdx.y * ldpart + c] += a;
-  }
-  for (int p = warp; p < KS * 32; p += 8) {
-    const int s = p >> 5, cc = p & 31;
-    if (c0 + cc < cols)
-      *reinterpret_cast<uint32_t*>(dst + (long long)s * slice_stride + (long long)(c0 + cc) * pitch + r0 + 4 * lane) =
-          sm[s][cc][lane];
-  }
-  if (dst2 == nullptr) return;
-  __syncthreads();   // sm[] is reused
-  const double base2 = digit_mult<KS>() * ginv * (ginv_ptr2 ? *ginv_ptr2 : 1.0);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const int r = r0 + warp * 16 + e;
-    // x[] holds src * rowmul (if any); the second output starts again from the raw value
-    double raw = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.0;
-    x[e] = (r < rows) ? raw * rowmul2[r] : 0.0;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t packed[KS];
-#pragma unroll
-    for (int s = 0; s < KS; ++s) packed[s] = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const long long qp = biased_q<KS>(x[4 * k + e] * base2);
-#pragma unroll
-      for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
-    }
-    sm[0][lane][warp * 4 + k] = packed[0];
-#pragma unroll
-    for (int s = 1; s < KS; ++s) sm[s][lane][warp * 4 + k] = fix_bytes(packed[s]);
-  }
-  __syncthreads();
-  for (int p = warp; p < KS * 32; p += 8) {
-    const int s = p >> 5, cc = p & 31;
-    if (c0 + cc < cols)
-      *reinterpret_cast<uint32_t*>(dst2 + (long long)s * slice_stride + (long long)(c0 + cc) * pitch + r0 + 4 * lane) =
-          sm[s][cc][lane];
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // Gram accumulation over one row chunk:  C[a][b] += sc * sum_r A[r,a] B[r,b]
-//   operands: transposed digits [KS][K][R]; items (a block of 128, b block of 64) cover the
-//   lower triangle (blocks that cross the diagonal are computed whole).
-//   sc = scale * *scale_ptr * 2^-14
+//   operands: row-major digit arrays [KS][rows][pitch] read MN-major (their rows are the contraction
+//   index); items (a block of 128, b block of 64) cover the lower triangle (blocks that cross the
+//   diagonal are computed whole).   sc = scale * *scale_ptr * 2^-14
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)

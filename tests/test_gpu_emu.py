@@ -354,3 +354,24 @@ def test_digit_gemm_bit_exact_against_cpu_restatement(digits, mnk):
     B = rng.standard_normal((n, k)) * np.exp(2 * rng.standard_normal((n, 1)))
     A[5] = 0.0                                              # an all-zero row (scale 2)
     np.testing.assert_array_equal(E.dbg_emu_gemm(A, B, digits), ED.emu_gemm(A, B, digits))
+
+
+def test_digit_cache_on_and_off_agree(monkeypatch):
+    """With the cache, passes 2 and 3 read Phi back from its digits instead of recomputing the
+    feature map: same results up to the digit rounding of Phi in the by-products."""
+    N, D, S, M = 20000, 8, 4, 100
+    X, y, h = synth.make_problem(N, D, S, M, seed=41)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SCFGP_PHI_CACHE", flag)
+        eng = Engine(D, S, M, precision="emu5")
+        eng.set_data(X, y)
+        res[flag] = eng.eval(h)
+        r2 = eng.eval(h)                                   # and each mode repeats bit for bit
+        assert r2[0] == res[flag][0]
+        np.testing.assert_array_equal(r2[1], res[flag][1])
+        eng.close()
+    a, b = res["1"], res["0"]
+    np.testing.assert_array_equal(a[3], b[3])              # pass 1 is identical: same Li, alpha
+    assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0])
+    assert rel(a[1], b[1]) <= 1e-7
