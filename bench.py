@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one 8192-row k_backward_i8 launch (ncu --set full), by digits
-TRAFFIC_BACKWARD_I8 = {5: 664.3e6}
+TRAFFIC_BACKWARD_I8 = {5: 766.6e6}
 
 WORKLOAD = dict(name="cfg4: synthetic N=10M, D=64, rank=16, feature_size=1024", N=10_000_000, D=64, S=16, M=1024)
 
@@ -385,7 +385,8 @@ def main():
             "traffic": TRAFFIC_BACKWARD_I8.get(digits),
             "traffic_note": "dram__bytes_read+write of one 8192-row k_backward_i8 launch from ncu --set full "
                             "(profiles/r1_prof_backward_i8_ncu_full.txt); algorithmic operand bytes per launch: "
-                            "A digits rows*2K*digits + C digits K*2K*digits + Phi slab read + Zbar write",
+                            "A digits rows*2K*digits (170 MB) + C digits K*2K*digits (44 MB) + Phi slab read (136 MB) "
+                            "+ Zbar write (68 MB) = 418 MB; the rest is A-operand re-reads that miss L2 (hit rate 86 %)",
             "how": f"int8 digit-product operations of pass 3 (4 N K^2 x {nprod} digit products) / pass-3 device time "
                    "(CUDA events on the launching stream) averaged over the timed steps; the pass includes the feature "
                    "map, digit extraction and dW kernels, so the GEMM kernel alone is faster than this",
