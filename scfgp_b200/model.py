@@ -124,10 +124,17 @@ class SCFGP(object):
                                   precision=self.precision)
         return self._engine
 
+    @staticmethod
+    def _is_cuda_tensor(a):
+        return hasattr(a, "is_cuda") and bool(a.is_cuda)
+
     def _upload(self, X, y):
-        key = (id(X), id(y), X.shape)
+        key = (id(X), id(y), tuple(X.shape))
         if self._engine_data_id != key:
-            self._engine.set_data(X, y)
+            if self._is_cuda_tensor(X):
+                self._engine.set_data_device(X, y)      # device-resident training set: zero-copy hand-off
+            else:
+                self._engine.set_data(X, y)
             self._engine_data_id = key
 
     def build_models(self, algo='adam', algo_params=None, engine=None):
@@ -161,17 +168,32 @@ class SCFGP(object):
 
     # ------------------------------------------------------------------ data (SCFGP.py:153-170)
     def set_data(self, X, y):
+        """X (N, D), y (N,) or (N, 1): NumPy arrays, or -- with ``scaler_device='gpu'`` -- float64 CUDA
+        tensors, in which case scaling, the scaled training set and every evaluation stay on the
+        device (no host copy of X is ever made; meant for N >= 1e7 rows)."""
         self.message("-" * 60, "\nNormalizing SCFGP training data...")
-        X = np.asarray(X, dtype=np.float64)
-        y = np.asarray(y, dtype=np.float64)
-        if y.ndim == 1:
-            y = y[:, None]
-        self.X_scaler.fit(X)
-        self.y_scaler.fit(y)
-        self.X = np.ascontiguousarray(self.X_scaler.forward_transform(X))
-        self.y = np.ascontiguousarray(self.y_scaler.forward_transform(y))
+        if self._is_cuda_tensor(X):
+            if not hasattr(self.X_scaler, "device"):
+                raise ValueError("CUDA tensors need scaler_device='gpu'")
+            import torch
+            y = y if self._is_cuda_tensor(y) else torch.as_tensor(np.asarray(y, dtype=np.float64), device=X.device)
+            if y.ndim == 1:
+                y = y[:, None]
+            self.X_scaler.fit(X)
+            self.y_scaler.fit(y)
+            self.X = self.X_scaler.forward_transform(X).contiguous()
+            self.y = self.y_scaler.forward_transform(y).contiguous()
+        else:
+            X = np.asarray(X, dtype=np.float64)
+            y = np.asarray(y, dtype=np.float64)
+            if y.ndim == 1:
+                y = y[:, None]
+            self.X_scaler.fit(X)
+            self.y_scaler.fit(y)
+            self.X = np.ascontiguousarray(self.X_scaler.forward_transform(X))
+            self.y = np.ascontiguousarray(self.y_scaler.forward_transform(y))
         self.message("done.")
-        self.N, self.D = self.X.shape
+        self.N, self.D = (int(v) for v in self.X.shape)
         if self.S_requested <= 0:
             self.S = self.D
             self.NAME = "SCFGP (Sparsity=%d, Fourier Features=%d)" % (self.S, self.M)
@@ -228,6 +250,8 @@ class SCFGP(object):
         report_every = max(1, max_iter // 10)
         for it in range(max_iter):
             if nbatches > 1:
+                if self._is_cuda_tensor(self.X):
+                    raise NotImplementedError("minibatch mode needs host (NumPy) training data")
                 cost_sum, params_list, batch_count = 0, [], 0
                 for Xb, yb in self.minibatches(self.X, self.y, batchsize):
                     params_list.append(self.params.copy())

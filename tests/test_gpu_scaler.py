@@ -122,3 +122,29 @@ def test_facade_with_gpu_scalers():
     m_gpu.optimize(max_iter=15)
     mu, sd = m_gpu.predict(X[:50])
     assert mu.shape == (50, 1) and np.all(np.isfinite(mu)) and np.all(sd > 0)
+
+
+def test_facade_device_resident_training_set():
+    """CUDA tensors in: scaling, the scaled training set and every evaluation stay on the device."""
+    import torch
+    rng = np.random.default_rng(4)
+    N, D = 3000, 6
+    X = rng.lognormal(size=(N, D))
+    yraw = np.sin(X.sum(1) / 3) + 0.1 * rng.standard_normal(N)
+    Xt, yt = torch.as_tensor(X, device="cuda"), torch.as_tensor(yraw, device="cuda")
+    np.random.seed(11)
+    m = SCFGP(rank=3, feature_size=20, scaler_device="gpu", precision="emu")
+    m.set_data(Xt, yt)
+    assert m.X.is_cuda and m.y.is_cuda and tuple(m.X.shape) == (N, D)
+    m.optimize(max_iter=12)
+    costs = m.evals["COST"][1]
+    assert len(costs) == 13 and costs[-1] < costs[0]
+    # same model on host arrays with the host scalers: same scaled data (up to the lambda search), same path
+    np.random.seed(11)
+    m2 = SCFGP(rank=3, feature_size=20)
+    m2.set_data(X, yraw[:, None])
+    np.testing.assert_allclose(m.X.cpu().numpy(), m2.X, rtol=0, atol=2e-3)
+    mu, sd = m.predict(X[:40])
+    assert mu.shape == (40, 1) and np.all(np.isfinite(mu)) and np.all(sd > 0)
+    with pytest.raises(ValueError):
+        SCFGP(rank=3, feature_size=20).set_data(Xt, yt)           # CUDA tensors need the GPU scalers
