@@ -375,3 +375,24 @@ def test_digit_cache_on_and_off_agree(monkeypatch):
     np.testing.assert_array_equal(a[3], b[3])              # pass 1 is identical: same Li, alpha
     assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0])
     assert rel(a[1], b[1]) <= 1e-7
+
+
+@pytest.mark.parametrize("prec,amp,gtol", [("emu5", 30.0, 1e-5), ("emu6", 1000.0, 1e-6)])
+def test_outliers_in_y(prec, amp, gtol):
+    """Outlier rows stretch the range of the per-row seeds gv (one power-of-two scale per chunk /
+    per rank for Psi = gv Phi): 30-sigma outliers stay inside north_star's gradient tolerance at 5
+    digits; 1000-sigma outliers need 6 digits (tools/outlier_check.py prints the whole table)."""
+    N, D, S, M = 5000, 8, 4, 100
+    X, y, h = synth.make_problem(N, D, S, M, seed=N)
+    y = y.copy()
+    y[::500] += amp
+    c0, g0, al0, Li0 = O.streaming_eval(h, X, y, S, M, chunk=1024)
+    eng = Engine(D, S, M, precision=prec)
+    eng.set_data(X, y)
+    c, g, al, Li = eng.eval(h)
+    assert abs(c - c0) <= 1e-6 * abs(c0)
+    for name, sl in grad_blocks(D, S, M).items():
+        if name != "phase":
+            assert rel(g[sl], g0[sl]) <= gtol, (name, rel(g[sl], g0[sl]))
+    assert np.abs(al - al0).max() <= 1e-5 * max(1.0, np.abs(al0).max())
+    eng.close()
