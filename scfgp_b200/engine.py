@@ -257,6 +257,32 @@ class Engine:
                                                   C.c_void_p(mu.data_ptr()), C.c_void_p(sd.data_ptr())))
         return mu, sd
 
+    def predict_sharded(self, params, Xs_t, group=None):
+        """Batched prediction over all ranks of ``torch.distributed``: the rows of ``Xs_t`` (a CUDA
+        tensor every rank holds, or at least its own shard of) are split with ``shard_bounds``, each
+        rank predicts its slice on its GPU and the results are all-gathered (no other collective).
+        Needs the factors of the last evaluation on every rank (they are replicated bit for bit)."""
+        import torch
+        import torch.distributed as td
+        from .sharding import predict_sharded
+        world = td.get_world_size(group) if td.is_initialized() else 1
+        rank = td.get_rank(group) if td.is_initialized() else 0
+
+        def local(lo, hi):
+            if hi <= lo:
+                e = torch.empty(0, dtype=torch.float64, device=Xs_t.device)
+                return e, e
+            return self.predict_device(params, Xs_t[lo:hi])
+
+        def gather(t, n):
+            if world == 1:
+                return [t]
+            parts = [torch.empty_like(t) for _ in range(world)]
+            td.all_gather(parts, t, group=group)
+            return parts
+
+        return predict_sharded(local, int(Xs_t.shape[0]), rank, world, gather)
+
     def features(self, params, X):
         """Debug hook: materialise Phi (N,K) through the feature kernel."""
         params = _lib.as_f64(params).reshape(-1)

@@ -32,3 +32,22 @@ def run_eval_phases(api, allreduce, want_grad: bool):
         api.backward()
         api.pass3()
         allreduce(api.reduce_buffer(3))
+
+
+def predict_sharded(predict_local, n_rows: int, rank: int, world: int, all_gather):
+    """Batched prediction over ranks (test rows shard independently, the only
+    exchange is the gather of the results).  ``predict_local(lo, hi)`` returns (mu, std) for the
+    rows [lo, hi) of this rank (1-D tensors); ``all_gather(t, padded_len)`` returns the list of every
+    rank's tensor padded to ``padded_len``.  Every rank gets the full (mu, std) of length n_rows."""
+    import torch
+    lo, hi = shard_bounds(n_rows, rank, world)
+    mu, sd = predict_local(lo, hi)
+    longest = max(b - a for a, b in (shard_bounds(n_rows, r, world) for r in range(world)))
+    outs = []
+    for t in (mu, sd):
+        pad = torch.zeros(longest, dtype=t.dtype, device=t.device)
+        pad[: hi - lo] = t.reshape(-1)
+        parts = all_gather(pad, longest)
+        outs.append(torch.cat([parts[r][: b - a] for r, (a, b) in
+                               enumerate(shard_bounds(n_rows, q, world) for q in range(world))]))
+    return outs[0], outs[1]

@@ -60,3 +60,30 @@ def test_two_rank_gloo_matches_single(tmp_path, shape):
     assert abs(float(z["cost"]) - c0) <= 1e-12 * abs(c0)
     np.testing.assert_allclose(z["grad"], g0, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(z["alpha"], a0, rtol=1e-8, atol=1e-10)
+
+
+def _pred_worker(rank, world, port, T):
+    sys.path.insert(0, ROOT)
+    from scfgp_b200 import predict_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    base = torch.arange(T, dtype=torch.float64)
+
+    def local(lo, hi):                      # stand-in for Engine.predict_device on this rank's slice
+        return base[lo:hi] * 2.0, base[lo:hi] + 0.5
+
+    def gather(t, n):
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return parts
+
+    mu, sd = predict_sharded(local, T, rank, world, gather)
+    assert torch.equal(mu, base * 2.0) and torch.equal(sd, base + 0.5)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("T", [7, 10, 1])
+def test_sharded_predict_gathers_in_row_order(T):
+    """Batched predict over ranks: uneven shards (and an empty one) come back in row order."""
+    mp.spawn(_pred_worker, args=(2, _free_port(), T), nprocs=2, join=True)

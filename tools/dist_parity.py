@@ -20,6 +20,11 @@ for (N, D, S, M) in [(5001, 8, 4, 100), (20000, 64, 16, 1024)]:
     eng = Engine(D, S, M, device=lr)
     eng.set_data(X[lo:hi], y[lo:hi], n_global=N)
     c, g, a, L = eng.eval(h)
+    # batched predict over ranks (rows of Xs sharded, results all-gathered) against this rank's own full predict
+    Xs = torch.rand((1001, D), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    mu_s, sd_s = eng.predict_sharded(h, Xs)
+    mu_f, sd_f = eng.predict_device(h, Xs)
+    assert float((mu_s - mu_f).abs().max()) == 0.0 and float((sd_s - sd_f).abs().max()) == 0.0, "sharded predict differs"
     cs = torch.tensor([c], dtype=torch.float64, device="cuda"); lst = [torch.zeros_like(cs) for _ in range(world)]
     dist.all_gather(lst, cs)
     same = all(float(x) == float(lst[0]) for x in lst)
