@@ -356,6 +356,39 @@ __global__ void k_seeds(const double* __restrict__ Phi, long long ldp, int rows,
   }
 }
 
+// The same per-row moments and seeds when mu_n is already known (emulated mode: mu is a column of the
+// Phi.[Li; alpha]T product) and Psi is not wanted: nothing but O(rows) work, one thread per row.
+// Block b owns slot b of `slots` (E, g_tau).
+__global__ void __launch_bounds__(256)
+k_seeds_rows(int rows, const double* __restrict__ mu_in, const double* __restrict__ vpart, long long ldv, int nkb,
+             const double* __restrict__ y, double tau, double* __restrict__ gmu, double* __restrict__ gv,
+             double* __restrict__ slots) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0, tt = 0;
+  if (r < rows) {
+    double v = 0;
+    for (int b = 0; b < nkb; ++b) v += vpart[(long long)b * ldv + r];
+    const double res = mu_in[r] - y[r];
+    const double d = tau * (v + 1.0);
+    const double num = res * res + v;
+    const double kk = -num / (d * d) + 1.0 / d;
+    gmu[r] = 2.0 * res / d;
+    gv[r] = 1.0 / d + tau * kk;
+    e = num / d + log(6.283185307179586476925286766559 * d);
+    tt = kk * (v + 1.0);
+  }
+  __shared__ double sh[2][8];
+  e = warp_sum(e); tt = warp_sum(tt);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = e; sh[1][threadIdx.x >> 5] = tt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    e = tt = 0;
+    for (int w = 0; w < 8; ++w) { e += sh[0][w]; tt += sh[1][w]; }
+    slots[2 * blockIdx.x] += e;
+    slots[2 * blockIdx.x + 1] += tt;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // (c) backward: Phibar = Phi.(2 Abar) + Psi.(2 B) + y pbarT + gmu alphaT, fused with the
 // trig derivative:  Zbar = -Phibar_c * Phi_s + Phibar_s * Phi_c ;  sbar += <Phibar, Phi>

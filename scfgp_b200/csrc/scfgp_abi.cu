@@ -1439,9 +1439,12 @@ int scfgp_eval_pass2(scfgp_handle* h) {
       if ((rc = run_tgemm(h, c, rows))) return rc;
     }
     trace_begin(h, "seeds", c.st);
-    k_seeds<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->dy + r0,
-                                          h->tau, h->gmu + r0, h->gv + r0, c.Psi, c.slots,
-                                          emu_on ? 0 : h->want_grad, emu_on ? c.mu : nullptr);
+    if (emu_on)
+      k_seeds_rows<<<cdiv(rows, 256), 256, 0, c.st>>>(rows, c.mu, c.vpart, h->R, nkb, h->dy + r0, h->tau, h->gmu + r0,
+                                                     h->gv + r0, c.slots);
+    else
+      k_seeds<<<kSeedBlocks, 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->alpha, c.vpart, h->R, nkb, h->dy + r0,
+                                            h->tau, h->gmu + r0, h->gv + r0, c.Psi, c.slots, h->want_grad, nullptr);
     trace_end(h, c.st);
     CKL();
     if (h->want_grad && emu_on) {
