@@ -385,9 +385,13 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   const int nnb = (K + 1 + TN - 1) / TN;
   int it0 = 0, seq = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
-    const int nb = nnb - 1 - tile % nnb;   // deepest reduction first within a row block
+    // Column-block major, deepest reduction first: tile k goes to CTA k mod gridDim, so every round of
+    // tiles has (nearly) one depth and the persistent CTAs stay balanced although Li is triangular;
+    // the CTAs of a round share the B operand (the same 64 rows of [Li; alpha]).
+    const int nrb = ntiles / nnb;
+    const int nb = nnb - 1 - tile / nrb;
     umma::Tile t;
-    const int rb0 = (tile / nnb) * TM;   // chunk-local first row of the tile
+    const int rb0 = (tile % nrb) * TM;   // chunk-local first row of the tile
     t.m0 = row0 + rb0;
     t.n0 = nb * TN;
     t.c_begin = 0;
