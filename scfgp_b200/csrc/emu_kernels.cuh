@@ -305,15 +305,19 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
 // ------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
-k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int row0_a,
-          int row0_b, int depth, int split_len, int K, const int2* __restrict__ items, int ngram, int ntiles,
+k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+          const __grid_constant__ CUtensorMap mapAt, const __grid_constant__ CUtensorMap mapBt, int row0_a,
+          int row0_b, int depth, int split_len, int K, const int4* __restrict__ items, int ngram, int ntiles,
           double* __restrict__ Call, long long ldc, long long split_stride, double scale,
           const double* __restrict__ scale_ptr) {
-  // MN-major operands: both maps are row-major digit arrays (feature index contiguous) whose ROWS are
-  // the contraction index; the chunk's rows start at row0_a / row0_b of the respective array.
+  // MN-major operands: the maps are row-major digit arrays (feature index contiguous) whose ROWS are
+  // the contraction index; the chunk's rows start at row0_a / row0_b of the A-side / B-side array.
   // work item = (row split, Gram tile): split sp reduces rows [sp split_len, (sp+1) split_len) of the
-  // chunk into its own accumulator Call + sp * split_stride (tile-major order keeps the operands of a
-  // split together in L2)
+  // chunk into its own accumulator Call + sp * split_stride.
+  // item.z = 1: the tile of the K mod 128 border row block, computed with the roles swapped -- the
+  // narrow block is the 64-wide N side, the 128-wide M side runs over all feature blocks -- through
+  // mapAt (128-byte boxes of the B-side array) / mapBt (64-byte boxes of the A-side array), and
+  // stored transposed: C[b][a] += sum_r Bside[r, a] * Aside[r, b].
   extern __shared__ uint8_t smem_raw[];
   umma::Pipe p = umma::pipe_init<KS>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
@@ -321,16 +325,18 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   int it0 = 0, seq = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
     const int sp = tile / ngram;
-    const int2 it = items[tile - sp * ngram];
+    const int4 it = items[tile - sp * ngram];
+    const bool tr = it.z != 0;
     double* __restrict__ C = Call + (long long)sp * split_stride;
     umma::Tile t;
     t.m0 = it.x * TM;
     t.n0 = it.y * TN;
-    t.c_begin = row0_a + sp * split_len;
-    t.c_end = row0_a + min(depth, (sp + 1) * split_len);
-    t.c_off_b = row0_b - row0_a;
+    const int ra = tr ? row0_b : row0_a, rb = tr ? row0_a : row0_b;   // rows of the M-side / N-side arrays
+    t.c_begin = ra + sp * split_len;
+    t.c_end = ra + min(depth, (sp + 1) * split_len);
+    t.c_off_b = rb - ra;
     if (front) {
-      umma::run_mainloop<KS, true>(p, tmem_base, &mapA, &mapB, t, it0, seq);
+      umma::run_mainloop<KS, true>(p, tmem_base, tr ? &mapAt : &mapA, tr ? &mapBt : &mapB, t, it0, seq);
       it0 += umma::tile_stages(t);
       continue;
     }
@@ -346,17 +352,24 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       for (int h16 = 0; h16 < 2; ++h16) {
         const double* v = h16 ? v1 : v0;
         const int b0 = t.n0 + e.col0 + 16 * h16;
-        double* crow = C + (long long)a * ldc + b0;
         const int nvalid = K - b0;
+        if (tr) {
+          // transposed store: lanes are consecutive a (coalesced along the row of C)
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          if (c + 1 < nvalid) {
-            double2 o = *reinterpret_cast<double2*>(crow + c);
-            o.x += sc * v[c];
-            o.y += sc * v[c + 1];
-            *reinterpret_cast<double2*>(crow + c) = o;
-          } else if (c < nvalid) {
-            crow[c] += sc * v[c];
+          for (int c = 0; c < 16; ++c)
+            if (c < nvalid) C[(long long)(b0 + c) * ldc + a] += sc * v[c];
+        } else {
+          double* crow = C + (long long)a * ldc + b0;
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            if (c + 1 < nvalid) {
+              double2 o = *reinterpret_cast<double2*>(crow + c);
+              o.x += sc * v[c];
+              o.y += sc * v[c + 1];
+              *reinterpret_cast<double2*>(crow + c) = o;
+            } else if (c < nvalid) {
+              crow[c] += sc * v[c];
+            }
           }
         }
       }

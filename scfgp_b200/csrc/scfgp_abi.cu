@@ -50,6 +50,7 @@ struct Ctx {
   // MN-major views of digR (contraction = chunk row) for the Gram products
   CUtensorMap mapPhiMN_A1, mapPhiMN_B1;                   // Phi half, ks planes (pass 1: G)
   CUtensorMap mapPhiMN_B, mapPsiMN_A;                     // Phi / Psi halves, ks2 planes (pass 2: H)
+  CUtensorMap mapPhiMN_A, mapPsiMN_B;                     // the same with the box widths swapped (border tiles)
 };
 
 }  // namespace
@@ -117,7 +118,7 @@ struct scfgp_handle {
   int cache_ks = 0;
   int want_cache = 1;          // SCFGP_PHI_CACHE=0 disables
   CUtensorMap mapCacheK, mapCacheMN_A, mapCacheMN_B;
-  int2* gram_items = nullptr;
+  int4* gram_items = nullptr;
   int gram_count = 0;
   int vparts = 0;              // partial rows of vpart per chunk
   int gsplit = 1;              // partial Gram accumulators per chunk stream (kGramSplit in the emulated mode)
@@ -579,6 +580,8 @@ int alloc_chunk_buffers(scfgp_handle* h) {
       if ((rc = make_tmap_digits_mn(h, &c.mapPhiMN_B1, c.digR, K, R, 2 * Kp, ks, umma::TN))) return rc;
       if ((rc = make_tmap_digits_mn(h, &c.mapPhiMN_B, c.digR, K, R, 2 * Kp, ks2, umma::TN))) return rc;
       if ((rc = make_tmap_digits_mn(h, &c.mapPsiMN_A, c.digR + Kp, K, R, 2 * Kp, ks2, umma::TM))) return rc;
+      if ((rc = make_tmap_digits_mn(h, &c.mapPhiMN_A, c.digR, K, R, 2 * Kp, ks2, umma::TM))) return rc;
+      if ((rc = make_tmap_digits_mn(h, &c.mapPsiMN_B, c.digR + Kp, K, R, 2 * Kp, ks2, umma::TN))) return rc;
     }
   }
   return SCFGP_OK;
@@ -615,13 +618,21 @@ int alloc_emu_static(scfgp_handle* h) {
   if ((rc = dalloc(h, &h->gvmax, 1))) return rc;
   if ((rc = make_tmap_digits(h, &h->mapLiB, h->digLi, K, K + 1, Kp, ks, umma::TN))) return rc;
   if ((rc = make_tmap_digits(h, &h->mapCB, h->digC, Kp + K, K, 2 * Kp, ks, umma::TN))) return rc;
-  std::vector<int2> v;
-  for (int mt = 0; mt < cdiv(K, umma::TM); ++mt)
+  // Gram tiles (128 x 64) of the lower triangle.  When the last 128-row block holds at most 64 valid rows
+  // (K = 2080: 32), it is computed with the roles swapped -- 17 tiles (all feature blocks x the border's
+  // 64-wide block) instead of 33 three-quarters-empty ones -- and stored transposed (item.z = 1); at
+  // K = 2080 that also brings the tile count from 306 to 290 <= 2 x 148 persistent CTAs.
+  std::vector<int4> v;
+  const int nmt = cdiv(K, umma::TM), border = K % umma::TM;
+  const bool swap_border = border > 0 && border <= umma::TN && nmt > 1;
+  for (int mt = 0; mt < nmt - (swap_border ? 1 : 0); ++mt)
     for (int nt = 0; nt < cdiv(K, umma::TN); ++nt)
-      if (nt * umma::TN <= mt * umma::TM + umma::TM - 1) v.push_back(make_int2(mt, nt));
+      if (nt * umma::TN <= mt * umma::TM + umma::TM - 1) v.push_back(make_int4(mt, nt, 0, 0));
+  if (swap_border)
+    for (int mt = 0; mt < nmt; ++mt) v.push_back(make_int4(mt, (nmt - 1) * (umma::TM / umma::TN), 1, 0));
   h->gram_count = (int)v.size();
-  CK(cudaMalloc((void**)&h->gram_items, v.size() * sizeof(int2)));
-  CK(cudaMemcpy(h->gram_items, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&h->gram_items, v.size() * sizeof(int4)));
+  CK(cudaMemcpy(h->gram_items, v.data(), v.size() * sizeof(int4), cudaMemcpyHostToDevice));
   EMU_KS_SWITCH(h->ks, if ((rc = set_emu_attrs<KS>(h))) return rc);
   EMU_KS_SWITCH(h->ks2, if ((rc = set_emu_attrs<KS>(h))) return rc);
   return SCFGP_OK;
@@ -775,7 +786,10 @@ int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows, long long r0, boo
   EMU_KS_SWITCH(a_is_psi ? h->ks2 : h->ks,
                 emu::k_gram_i8<KS><<<std::min(nitems, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                     a_is_psi ? c.mapPsiMN_A : (use_cache ? h->mapCacheMN_A : c.mapPhiMN_A1),
-                    use_cache ? h->mapCacheMN_B : (a_is_psi ? c.mapPhiMN_B : c.mapPhiMN_B1), row0_a, row0_b, depth,
+                    use_cache ? h->mapCacheMN_B : (a_is_psi ? c.mapPhiMN_B : c.mapPhiMN_B1),
+                    // border tiles (roles swapped): M side = the B-side array in 128-byte boxes, N side = the A-side array
+                    use_cache ? h->mapCacheMN_A : (a_is_psi ? c.mapPhiMN_A : c.mapPhiMN_A1),
+                    a_is_psi ? c.mapPsiMN_B : (use_cache ? h->mapCacheMN_B : c.mapPhiMN_B1), row0_a, row0_b, depth,
                     split_len, h->K, h->gram_items, h->gram_count, nitems, c.acc, h->ldk, (long long)h->K * h->ldk,
                     h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
   prof_end(h, SCFGP_FAM_SYRK, c.sg);
