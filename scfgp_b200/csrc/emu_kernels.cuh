@@ -445,7 +445,8 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)
 k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
-              const __grid_constant__ CUtensorMap mapC, int seg1_stages, int row0, int rows, int J,
+              const __grid_constant__ CUtensorMap mapC, int seg1_stages, int row0, const int8_t* __restrict__ dphi,
+              long long dpitch, long long dplane, double recon, int rows, int J,
               int depth2, int ntiles, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
               long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
               const double* __restrict__ pbar, const double* __restrict__ alpha, double* __restrict__ Zbar,
@@ -492,6 +493,39 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (h16 == 1) umma::epilogue_release(p);
       double zb[8];
       const int f0 = (t.n0 + pcol) >> 1;
+      // Phi of this row's 8 features (cos and sin halves).  With the digit cache they are rebuilt from
+      // the cached digits -- the very bytes the TMA producer has just pulled through L2 for this tile --
+      // as one 8-byte load per digit plane (needs J % 8 == 0: host passes dphi only then).
+      double phc8[8], phs8[8];
+      if (dphi != nullptr) {
+        long long qc[8], qs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qc[i] = qs[i] = 0;
+        if (rvalid && f0 < J) {
+          const int8_t* dp = dphi + (long long)(row0 + r) * dpitch + f0;
+#pragma unroll
+          for (int d = 0; d < KS; ++d) {
+            const uint2 wc = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane);
+            const uint2 ws = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane + J);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t bc = (i < 4 ? wc.x : wc.y) >> (8 * (i & 3));
+              const uint32_t bs = (i < 4 ? ws.x : ws.y) >> (8 * (i & 3));
+              qc[i] = qc[i] * 256 + (long long)(int8_t)bc;
+              qs[i] = qs[i] * 256 + (long long)(int8_t)bs;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { phc8[i] = (double)qc[i] * recon; phs8[i] = (double)qs[i] * recon; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = rvalid && f0 + i < J;
+          phc8[i] = ok ? prow[f0 + i] : 0.0;
+          phs8[i] = ok ? prow[J + f0 + i] : 0.0;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int f = f0 + i;
@@ -500,7 +534,7 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           const int pj = t.n0 + pcol + 2 * i;
           const double pc = v[2 * i] * (cscale[pj] * sc) + yn * pbar[f] + gm * alpha[f];
           const double ps = v[2 * i + 1] * (cscale[pj + 1] * sc) + yn * pbar[J + f] + gm * alpha[J + f];
-          const double phc = prow[f], phs = prow[J + f];
+          const double phc = phc8[i], phs = phs8[i];
           zb[i] = -pc * phs + ps * phc;
           Zbar[(long long)r * ldz + f] = zb[i];
           sacc += pc * phc + ps * phs;

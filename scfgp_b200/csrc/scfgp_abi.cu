@@ -812,12 +812,16 @@ int emu_tgemm(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
 
 int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
   const int ntiles = cdiv(h->J, 32) * cdiv(rows, umma::TM);
+  // the epilogue rebuilds Phi from the cached digits (8-byte loads: needs J % 8 == 0), else reads the slab
+  const bool phi_from_digits = use_cache && h->J % 8 == 0;
+  const double recon = h->s2 * std::ldexp(1.0, -(8 * std::max(h->cache_ks, 1) - 1));
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
   EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
                            c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA, h->mapCB,
-                           use_cache ? (int)(h->Kp / umma::KB) : 0, use_cache ? (int)r0 : 0, rows, h->J,
+                           use_cache ? (int)(h->Kp / umma::KB) : 0, use_cache ? (int)r0 : 0,
+                           phi_from_digits ? h->phi_cache : nullptr, h->Kc, h->cache_rows * h->Kc, recon, rows, h->J,
                            (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0,
                            h->pbar, h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K));
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
@@ -1559,9 +1563,10 @@ int scfgp_eval_pass3(scfgp_handle* h) {
       // A operand digits [Phi | (gv / sigma) Phi], both against the scale s2: with the cache only the Psi
       // half is made (from the cached digits), the Phi half is read from the cache itself
       if (cached) {
-        // (also rewrites the float64 Phi slab from the cached digits: the backward epilogue reads it)
+        // (when J % 8 != 0 it also rewrites the float64 Phi slab from the cached digits for the backward
+        // epilogue; otherwise the epilogue rebuilds its Phi values from the cache directly)
         if ((rc = emu_digits_slab(h, c, h->ks2, true, r0, rows, h->gv + r0, h->sigg + 1, c.digR + h->Kp, nullptr,
-                                  nullptr, nullptr, rpitch, rplane, nullptr, nullptr, true)))
+                                  nullptr, nullptr, rpitch, rplane, nullptr, nullptr, h->J % 8 != 0)))
           return rc;
       } else {
         if ((rc = run_features(h, c, Xc, h->xvec, rows, nullptr, nullptr))) return rc;
