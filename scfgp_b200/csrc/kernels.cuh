@@ -499,54 +499,81 @@ __global__ void k_add_diag(double* __restrict__ A, long long ld, int K, double v
 
 // Factor the nb x nb diagonal block at (k0,k0) in place (lower), zero its strict upper
 // part, and write inv(L11) (lower) to Dinv (NB x NB, zero padded).        SCFGP.py:106-107
+//   Factorisation: right-looking; the 256 threads hold the 64 x 64 block as 4 x 4 register tiles and
+//   only column j travels through shared memory (double-buffered: ONE barrier per column).  The
+//   trailing update uses the unscaled column:  a[i][c] -= a[i][j] a[c][j] / a[j][j].
+//   Inverse: forward substitution, 4 lanes per column split every dot product (quad shuffles).
 constexpr size_t POTRF_SMEM = 2 * NB * (NB + 1) * sizeof(double);
 __global__ void __launch_bounds__(256, 1)
 k_potrf_diag(double* __restrict__ A, long long ld, int k0, int nb, double* __restrict__ Dinv,
              long long* __restrict__ info) {
+  static_assert(NB == 64, "4 x 4 tiles of 16 x 16 threads");
   extern __shared__ __align__(16) double smem_pd[];
-  double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_pd);
-  double (*b)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_pd + NB * (NB + 1));
+  double (*L)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_pd);                  // the factor
+  double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_pd + NB * (NB + 1));  // its inverse
+  __shared__ double colbuf[2][NB];
   const int tid = threadIdx.x;
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    int i = e / NB, j = e % NB;
-    a[i][j] = (i < nb && j <= i) ? A[(long long)(k0 + i) * ld + k0 + j] : 0.0;
-    b[i][j] = 0.0;
-  }
+  const int ty = tid >> 4, tx = tid & 15;
+  double r[4][4];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int i = 4 * ty + ii, c = 4 * tx + cc;
+      // rows / columns beyond nb: identity padding keeps the arithmetic finite
+      r[ii][cc] = (i < nb && c <= i) ? A[(long long)(k0 + i) * ld + k0 + c] : ((i == c && i >= nb) ? 1.0 : 0.0);
+    }
+  for (int e = tid; e < NB * (NB + 1); e += blockDim.x) { (&L[0][0])[e] = 0.0; (&X[0][0])[e] = 0.0; }
   __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (tid == 0) {
-      double d = a[j][j];
-      if (!(d > 0.0)) {
-        if (*info == 0) *info = (long long)(k0 + j) + 1;
+  for (int j = 0; j < NB; ++j) {
+    const int jj = j & 3;
+    if (tx == (j >> 2)) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+        colbuf[j & 1][4 * ty + ii] = jj == 0 ? r[ii][0] : (jj == 1 ? r[ii][1] : (jj == 2 ? r[ii][2] : r[ii][3]));
+    }
+    __syncthreads();
+    const double* col = colbuf[j & 1];
+    const double d = col[j];
+    if (tid == 0 && j < nb && !(d > 0.0) && *info == 0) *info = (long long)(k0 + j) + 1;
+    const double sq = sqrt(d), rs = 1.0 / sq, rd = 1.0 / d;
+    if (tx == (j >> 2)) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = 4 * ty + ii;
+        if (i >= j) L[i][j] = (i == j) ? sq : col[i] * rs;
       }
-      a[j][j] = sqrt(d);
     }
-    __syncthreads();
-    const double dj = a[j][j];
-    for (int i = j + 1 + tid; i < nb; i += blockDim.x) a[i][j] /= dj;
-    __syncthreads();
-    const int rem = nb - j - 1;
-    for (int e = tid; e < rem * rem; e += blockDim.x) {
-      int i = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= i) a[i][c] -= a[i][j] * a[c][j];
-    }
-    __syncthreads();
+    double ci[4], cc4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ci[k] = col[4 * ty + k]; cc4[k] = col[4 * tx + k] * rd; }
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int i = 4 * ty + ii, c = 4 * tx + cc;
+        if (c > j && c <= i) r[ii][cc] -= ci[ii] * cc4[cc];
+      }
   }
-  // inverse by forward substitution, one column per thread
-  if (tid < nb) {
-    const int c = tid;
-    b[c][c] = 1.0 / a[c][c];
-    for (int i = c + 1; i < nb; ++i) {
-      double sacc = 0;
-      for (int m = c; m < i; ++m) sacc += a[i][m] * b[m][c];
-      b[i][c] = -sacc / a[i][i];
+  __syncthreads();
+  // inverse: column c by the quad of lanes 4c .. 4c+3
+  {
+    const int c = tid >> 2, part = tid & 3;
+    for (int i = 0; i < NB; ++i) {
+      double sacc = 0.0;
+      if (i > c)
+        for (int m = c + part; m < i; m += 4) sacc += L[i][m] * X[m][c];
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+      if (part == 0 && i >= c) X[i][c] = ((i == c ? 1.0 : 0.0) - sacc) / L[i][i];
+      __syncwarp();
     }
   }
   __syncthreads();
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     int i = e / NB, j = e % NB;
-    if (i < nb && j < nb) A[(long long)(k0 + i) * ld + k0 + j] = (j <= i) ? a[i][j] : 0.0;
-    Dinv[e] = b[i][j];
+    if (i < nb && j < nb) A[(long long)(k0 + i) * ld + k0 + j] = (j <= i) ? L[i][j] : 0.0;
+    Dinv[e] = (i < nb && j < nb) ? X[i][j] : 0.0;
   }
 }
 
