@@ -15,6 +15,7 @@ using CfgTall = TileCfg<128, 64, 32, 32, 3>;   // 8 warps, panels
 using CfgFeat = TileCfg<128, 64, 32, 32, 2, 8>;   // 8 warps, 2 stages
 using CfgWide = TileCfg<64, 128, 32, 32, 3>;   // 8 warps, small dense NN products
 using CfgDw = TileCfg<64, 128, 32, 32, 2, 8>;  // 8 warps, D x J contraction (dW)
+using CfgSq = TileCfg<64, 64, 32, 32, 3>;      // 4 warps, 64 x 64 tiles: block-recursive triangular inverse
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -594,6 +595,16 @@ __global__ void k_symmetrize(double* __restrict__ A, long long ld, int K) {
   // write transposed block into (bj, bi)
   int ti = bj * 32 + threadIdx.y, tj = bi * 32 + threadIdx.x;
   if (ti < K && tj < K && tj > ti) A[(long long)ti * ld + tj] = tile[threadIdx.x][threadIdx.y];
+}
+
+// all diagonal blocks at once: Li[b NB + i][b NB + j] = Dinv[b][i][j]
+__global__ void k_place_diag_blocks(const double* __restrict__ Dinv, double* __restrict__ Li, long long ld, int K) {
+  const int b = blockIdx.x;
+  const int nb = min(NB, K - b * NB);
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+    const int i = e / nb, j = e % nb;
+    Li[(long long)(b * NB + i) * ld + b * NB + j] = Dinv[(long long)b * NB * NB + i * NB + j];
+  }
 }
 
 // copy a block (used to place inv(L_ii) on Li's diagonal)

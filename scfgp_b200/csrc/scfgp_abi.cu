@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <functional>
 
 #include <cuda_runtime.h>
 
@@ -126,7 +127,8 @@ struct scfgp_handle {
 
   // work lists
   ItemList lowerK, syrkK, fullK, tgemm, bwd, dw;
-  std::vector<ItemList> potrf_panel, potrf_trail, trtri_s, trtri_x;
+  std::vector<ItemList> potrf_panel, potrf_trail;
+  std::vector<ItemList> inv_t, inv_x;   // per level of the block-recursive triangular inverse: T = L21.Li11, Li21 = -Li22.T
   std::vector<int4*> to_free;
 
   // host state of the evaluation in flight
@@ -917,23 +919,19 @@ int factor_device(scfgp_handle* h, double* L, double* Li, int K, long long ld) {
         return rc;
     }
   }
-  // Li by block-row forward substitution:  Li[i,:i0] = -inv(L_ii) . (L[i,:i0] . Li[:i0,:i0])
+  // Li = inv(L), block-recursively:  inv([L11 0; L21 L22]) = [Li11 0; -Li22 (L21 Li11)  Li22].  The diagonal
+  // 64-blocks are the Dinv of the factorisation; every level of the recursion is two launches that do all
+  // merges of that level at once (tile lists with per-tile reduction ranges: the triangular zeros are skipped).
   CK(cudaMemsetAsync(Li, 0, (size_t)K * ld * sizeof(double), h->stream));
-  for (int bi = 0; bi < nblk; ++bi) {
-    const int i0 = bi * NB, nb = std::min(NB, K - i0);
-    double* Dk = h->Dinv + (size_t)bi * NB * NB;
-    if (i0 > 0) {
-      // S (nb x i0) = L[i0:, 0:i0] . Li[0:i0, 0:i0]       (NN; column block c needs k >= c)
-      if ((rc = launch_gemm<CfgWide, true, false, 2, 2>(h, L + (size_t)i0 * ld, ld, nb, Li, ld, i0, h->tmpS,
-                                                        ld, 1.0, 0.0, h->trtri_s[bi], i0)))
-        return rc;
-      // Li[i0:, 0:i0] = -Dinv . S
-      if ((rc = launch_gemm<CfgWide, true, false, 2, 2>(h, Dk, NB, nb, h->tmpS, ld, i0, Li + (size_t)i0 * ld,
-                                                        ld, -1.0, 0.0, h->trtri_x[bi], nb)))
-        return rc;
-    }
-    k_copy_block<<<cdiv(nb * nb, 256), 256, 0, h->stream>>>(Dk, NB, Li + (size_t)i0 * ld + i0, ld, nb, nb);
-    CKL();
+  k_place_diag_blocks<<<nblk, 256, 0, h->stream>>>(h->Dinv, Li, ld, K);
+  CKL();
+  for (size_t lev = 0; lev < h->inv_t.size(); ++lev) {
+    // T (in the scratch matrix BH, same position as the block it will become) = L21 . Li11
+    if ((rc = launch_gemm<CfgSq, true, false, 2, 2>(h, L, ld, K, Li, ld, K, h->BH, ld, 1.0, 0.0, h->inv_t[lev], K)))
+      return rc;
+    // Li21 = -Li22 . T
+    if ((rc = launch_gemm<CfgSq, true, false, 2, 2>(h, Li, ld, K, h->BH, ld, K, Li, ld, -1.0, 0.0, h->inv_x[lev], K)))
+      return rc;
   }
   return SCFGP_OK;
 }
@@ -969,8 +967,6 @@ int build_static_lists(scfgp_handle* h) {
   const int nblk = cdiv(K, NB);
   h->potrf_panel.resize(nblk);
   h->potrf_trail.resize(nblk);
-  h->trtri_s.resize(nblk);
-  h->trtri_x.resize(nblk);
   for (int bi = 0; bi < nblk; ++bi) {
     const int k0 = bi * NB, nb = std::min(NB, K - k0);
     const int m = K - k0 - nb;
@@ -978,13 +974,32 @@ int build_static_lists(scfgp_handle* h) {
     for (int i = 0; i < cdiv(m, 128); ++i) pv.push_back(make_int4(i, 0, 0, -1));
     if ((rc = upload_items(h, pv, &h->potrf_panel[bi]))) return rc;
     if ((rc = upload_items(h, lower_tiles(m, 128, 0, -1), &h->potrf_trail[bi]))) return rc;
-    std::vector<int4> sv, xv;
-    for (int j = 0; j < cdiv(k0, 128); ++j) {
-      sv.push_back(make_int4(0, j, j * 128, -1));  // skip the zero upper part of Li
-      xv.push_back(make_int4(0, j, 0, -1));
+  }
+  // block-recursive inverse: merges grouped by level (height of the recursion tree above the leaves)
+  {
+    std::vector<std::vector<int4>> lt, lx;
+    // returns the level of the merged range [lo, hi) (in 64-blocks); leaves have level -1
+    std::function<int(int, int)> rec = [&](int lo, int hi) -> int {
+      if (hi - lo <= 1) return -1;
+      const int mid = (lo + hi + 1) / 2;
+      const int lev = std::max(rec(lo, mid), rec(mid, hi)) + 1;
+      if ((int)lt.size() <= lev) { lt.resize(lev + 1); lx.resize(lev + 1); }
+      for (int i = mid; i < hi; ++i)
+        for (int j = lo; j < mid; ++j) {
+          // T[i][j] = sum_{k in [j, mid)} L[i][k] Li[k][j]        (Li11 lower triangular: k >= j)
+          lt[lev].push_back(make_int4(i, j, j * NB, std::min(mid * NB, K) - j * NB));
+          // Li[i][j] = - sum_{k in [mid, i]} Li[i][k] T[k][j]     (Li22 lower triangular: k <= i)
+          lx[lev].push_back(make_int4(i, j, mid * NB, std::min((i + 1) * NB, K) - mid * NB));
+        }
+      return lev;
+    };
+    rec(0, nblk);
+    h->inv_t.resize(lt.size());
+    h->inv_x.resize(lx.size());
+    for (size_t l = 0; l < lt.size(); ++l) {
+      if ((rc = upload_items(h, lt[l], &h->inv_t[l]))) return rc;
+      if ((rc = upload_items(h, lx[l], &h->inv_x[l]))) return rc;
     }
-    if ((rc = upload_items(h, sv, &h->trtri_s[bi]))) return rc;
-    if ((rc = upload_items(h, xv, &h->trtri_x[bi]))) return rc;
   }
   return SCFGP_OK;
 }
