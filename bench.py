@@ -236,7 +236,8 @@ def main():
     n_local = hi - lo
 
     Xd, yd, params0 = make_device_problem(n_local, D, S, M, seed=1000 + rank, device=device, dist=dist)
-    eng = Engine(D, S, M, device=local_rank, chunk_rows=args.chunk_rows or None, precision=args.precision)
+    eng = Engine(D, S, M, device=local_rank, chunk_rows=args.chunk_rows or None, precision=args.precision,
+                 pinned_results=True)   # results land in page-locked host buffers owned by the engine
     eng.set_data_device(Xd, yd, n_global=N)
     emulated = eng.precision.startswith("emu")
     digits = int(eng.precision[3:]) if emulated else 0
@@ -269,6 +270,7 @@ def main():
         pass_ms.append(eng.pass_ms())
     e1.record()
     barrier()
+    grad, alpha, Li = grad.copy(), alpha.copy(), Li.copy()   # (views of the engine's pinned buffers: later evals overwrite them)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     launches = eng.launches - launches0

@@ -30,7 +30,7 @@ class _DevBuf:
 
 class Engine:
     def __init__(self, D: int, S: int, M: int, fftype: int = _lib.FF_PHASE, device: int = 0,
-                 chunk_rows: int | None = None, precision: str | None = None):
+                 chunk_rows: int | None = None, precision: str | None = None, pinned_results: bool = False):
         self.lib = _lib.load()
         self.D, self.S, self.M = int(D), int(S), int(M)
         self.J = self.S + self.M
@@ -50,6 +50,10 @@ class Engine:
         if precision is not None:
             self.set_precision(precision)
         self.N = 0
+        # pinned_results: eval() returns grad / alpha / Li as views of page-locked buffers owned by the
+        # engine (the 8 K^2-byte copy of Li runs at PCIe speed instead of through the driver's bounce
+        # buffers); the views are overwritten by the next eval() -- copy them if they must survive it
+        self._pinned = {} if pinned_results else None
         self._keep = None   # keeps borrowed torch tensors alive
         self._red = {}
 
@@ -193,9 +197,18 @@ class Engine:
         except ImportError:
             pass
         cost = np.zeros(1)
-        grad = np.zeros(self.P) if want_grad else None
-        alpha = np.zeros(self.K) if want_factors else None
-        Li = np.zeros((self.K, self.K)) if want_factors else None
+        if self._pinned is not None:
+            if not self._pinned:
+                import torch
+                for name, shape in (("grad", (self.P,)), ("alpha", (self.K,)), ("Li", (self.K, self.K))):
+                    self._pinned[name] = torch.zeros(shape, dtype=torch.float64, pin_memory=True).numpy()
+            grad = self._pinned["grad"] if want_grad else None
+            alpha = self._pinned["alpha"] if want_factors else None
+            Li = self._pinned["Li"] if want_factors else None
+        else:
+            grad = np.zeros(self.P) if want_grad else None
+            alpha = np.zeros(self.K) if want_factors else None
+            Li = np.zeros((self.K, self.K)) if want_factors else None
         nul = C.POINTER(C.c_double)()
         gp = _lib.dptr(grad) if want_grad else nul
         ap = _lib.dptr(alpha) if want_factors else nul

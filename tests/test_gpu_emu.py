@@ -396,3 +396,19 @@ def test_outliers_in_y(prec, amp, gtol):
             assert rel(g[sl], g0[sl]) <= gtol, (name, rel(g[sl], g0[sl]))
     assert np.abs(al - al0).max() <= 1e-5 * max(1.0, np.abs(al0).max())
     eng.close()
+
+
+def test_pinned_result_buffers():
+    """pinned_results=True: same numbers, returned as views of page-locked buffers the engine reuses."""
+    N, D, S, M = 3000, 8, 4, 100
+    X, y, h = synth.make_problem(N, D, S, M, seed=8)
+    ref = Engine(D, S, M, precision="emu5"); ref.set_data(X, y)
+    c0, g0, a0, L0 = ref.eval(h)
+    eng = Engine(D, S, M, precision="emu5", pinned_results=True); eng.set_data(X, y)
+    c1, g1, a1, L1 = eng.eval(h)
+    assert c1 == c0
+    np.testing.assert_array_equal(g1, g0); np.testing.assert_array_equal(L1, L0); np.testing.assert_array_equal(a1, a0)
+    h2 = h.copy(); h2[1] += 0.1
+    c2, g2, a2, L2 = eng.eval(h2)
+    assert g2 is g1 and L2 is L1 and not np.array_equal(g2, g0)     # reused storage, new contents
+    ref.close(); eng.close()
