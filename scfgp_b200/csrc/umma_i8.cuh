@@ -50,12 +50,15 @@ struct Geo {
   static constexpr int B_BYTES = KS * TN * KB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (224 * 1024) / STAGE_BYTES;
+#ifndef UMMA_A_TMEM
+#define UMMA_A_TMEM 0
+#endif
 #ifndef UMMA_MAX_STAGES
 #define UMMA_MAX_STAGES 4
 #endif
   static constexpr int STAGES = STAGES_RAW > UMMA_MAX_STAGES ? UMMA_MAX_STAGES : STAGES_RAW;
   static constexpr int CLASS_COLS = KS * TN;
-  static constexpr int TMEM_COLS = CLASS_COLS <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = (CLASS_COLS <= 256 && !UMMA_A_TMEM) ? 256 : 512;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(KS >= 2 && KS <= 8, "2..8 digits");
   static_assert(STAGES >= 2, "need a double buffer");
@@ -97,6 +100,22 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// same with A read from tensor memory (lane = tile row, 8 columns = the 32 contraction bytes)
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared memory (128 rows x 32 bytes, described like an MMA operand) -> 128 lanes x 8 columns of tensor memory
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 // 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (quarter*32 + t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -287,6 +306,17 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         tc_fence_after();
         const uint32_t sa = smem_u32(p.stages + (size_t)st * G::STAGE_BYTES);
         const uint32_t sb = sa + G::A_BYTES;
+#if UMMA_A_TMEM
+        // A digits staged into tensor memory behind the class accumulators (double-buffered per stage)
+        const uint32_t abuf = tmem_base + (uint32_t)(TN * KS + (it & 1) * (KS * 16));
+        if (!TR) {
+#pragma unroll
+          for (int ks = 0; ks < KB / 32; ++ks)
+#pragma unroll
+            for (int i = 0; i < KS; ++i)
+              tmem_cp_128x256b(abuf + (uint32_t)((ks * KS + i) * 8), smem_desc_sw64(sa + i * (TM * KB) + ks * 32));
+        }
+#endif
 #pragma unroll
         for (int ks = 0; ks < KB / 32; ++ks) {
 #if UMMA_PROBE_MODE == 3 || UMMA_PROBE_MODE == 4
@@ -317,6 +347,12 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
                      : smem_desc_sw64(sb + j0 * (TN * KB) + ks * 32);
               const uint32_t acc = (kb == 0 && ks == 0 && i == 0) ? 0u : 1u;
 #if UMMA_PROBE_MODE != 1
+#if UMMA_A_TMEM
+              if (!TR)
+                mma_i8_ts(tmem_base + (uint32_t)(TN * (i + j0)), abuf + (uint32_t)((ks * KS + i) * 8), bdesc,
+                          idesc_i8(TN * cnt), acc);
+              else
+#endif
               mma_i8(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
                      TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
 #else

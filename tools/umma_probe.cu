@@ -268,6 +268,20 @@ int main(int argc, char** argv) {
     run_case<6>(8192, 2080, 4160, 0, 4160, false, 2000);
     return 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "ts")) {
+    // A-in-tensor-memory experiment (build with -DUMMA_A_TMEM=1; at most 5 digits): exactness, burst, sustained
+    int bad = 0;
+    bad += run_case<2>(128, 64, 64, 0, 64, true, 0);
+    bad += run_case<4>(256, 64, 512, 0, 512, true, 0);
+    bad += run_case<5>(300, 200, 520, 64, 520, true, 0);
+    bad += run_case<5>(256, 128, 1000, 128, 960, true, 0);
+    printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
+    run_case<5>(8192, 2080, 4160, 0, 4160, false, 5);
+    run_case<5>(8192, 2080, 4160, 0, 4160, false, 20);
+    run_case<5>(8192, 2080, 4160, 0, 4160, false, 2500);
+    run_case<4>(8192, 2080, 4160, 0, 4160, false, 20);
+    return bad ? 1 : 0;
+  }
   const bool perf = argc > 1 && !strcmp(argv[1], "perf");
   int bad = 0;
   if (!perf) {
