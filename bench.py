@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one 8192-row k_backward_i8 launch (ncu --set full), by digits
-TRAFFIC_BACKWARD_I8 = {5: 766.6e6}
+TRAFFIC_BACKWARD_I8 = {5: 535.4e6}   # profiles/r1_prof_backward_i8_ncu_full.txt
 
 WORKLOAD = dict(name="cfg4: synthetic N=10M, D=64, rank=16, feature_size=1024", N=10_000_000, D=64, S=16, M=1024)
 
