@@ -355,3 +355,49 @@ def test_save_load_roundtrip(tmp_path):
     mu2, sd2 = m2.predict(X[:20])
     np.testing.assert_allclose(mu2, mu, rtol=1e-12)
     np.testing.assert_allclose(sd2, sd, rtol=1e-12)
+
+
+class _OracleEngine:
+    """Oracle-backed stand-in for the CUDA engine (checker only): drives the same facade loop on the CPU."""
+
+    def __init__(self, D, S, M):
+        self.D, self.S, self.M = D, S, M
+
+    def set_data(self, X, y, n_global=None):
+        self.X, self.y = X, np.asarray(y).reshape(-1)
+
+    def eval(self, h, want_grad=True, **_):
+        return O.streaming_eval(h, self.X, self.y, self.S, self.M, want_grad=want_grad)
+
+    def predict(self, h, Xs, a, L):
+        return O.literal_predict(h, Xs, a, L, self.S, self.M)
+
+
+@pytest.mark.parametrize("precision,ptol,ctol", [("fp64", 1e-8, 1e-10), ("emu5", None, 1e-6)])
+def test_optimizer_trajectory_matches_oracle_driven_fit(precision, ptol, ctol):
+    """Row f1 of SURVEY section 8: the whole training loop (SCFGP.py:184-276; Adam + the Nesterov wrapper,
+    Optimizer.py) driven by the CUDA evaluation follows the loop driven by the oracle: same costs per
+    iteration, same final parameters (FP64 path) and the same predictions."""
+    rng = np.random.default_rng(11)
+    X = rng.lognormal(size=(300, 6))
+    y = (np.tanh(X @ rng.standard_normal(6) / 4) * 5 + 20 + 0.3 * rng.standard_normal(300))[:, None]
+    Xtr, ytr, Xte, yte = X[:240], y[:240], X[240:], y[240:]
+    runs = []
+    for which in ("oracle", "cuda"):
+        np.random.seed(21)
+        m = SCFGP(rank=3, feature_size=20, fftype="phase", msg=False,
+                  **({"precision": precision} if which == "cuda" else {}))
+        m.set_data(Xtr, ytr)
+        if which == "oracle":
+            m._engine = _OracleEngine(m.D, m.S, m.M)
+        m.optimize(Xte, yte, None, None, max_iter=20, restore_best=False)
+        mu, sd = m.predict(Xte)
+        runs.append((np.array(m.evals["COST"][1]), m.params.copy(), mu, sd))
+    (c0, p0, mu0, sd0), (c1, p1, mu1, sd1) = runs
+    assert len(c0) == len(c1) == 21
+    np.testing.assert_allclose(c1, c0, rtol=ctol)
+    if ptol is not None:
+        np.testing.assert_allclose(p1, p0, atol=ptol)
+    scale = float(np.std(yte))
+    np.testing.assert_allclose(mu1, mu0, atol=1e-5 * scale if ptol else 1e-3 * scale)
+    np.testing.assert_allclose(sd1, sd0, atol=1e-5 * scale if ptol else 1e-3 * scale)
