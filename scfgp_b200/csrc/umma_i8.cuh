@@ -53,6 +53,9 @@ struct Geo {
 #ifndef UMMA_A_TMEM
 #define UMMA_A_TMEM 0
 #endif
+#ifndef UMMA_COLLECTOR
+#define UMMA_COLLECTOR 0
+#endif
 #ifndef UMMA_MAX_STAGES
 #define UMMA_MAX_STAGES 4
 #endif
@@ -100,6 +103,29 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// collector hints: COLL 1 = keep the fetched A slice for the next instruction (fill), 2 = reuse it (lastuse)
+template <int COLL>
+__device__ __forceinline__ void mma_i8_coll(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if (COLL == 1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // same with A read from tensor memory (lane = tile row, 8 columns = the 32 contraction bytes)
 __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
@@ -352,6 +378,16 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
                 mma_i8_ts(tmem_base + (uint32_t)(TN * (i + j0)), abuf + (uint32_t)((ks * KS + i) * 8), bdesc,
                           idesc_i8(TN * cnt), acc);
               else
+#endif
+#if UMMA_COLLECTOR
+              if (KS - i > 4) {   // two instructions share this A slice
+                if (j0 == 0)
+                  mma_i8_coll<1>(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
+                                 TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
+                else
+                  mma_i8_coll<2>(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
+                                 TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
+              } else
 #endif
               mma_i8(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
                      TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
