@@ -1,10 +1,14 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name.
+
+    python tools/launch_summary.py launches.csv [top] [regex of kernel names to keep]
+"""
 import collections
 import csv
+import re
 import sys
 
 
-def main(path, top=25):
+def main(path, top=25, only=None):
     rows = list(csv.reader(open(path, errors="replace")))
     hdr = None
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -23,6 +27,8 @@ def main(path, top=25):
             elif d.get("Metric Unit", "ns") in ("ms", "msecond"):
                 v *= 1e6
             k = d["Kernel Name"].split("(")[0][:70]
+            if only and not re.search(only, k):
+                continue
             agg[k][0] += 1
             agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
@@ -32,4 +38,4 @@ def main(path, top=25):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25, sys.argv[3] if len(sys.argv) > 3 else None)
