@@ -62,6 +62,40 @@ __device__ __forceinline__ uint32_t digit_byte(long long qp, int i) {
 }
 __device__ __forceinline__ uint32_t fix_bytes(uint32_t w) { return w ^ 0x80808080u; }  // per byte: u -> u - 128
 
+// ---- 5-digit fast paths (the default format): q' = q + 0x80808080 is a 40-bit field, top byte : four u fields ----
+// quant5: q' of v (= x * 2^39 / scale) as (hi byte, 32-bit word).  Adding 1.5 * 2^52 + bias rounds v to the nearest
+// integer (ties to even, as llrint does) and leaves q' in the low mantissa bits (two's complement).
+__device__ __forceinline__ void quant5(double v, uint32_t& hi, uint32_t& lo) {
+  const double lim = 274877906944.0;  // 2^38
+  v = fmin(fmax(v, -lim), lim);
+  const double d = v + (6755399441055744.0 + 2155905152.0);
+  lo = (uint32_t)__double2loint(d);
+  hi = (uint32_t)__double2hiint(d);  // only its low byte is used
+}
+// four q' -> the five plane words (byte e of a word = element e): a 4 x 4 byte transpose with byte permutes
+__device__ __forceinline__ void pack5x4(const uint32_t (&hi)[4], const uint32_t (&lo)[4], uint32_t (&w)[5]) {
+  const uint32_t a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[0], lo[1], 0x7362);
+  const uint32_t c = __byte_perm(lo[2], lo[3], 0x5140), d = __byte_perm(lo[2], lo[3], 0x7362);
+  w[4] = fix_bytes(__byte_perm(a, c, 0x5410));
+  w[3] = fix_bytes(__byte_perm(a, c, 0x7632));
+  w[2] = fix_bytes(__byte_perm(b, d, 0x5410));
+  w[1] = fix_bytes(__byte_perm(b, d, 0x7632));
+  w[0] = __byte_perm(__byte_perm(hi[0], hi[1], 0x0040), __byte_perm(hi[2], hi[3], 0x0040), 0x5410);
+}
+// the five plane words of four elements -> the four integers q as doubles (exact)
+__device__ __forceinline__ void unpack5x4(const uint32_t (&w)[5], double (&q)[4]) {
+  const uint32_t u1 = fix_bytes(w[1]), u2 = fix_bytes(w[2]), u3 = fix_bytes(w[3]), u4 = fix_bytes(w[4]);
+  const uint32_t a = __byte_perm(u4, u3, 0x5140), b = __byte_perm(u4, u3, 0x7362);
+  const uint32_t c = __byte_perm(u2, u1, 0x5140), d = __byte_perm(u2, u1, 0x7362);
+  const uint32_t lo[4] = {__byte_perm(a, c, 0x5410), __byte_perm(a, c, 0x7632), __byte_perm(b, d, 0x5410),
+                          __byte_perm(b, d, 0x7632)};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int hi = (int)(int8_t)(w[0] >> (8 * e));
+    q[e] = fma((double)hi, 4294967296.0, (double)lo[e] - 2155905152.0);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // per-row power-of-two scales of [M1 | f2 * M2] (either may be absent)
 //   scale[p(r)] = pow2_ceil(max_c |row r|), inv[p(r)] = 1 / scale
@@ -180,6 +214,32 @@ k_digits_rows(const double* __restrict__ src, long long ld, int rows, int cols, 
   }
 }
 
+// digits of four neighbouring elements x[e] * mm -> one 32-bit word per digit plane
+template <int KS>
+__device__ __forceinline__ void store_digits4(const double (&x)[4], double mm, int8_t* o, long long plane) {
+  if constexpr (KS == 5) {
+    uint32_t hi[4], lo[4], w[5];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) quant5(x[e] * mm, hi[e], lo[e]);
+    pack5x4(hi, lo, w);
+#pragma unroll
+    for (int s = 0; s < 5; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * plane) = w[s];
+  } else {
+    uint32_t packed[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) packed[s] = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long qp = biased_q<KS>(x[e] * mm);
+#pragma unroll
+      for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
+    }
+    *reinterpret_cast<uint32_t*>(o) = packed[0];
+#pragma unroll
+    for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * plane) = fix_bytes(packed[s]);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // digits of a streaming row slab (the Phi chunk), all its by-products in ONE pass over the data:
 //   source  : the float64 slab (FROM_DIGITS = false) or the digit cache (true: x = recon * sum_i d_i 256^(KS-1-i))
@@ -215,15 +275,27 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
       double x[4] = {0.0, 0.0, 0.0, 0.0};
       if (r < rows) {
         if (FROM_DIGITS) {
-          long long q[4] = {0, 0, 0, 0};
+          if constexpr (KS == 5) {
+            uint32_t w[5];
 #pragma unroll
-          for (int s = 0; s < KS; ++s) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(dsrc + (long long)s * dplane + (long long)r * dpitch + c);
+            for (int s = 0; s < 5; ++s)
+              w[s] = *reinterpret_cast<const uint32_t*>(dsrc + (long long)s * dplane + (long long)r * dpitch + c);
+            double q[4];
+            unpack5x4(w, q);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) q[e] = q[e] * 256 + (long long)(int8_t)(w >> (8 * e));
+            for (int e = 0; e < 4; ++e) x[e] = (c + e < cols) ? q[e] * recon : 0.0;
+          } else {
+            long long q[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+              const uint32_t w =
+                  *reinterpret_cast<const uint32_t*>(dsrc + (long long)s * dplane + (long long)r * dpitch + c);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) q[e] = q[e] * 256 + (long long)(int8_t)(w >> (8 * e));
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = (c + e < cols) ? (double)q[e] * recon : 0.0;
           }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] = (c + e < cols) ? (double)q[e] * recon : 0.0;
         } else {
           const double* p = src + (long long)r * ld + c;
           if (vec && c + 3 < cols) {
@@ -254,35 +326,11 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
       }
       if (dst1) {
         const double mm = (r < rows && rowmul1) ? m1 * rowmul1[r] : m1;
-        uint32_t packed[KS];
-#pragma unroll
-        for (int s = 0; s < KS; ++s) packed[s] = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const long long qp = biased_q<KS>(x[e] * mm);
-#pragma unroll
-          for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
-        }
-        int8_t* o = dst1 + (long long)r * pitch + c;
-        *reinterpret_cast<uint32_t*>(o) = packed[0];
-#pragma unroll
-        for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * plane) = fix_bytes(packed[s]);
+        store_digits4<KS>(x, mm, dst1 + (long long)r * pitch + c, plane);
       }
       if (dst2) {
         const double mm = (r < rows && rowmul2) ? m2 * rowmul2[r] : m2;
-        uint32_t packed[KS];
-#pragma unroll
-        for (int s = 0; s < KS; ++s) packed[s] = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const long long qp = biased_q<KS>(x[e] * mm);
-#pragma unroll
-          for (int s = 0; s < KS; ++s) packed[s] |= digit_byte<KS>(qp, s) << (8 * e);
-        }
-        int8_t* o = dst2 + (long long)r * pitch + c;
-        *reinterpret_cast<uint32_t*>(o) = packed[0];
-#pragma unroll
-        for (int s = 1; s < KS; ++s) *reinterpret_cast<uint32_t*>(o + (long long)s * plane) = fix_bytes(packed[s]);
+        store_digits4<KS>(x, mm, dst2 + (long long)r * pitch + c, plane);
       }
     }
   }
