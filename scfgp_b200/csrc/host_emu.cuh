@@ -1,0 +1,189 @@
+// Launch helpers of the emulated-FP64 path (int8 digit products, emu_kernels.cuh) and the digit cache.
+// (part of the single translation unit scfgp_abi.cu; included in this order)
+#pragma once
+
+namespace {
+
+// ---------------------------------------------------------------------------------
+// emulated-FP64 path: digit extraction + int8 tensor-core products (emu_kernels.cuh)
+// ---------------------------------------------------------------------------------
+int emu_digits_rows(scfgp_handle* h, cudaStream_t st, const double* src, long long ld, int rows, int cols,
+                    const double* rowmul, const double* rowinv, double ginv, const double* ginv_ptr, int permJ,
+                    int8_t* dst, long long pitch, long long slice_stride, int col_off, int nd = 0,
+                    const double* rowmul2 = nullptr, const double* ginv_ptr2 = nullptr, int col_off2 = 0) {
+  if (nd == 0) nd = h->ks2;
+  const long long total = (long long)rows * (cdiv(cols, 16) * 4);
+  trace_begin(h, "digits_rows", st);
+  EMU_KS_SWITCH(nd, emu::k_digits_rows<KS><<<cdiv(total, 256), 256, 0, st>>>(
+                           src, ld, rows, cols, rowmul, rowinv, ginv, ginv_ptr, permJ, dst, pitch, slice_stride, col_off,
+                           rowmul2, ginv_ptr2, col_off2));
+  trace_end(h, st);
+  CKL();
+  return SCFGP_OK;
+}
+
+// digits of one Phi chunk and their by-products (k_digits_slab): source = the float64 slab of the chunk
+// stream, or (from_cache) the digit cache rows r0..; dst1 / dst2 = digit arrays with row pitch `pitch`
+int emu_digits_slab(scfgp_handle* h, Ctx& c, int nd, bool from_cache, long long r0, int rows, const double* rowmul1,
+                    const double* gptr1, int8_t* dst1, const double* rowmul2, const double* gptr2, int8_t* dst2,
+                    long long pitch, long long plane, const double* wsum, double* cpart, bool write_slab = false) {
+  const int K = h->K;
+  const dim3 grid(cdiv((K + 15) / 16 * 16, 256), cdiv(rows, 128));
+  const double recon = h->s2 * std::ldexp(1.0, -(8 * h->cache_ks - 1));
+  trace_begin(h, from_cache ? "digits(cache)" : "digits(slab)", c.st);
+  if (from_cache) {
+    EMU_KS_SWITCH(nd, emu::k_digits_slab<KS, true><<<grid, 256, 0, c.st>>>(
+                          nullptr, 0, h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon, rows, K,
+                          1.0 / h->s2, rowmul1, gptr1, dst1, rowmul2, gptr2, dst2, pitch, plane, wsum, cpart,
+                          (long long)K, write_slab ? c.Phi : nullptr, h->ldk));
+  } else {
+    EMU_KS_SWITCH(nd, emu::k_digits_slab<KS, false><<<grid, 256, 0, c.st>>>(
+                          c.Phi, h->ldk, nullptr, 0, 0, 0.0, rows, K, 1.0 / h->s2, rowmul1, gptr1, dst1, rowmul2,
+                          gptr2, dst2, pitch, plane, wsum, cpart, (long long)K, nullptr, 0));
+  }
+  trace_end(h, c.st);
+  CKL();
+  return SCFGP_OK;
+}
+
+// The GEMM kernels of a chunk stream run on its low-priority companion stream: enter = the
+// companion waits for everything queued on the chunk stream, leave = the chunk stream waits
+// for the GEMM.
+int gemm_enter(scfgp_handle* h, Ctx& c) {
+  CK(cudaEventRecord(c.ev_sg, c.st));
+  CK(cudaStreamWaitEvent(c.sg, c.ev_sg, 0));
+  return SCFGP_OK;
+}
+int gemm_leave(scfgp_handle* h, Ctx& c) {
+  CK(cudaEventRecord(c.ev_gs, c.sg));
+  CK(cudaStreamWaitEvent(c.st, c.ev_gs, 0));
+  return SCFGP_OK;
+}
+
+// acc(lower tiles) += sc * digits(A)T . digits(Phi) over the rows of one chunk; both operands are
+// row-major digit arrays read MN-major (no transposed copies).  Pass 1: A = B = Phi (chunk buffer, or
+// the cache rows r0..); pass 2: A = Psi (chunk buffer), B = Phi (chunk buffer or cache).
+int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows, long long r0, bool use_cache) {
+  const int depth = (rows + umma::KB - 1) / umma::KB * umma::KB;
+  // rows per split: a multiple of the stage depth; short chunks use fewer splits
+  const int split_len = cdiv(cdiv(depth, h->gsplit), umma::KB) * umma::KB;
+  const int nsplit = cdiv(depth, split_len);
+  const int nitems = h->gram_count * nsplit;
+  const int row0_b = use_cache ? (int)r0 : 0;
+  const int row0_a = (use_cache && !a_is_psi) ? (int)r0 : 0;
+  int rc;
+  if ((rc = gemm_enter(h, c))) return rc;
+  prof_begin(h, SCFGP_FAM_SYRK, c.sg);
+  // pass 1 (G, feeds the Cholesky): ks digits; pass 2 (H): ks2 leading digits
+  EMU_KS_SWITCH(a_is_psi ? h->ks2 : h->ks,
+                emu::k_gram_i8<KS><<<std::min(nitems, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                    a_is_psi ? c.mapPsiMN_A : (use_cache ? h->mapCacheMN_A : c.mapPhiMN_A1),
+                    use_cache ? h->mapCacheMN_B : (a_is_psi ? c.mapPhiMN_B : c.mapPhiMN_B1),
+                    // border tiles (roles swapped): M side = the B-side array in 128-byte boxes, N side = the A-side array
+                    use_cache ? h->mapCacheMN_A : (a_is_psi ? c.mapPhiMN_A : c.mapPhiMN_A1),
+                    a_is_psi ? c.mapPsiMN_B : (use_cache ? h->mapCacheMN_B : c.mapPhiMN_B1), row0_a, row0_b, depth,
+                    split_len, h->K, h->gram_items, h->gram_count, nitems, c.acc, h->ldk, (long long)h->K * h->ldk,
+                    h->s2 * h->s2, a_is_psi ? c.sig : nullptr));
+  prof_end(h, SCFGP_FAM_SYRK, c.sg);
+  CKL();
+  return gemm_leave(h, c);
+}
+
+int emu_tgemm(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
+  const int ntiles = cdiv(h->K + 1, umma::TN) * cdiv(rows, umma::TM);
+  int rc;
+  if ((rc = gemm_enter(h, c))) return rc;
+  prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
+  EMU_KS_SWITCH(h->ks2, emu::k_tgemm_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                           use_cache ? h->mapCacheK : c.mapRowsA, h->mapLiB, use_cache ? (int)r0 : 0, rows, h->K, ntiles,
+                           h->liscale, h->s2, c.vpart, h->R, c.mu));
+  prof_end(h, SCFGP_FAM_TGEMM, c.sg);
+  CKL();
+  return gemm_leave(h, c);
+}
+
+int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
+  const int ntiles = cdiv(h->J, 32) * cdiv(rows, umma::TM);
+  // the epilogue rebuilds Phi from the cached digits (8-byte loads: needs J % 8 == 0), else reads the slab
+  const bool phi_from_digits = use_cache && h->J % 8 == 0;
+  const double recon = h->s2 * std::ldexp(1.0, -(8 * std::max(h->cache_ks, 1) - 1));
+  int rc;
+  if ((rc = gemm_enter(h, c))) return rc;
+  prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
+  EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
+                           c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA, h->mapCB,
+                           use_cache ? (int)(h->Kp / umma::KB) : 0, use_cache ? (int)r0 : 0,
+                           phi_from_digits ? h->phi_cache : nullptr, h->Kc, h->cache_rows * h->Kc, recon, rows, h->J,
+                           (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0,
+                           h->pbar, h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K));
+  prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
+  CKL();
+  return gemm_leave(h, c);
+}
+
+// (re)allocate the digit cache for the current data set if it is wanted and fits; otherwise run without
+void free_phi_cache(scfgp_handle* h) {
+  if (h->phi_cache) cudaFree(h->phi_cache);
+  h->phi_cache = nullptr;
+  h->cache_rows = 0;
+  h->cache_ks = 0;
+}
+int ensure_phi_cache(scfgp_handle* h) {
+  const bool want = h->prec == SCFGP_PREC_EMU_I8 && h->want_cache && h->ks == h->ks2 && h->N > 0;
+  const long long rows = (h->N + 127) / 128 * 128;
+  if (want && h->phi_cache && h->cache_rows >= rows && h->cache_ks == h->ks) return SCFGP_OK;
+  free_phi_cache(h);
+  if (!want) return SCFGP_OK;
+  h->Kc = (h->K + 15) / 16 * 16;
+  const size_t bytes = (size_t)h->ks * rows * h->Kc;
+  size_t fr = 0, tot = 0;
+  CK(cudaMemGetInfo(&fr, &tot));
+  if (bytes + ((size_t)6 << 30) > fr) return SCFGP_OK;   // keep 6 GB of head room for the caller
+  if (cudaMalloc((void**)&h->phi_cache, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    h->phi_cache = nullptr;
+    return SCFGP_OK;
+  }
+  h->cache_rows = rows;
+  h->cache_ks = h->ks;
+  int rc;
+  if ((rc = make_tmap_digits(h, &h->mapCacheK, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TM))) return rc;
+  if ((rc = make_tmap_digits_mn(h, &h->mapCacheMN_A, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TM))) return rc;
+  if ((rc = make_tmap_digits_mn(h, &h->mapCacheMN_B, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TN))) return rc;
+  return SCFGP_OK;
+}
+
+// digits of Li with per-row power-of-two scales (B operand of Phi.LiT)
+int emu_prepare_li(scfgp_handle* h) {
+  const int K = h->K;
+  emu::k_rowscale<<<K, 128, 0, h->stream>>>(h->Li, h->ldk, nullptr, 0, nullptr, K, K, 0, h->liscale, h->liinv);
+  CKL();
+  const long long plane = (long long)(K + 1) * h->Kp;
+  int rc;
+  if ((rc = emu_digits_rows(h, h->stream, h->Li, h->ldk, K, K, nullptr, h->liinv, 1.0, nullptr, 0, h->digLi, h->Kp,
+                            plane, 0)))
+    return rc;
+  // row K = alpha (its own power-of-two scale): the product's column K is mu = Phi.alpha
+  emu::k_rowscale<<<1, 128, 0, h->stream>>>(h->alpha, K, nullptr, 0, nullptr, 1, K, 0, h->liscale + K, h->liinv + K);
+  CKL();
+  return emu_digits_rows(h, h->stream, h->alpha, K, 1, K, nullptr, h->liinv + K, 1.0, nullptr, 0,
+                         h->digLi + (long long)K * h->Kp, h->Kp, plane, 0);
+}
+
+// digits of Cmat = [2 Abar | 2 sigma B] (rows permuted cos/sin-interleaved, per-row scales);
+// sigma = power-of-two bound of |gv| over this rank's rows (pass 2)
+int emu_prepare_c(scfgp_handle* h) {
+  const int K = h->K;
+  int rc;
+  emu::k_scale_from_bits<<<1, 1, 0, h->stream>>>(h->gvmax, h->sigg);
+  CKL();
+  emu::k_rowscale<<<K, 128, 0, h->stream>>>(h->A2, h->ldk, h->B2, h->ldk, h->sigg, K, K, h->J, h->cscale, h->cinv);
+  CKL();
+  if ((rc = emu_digits_rows(h, h->stream, h->A2, h->ldk, K, K, nullptr, h->cinv, 1.0, nullptr, h->J, h->digC,
+                            2 * h->Kp, (long long)K * 2 * h->Kp, 0)))
+    return rc;
+  return emu_digits_rows(h, h->stream, h->B2, h->ldk, K, K, nullptr, h->cinv, 1.0, h->sigg, h->J, h->digC, 2 * h->Kp,
+                         (long long)K * 2 * h->Kp, (int)h->Kp);
+}
+
+}  // namespace
