@@ -173,16 +173,17 @@ def test_repeatable_bitwise():
     eng.close()
 
 
-def test_nophase_fftype():
+@pytest.mark.parametrize("precision", ["fp64", "emu5"])
+def test_nophase_fftype(precision):
     """fftype='non-phase' (Z = X.W): same cost as the oracle evaluated with the phase
-    parameters chosen so that the centred phase vanishes."""
+    parameters chosen so that the centred phase vanishes (both arithmetic modes)."""
     N, D, S, M = 600, 6, 3, 40
     X, y, h = synth.make_problem(N, D, S, M, seed=10)
     a, b, c, l_F, r_F, F, l_FC, FC = O.unpack_params(h, D, S, M)
     h0 = h.copy()
     h0[-(S + M):-M] = l_F.mean(0)           # l_p = mean(l_F)  -> l_FC = 0
     h0[-M:] = F.mean(0)                     # p = mean(F)      -> FC = 0
-    eng = Engine(D, S, M, fftype=_lib.FF_NOPHASE)
+    eng = Engine(D, S, M, fftype=_lib.FF_NOPHASE, precision=precision)
     eng.set_data(X, y)
     c1, g1, al1, Li1 = eng.eval(h)
     c0, g0, al0, Li0 = O.streaming_eval(h0, X, y, S, M)
@@ -190,9 +191,9 @@ def test_nophase_fftype():
     assert np.abs(al1 - al0).max() <= PRED_TOL
     assert np.all(g1[-(S + M):] == 0)
     # and, by phase invariance, the same cost as the phase variant at h
-    eng2 = Engine(D, S, M, fftype=_lib.FF_PHASE)
+    eng2 = Engine(D, S, M, fftype=_lib.FF_PHASE, precision=precision)
     eng2.set_data(X, y)
-    assert abs(eng2.eval(h, want_grad=False)[0] - c1) <= 1e-9 * abs(c1)
+    assert abs(eng2.eval(h, want_grad=False)[0] - c1) <= (1e-9 if precision == "fp64" else COST_RTOL) * abs(c1)
     eng.close(); eng2.close()
 
 

@@ -28,14 +28,8 @@ for (N, D, S, M) in [(5001, 8, 4, 100), (20000, 64, 16, 1024)]:
     cs = torch.tensor([c], dtype=torch.float64, device="cuda"); lst = [torch.zeros_like(cs) for _ in range(world)]
     dist.all_gather(lst, cs)
     same = all(float(x) == float(lst[0]) for x in lst)
-    if rank == 0:
-        dist.barrier()
-    else:
-        dist.barrier()
+    dist.barrier()
     eng.close()
-    if rank == 0:
-        # single-GPU reference on rank 0 (not collective: process group bypassed by a 1-rank subgroup)
-        pass
     out.append((N, D, S, M, c, g, a, L, same))
 dist.barrier()
 if rank == 0:
