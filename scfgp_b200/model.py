@@ -21,6 +21,7 @@ from . import _lib
 from .engine import Engine
 from .optimizer import Optimizer as OPT
 from .scaler import Scaler
+from .sharding import shard_bounds
 
 _PHASE_NAMES = {None: _lib.FF_PHASE, True: _lib.FF_PHASE, "phase": _lib.FF_PHASE, "ph": _lib.FF_PHASE,
                 False: _lib.FF_NOPHASE, "non-phase": _lib.FF_NOPHASE, "nonphase": _lib.FF_NOPHASE,
@@ -52,9 +53,12 @@ class SCFGP(object):
 
     def __init__(self, rank=None, feature_size=None, fftype=None, msg=None, *, sparsity=None, nfeats=None,
                  evals=None, X_scaling_method='auto-inv-normal', y_scaling_method='auto-normal',
-                 verbose=None, device=0, chunk_rows=None, precision=None, scaler_device='cpu'):
+                 verbose=None, device=None, chunk_rows=None, precision=None, scaler_device='cpu'):
         # G2 spelling: SCFGP(sparsity=20, nfeats=18, ...) (SCFGP.py:33-35);
         # G1 spelling: SCFGP(rank, feature_size, fftype, msg) (README.md:47-50).
+        if device is None:             # one process per GPU under torchrun: LOCAL_RANK picks the device
+            import os
+            device = int(os.environ.get("LOCAL_RANK", 0))
         S = sparsity if sparsity is not None else (rank if rank is not None else 20)
         M = nfeats if nfeats is not None else (feature_size if feature_size is not None else 18)
         self.S_requested = int(S)      # rank <= 0 ("-1" in the G1 scripts): resolved to D in set_data
@@ -128,13 +132,45 @@ class SCFGP(object):
     def _is_cuda_tensor(a):
         return hasattr(a, "is_cuda") and bool(a.is_cuda)
 
+    @staticmethod
+    def _ranks():
+        """(rank, world) of ``torch.distributed`` when it is initialised (one process per GPU), else (0, 1)."""
+        try:
+            import torch.distributed as td
+            if td.is_available() and td.is_initialized():
+                return td.get_rank(), td.get_world_size()
+        except ImportError:
+            pass
+        return 0, 1
+
+    def _sync_params(self):
+        """Every rank must evaluate the same hyper-parameters: rank 0's draw wins (the reference draws
+        from the unseeded global NumPy state, SCFGP.py:65-71)."""
+        rank, world = self._ranks()
+        if world == 1 or self.params is None:
+            return
+        import torch
+        import torch.distributed as td
+        dev = f"cuda:{self.device}" if td.get_backend() == "nccl" else "cpu"
+        t = torch.as_tensor(np.ascontiguousarray(self.params, dtype=np.float64)).to(dev)
+        td.broadcast(t, src=0)
+        self.params = t.cpu().numpy().copy()
+
     def _upload(self, X, y):
+        """Hand the (scaled) training set to the engine.  Under ``torch.distributed`` every rank holds the
+        same X, y and uploads only its own contiguous row shard (``shard_bounds``); the evaluation then
+        all-reduces the three partial reductions."""
         key = (id(X), id(y), tuple(X.shape))
         if self._engine_data_id != key:
+            rank, world = self._ranks()
+            n = int(X.shape[0])
+            if world > 1:
+                lo, hi = shard_bounds(n, rank, world)
+                X, y = X[lo:hi], y[lo:hi]
             if self._is_cuda_tensor(X):
-                self._engine.set_data_device(X, y)      # device-resident training set: zero-copy hand-off
+                self._engine.set_data_device(X, y, n_global=n)   # device-resident training set: zero-copy hand-off
             else:
-                self._engine.set_data(X, y)
+                self._engine.set_data(np.ascontiguousarray(X), np.ascontiguousarray(y), n_global=n)
             self._engine_data_id = key
 
     def build_models(self, algo='adam', algo_params=None, engine=None):
@@ -201,6 +237,7 @@ class SCFGP(object):
             self.message("-" * 60, "\nInitializing SCFGP hyperparameters...")
             if self.params is None or len(self.params) != 3 + self.D * self.S + self.M * self.S + self.S + self.M:
                 self.init_params()
+            self._sync_params()
             self.message("done.")
         else:
             cost, self.alpha, self.Li = self.train_func(self.X, self.y)
@@ -240,6 +277,7 @@ class SCFGP(object):
             self.build_models(algo['algo'], algo.get('algo_params'), engine=getattr(funcs, "engine", None))
         if visualizer is not None:
             raise NotImplementedError("Visualizer (matplotlib live plots) is out of scope of the hot path")
+        self._sync_params()
         if Xv is None or yv is None:
             obj = 'COST'
             for m in ('MAE', 'NMAE', 'MSE', 'NMSE', 'MNLP', 'SCORE'):
@@ -252,6 +290,8 @@ class SCFGP(object):
             if nbatches > 1:
                 if self._is_cuda_tensor(self.X):
                     raise NotImplementedError("minibatch mode needs host (NumPy) training data")
+                if self._ranks()[1] > 1:
+                    raise NotImplementedError("minibatch mode is single-process (its shuffles are per process)")
                 cost_sum, params_list, batch_count = 0, [], 0
                 for Xb, yb in self.minibatches(self.X, self.y, batchsize):
                     params_list.append(self.params.copy())

@@ -87,3 +87,93 @@ def _pred_worker(rank, world, port, T):
 def test_sharded_predict_gathers_in_row_order(T):
     """Batched predict over ranks: uneven shards (and an empty one) come back in row order."""
     mp.spawn(_pred_worker, args=(2, _free_port(), T), nprocs=2, join=True)
+
+
+class _PhaseEngine:
+    """Stand-in for the CUDA Engine on a CPU rank: the oracle's NumPy phases on this rank's row shard,
+    driven by the product's own run_eval_phases with a gloo all-reduce (what Engine.eval does over NCCL)."""
+
+    def __init__(self, D, S, M):
+        self.D, self.S, self.M = D, S, M
+        self.rows = None
+
+    def set_data(self, X, y, n_global=None):
+        self.X, self.y, self.n_global = X, np.asarray(y).reshape(-1), n_global
+        self.rows = X.shape[0]
+
+    def eval(self, h, want_grad=True, **_):
+        from oracle import scfgp_oracle as O
+        from scfgp_b200 import run_eval_phases
+        po = O.PhaseOracle(self.X, self.y, self.S, self.M, n_global=self.n_global, chunk=64)
+        po.begin(h)
+        run_eval_phases(po, lambda buf: dist.all_reduce(torch.from_numpy(buf)), want_grad=want_grad)
+        return po.finish(want_grad=want_grad)
+
+    def predict(self, h, Xs, a, L):
+        from oracle import scfgp_oracle as O
+        return O.literal_predict(h, Xs, a, L, self.S, self.M)
+
+
+def _facade_data():
+    rng = np.random.default_rng(3)
+    X = rng.lognormal(size=(161, 5))
+    y = np.tanh(X @ rng.standard_normal(5) / 4) * 5 + 20 + 0.3 * rng.standard_normal(161)
+    return X[:121], y[:121, None], X[121:], y[121:, None]
+
+
+def _facade_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from scfgp_b200 import SCFGP, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Xtr, ytr, Xte, yte = _facade_data()
+    np.random.seed(100 + rank)                  # different draws per rank: rank 0's must win
+    m = SCFGP(sparsity=3, nfeats=12)
+    m.set_data(Xtr, ytr)
+    m._engine = _PhaseEngine(m.D, m.S, m.M)
+    m.optimize(Xte, yte, None, None, max_iter=6)
+    lo, hi = shard_bounds(len(Xtr), rank, world)
+    assert m._engine.rows == hi - lo and m._engine.n_global == len(Xtr)
+    mu, sd = m.predict(Xte)
+    if rank == 0:
+        np.savez(out, params=m.params, cost=np.array(m.evals["COST"][1]), mu=mu, sd=sd)
+    t = torch.from_numpy(m.params.copy()); lst = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(lst, t)
+    assert all(torch.equal(x, lst[0]) for x in lst)      # replicated optimizer state stays in lock-step
+    dist.destroy_process_group()
+
+
+def test_facade_fit_shards_rows_over_two_ranks(tmp_path):
+    """SCFGP.set_data/optimize/predict under torch.distributed: every rank passes the same training set,
+    uploads only its row shard and follows the single-process fit started from rank 0's parameters."""
+    from oracle import scfgp_oracle as O
+    from scfgp_b200 import SCFGP
+
+    class OracleEngine:                                  # single-process stand-in (as in test_facade_cpu.py)
+        def __init__(self, D, S, M):
+            self.D, self.S, self.M = D, S, M
+
+        def set_data(self, X, y, n_global=None):
+            self.X, self.y = X, np.asarray(y).reshape(-1)
+
+        def eval(self, h, want_grad=True, **_):
+            return O.streaming_eval(h, self.X, self.y, self.S, self.M, want_grad=want_grad)
+
+        def predict(self, h, Xs, a, L):
+            return O.literal_predict(h, Xs, a, L, self.S, self.M)
+
+    out = str(tmp_path / "facade.npz")
+    mp.spawn(_facade_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    Xtr, ytr, Xte, yte = _facade_data()
+    np.random.seed(100)
+    m = SCFGP(sparsity=3, nfeats=12)
+    m.set_data(Xtr, ytr)
+    m._engine = OracleEngine(m.D, m.S, m.M)
+    m.optimize(Xte, yte, None, None, max_iter=6)
+    mu, sd = m.predict(Xte)
+    z = np.load(out)
+    np.testing.assert_allclose(z["cost"], np.array(m.evals["COST"][1]), rtol=1e-10)
+    np.testing.assert_allclose(z["params"], m.params, atol=1e-9)
+    np.testing.assert_allclose(z["mu"], mu, atol=1e-8)
+    np.testing.assert_allclose(z["sd"], sd, atol=1e-8)

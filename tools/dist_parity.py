@@ -8,7 +8,7 @@ import os, sys, json
 import numpy as np
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from scfgp_b200 import Engine, synth, shard_bounds
+from scfgp_b200 import Engine, SCFGP, synth, shard_bounds
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -31,6 +31,21 @@ for (N, D, S, M) in [(5001, 8, 4, 100), (20000, 64, 16, 1024)]:
     dist.barrier()
     eng.close()
     out.append((N, D, S, M, c, g, a, L, same))
+
+
+def facade_fit():
+    """SCFGP.fit through the facade: the same call on every rank (rows sharded inside) or on one GPU."""
+    rng = np.random.default_rng(4)
+    X = rng.lognormal(size=(3000, 8))
+    y = (np.tanh(X @ rng.standard_normal(8) / 4) * 5 + 20 + 0.3 * rng.standard_normal(3000))[:, None]
+    np.random.seed(17 + rank)                         # rank 0's initial parameters are broadcast
+    m = SCFGP(rank=4, feature_size=100, fftype="phase", msg=False, device=lr)
+    m.fit(X[:2500], y[:2500], X[2500:], y[2500:], max_iter=15)
+    mu, sd = m.predict(X[2500:])
+    return np.array(m.evals["COST"][1]), m.params.copy(), mu, sd
+
+
+fit_sharded = facade_fit()
 dist.barrier()
 if rank == 0:
     # now evaluate the same problems on one GPU with no process group in play
@@ -43,5 +58,11 @@ if rank == 0:
                           "cost_rel": abs(c - c1) / abs(c1), "grad_rel": float(np.linalg.norm(g - g1) / np.linalg.norm(g1)),
                           "alpha_abs": float(np.abs(a - a1).max()), "Li_abs": float(np.abs(L - L1).max())}), flush=True)
         e1.close()
+    c1, p1, mu1, sd1 = facade_fit()
+    c0, p0, mu0, sd0 = fit_sharded
+    print(json.dumps({"facade_fit": "SCFGP.fit, 2500 rows, 15 iterations", "world": world,
+                      "cost_traj_rel": float(np.abs(c0 - c1).max() / np.abs(c1).max()),
+                      "params_abs": float(np.abs(p0 - p1).max()), "mu_abs": float(np.abs(mu0 - mu1).max()),
+                      "sd_abs": float(np.abs(sd0 - sd1).max())}), flush=True)
 else:
     dist.destroy_process_group()
