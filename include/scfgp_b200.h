@@ -192,7 +192,12 @@ int scfgp_get_profile(const scfgp_handle* h, double* total_ms, long long* launch
  *   gather_column  : dcol[r] = (X[r][col] - shift) / range (contiguous copy of one column)
  *   column_moments : mean, population variance and skewness g1 = m3 / m2^1.5 of
  *                    boxcox(dcol, lambda) (lambda <= 0: of dcol itself)      Scaler.py:61-66,71-72
+ *   column_sums    : the raw sums behind column_moments over THIS rank's rows, for tables sharded by rows
+ *                    (central == 0: s1 = sum g(z); central != 0: s1 = sum (g(z) - centre)^2, s2 = sum (g(z) - centre)^3;
+ *                    g = boxcox(., lambda) or the identity for lambda <= 0); the caller all-reduces them
  *   column_distinct: min(number of distinct values, cap + 1), cap <= 15      Scaler.py:63
+ *   column_distinct_values: the same, and when there are at most `cap` the sorted values themselves in
+ *                    values[0 .. *ndistinct) (host array of cap doubles; the union over ranks decides)
  *   forward        : Scaler.forward_transform on the columns `cols` (host int array); algo
  *                    0 min-max, 1 normal, 2 inv-normal, 3 auto-normal, 4 auto-inv-normal; the
  *                    per-column parameter arrays are host pointers (unused ones may be NULL) */
@@ -202,7 +207,11 @@ int scfgp_scaler_gather_column(int device, const double* dX, long long N, long l
                                double range, double* dcol);
 int scfgp_scaler_column_moments(int device, const double* dcol, long long N, double lambda, double* mean,
                                 double* var, double* skew_g1);
+int scfgp_scaler_column_sums(int device, const double* dcol, long long N, double lambda, int central, double centre,
+                             double* s1, double* s2);
 int scfgp_scaler_column_distinct(int device, const double* dcol, long long N, int cap, int* ndistinct);
+int scfgp_scaler_column_distinct_values(int device, const double* dcol, long long N, int cap, int* ndistinct,
+                                        double* values);
 int scfgp_scaler_forward(int device, int algo, const double* dX, long long N, long long ld, const int* cols, int ncols,
                          const double* mn, const double* mx, const double* lambda, const double* mu,
                          const double* sd, double* dOut, long long ldo);

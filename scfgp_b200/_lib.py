@@ -65,7 +65,9 @@ PROTOTYPES = {
     "scfgp_scaler_gather_column": (C.c_int, [C.c_int, C.c_void_p, _ll, _ll, C.c_int, C.c_double, C.c_double,
                                              C.c_void_p]),
     "scfgp_scaler_column_moments": (C.c_int, [C.c_int, C.c_void_p, _ll, C.c_double, _dp, _dp, _dp]),
+    "scfgp_scaler_column_sums": (C.c_int, [C.c_int, C.c_void_p, _ll, C.c_double, C.c_int, C.c_double, _dp, _dp]),
     "scfgp_scaler_column_distinct": (C.c_int, [C.c_int, C.c_void_p, _ll, C.c_int, C.POINTER(C.c_int)]),
+    "scfgp_scaler_column_distinct_values": (C.c_int, [C.c_int, C.c_void_p, _ll, C.c_int, C.POINTER(C.c_int), _dp]),
     "scfgp_scaler_forward": (C.c_int, [C.c_int, C.c_int, C.c_void_p, _ll, _ll, C.POINTER(C.c_int), C.c_int,
                                        _dp, _dp, _dp, _dp, _dp, C.c_void_p, _ll]),
     "scfgp_dbg_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),

@@ -190,29 +190,46 @@ int scfgp_scaler_gather_column(int device, const double* dX, long long N, long l
   return SCFGP_OK;
 }
 
-int scfgp_scaler_column_moments(int device, const double* dcol, long long N, double lambda, double* mean,
-                                double* var, double* skew_g1) {
-  if (!dcol || N <= 0 || !mean || !var || !skew_g1) return SCFGP_ERR_ARG;
+static int column_sums(int device, const double* dcol, long long N, double lambda, int mode, double centre,
+                       double* s1, double* s2) {
   SCK(cudaSetDevice(device));
   static double* part_cache[64] = {nullptr};   // one small partial buffer per device, kept for the process
   if (device < 0 || device >= 64) return SCFGP_ERR_ARG;
   if (!part_cache[device]) SCK(cudaMalloc((void**)&part_cache[device], 2 * kBlocks * sizeof(double)));
   double* dpart = part_cache[device];
   std::vector<double> part(2 * kBlocks);
-  k_col_moments<<<kBlocks, kThreads>>>(dcol, N, lambda, 0, 0.0, dpart);
+  k_col_moments<<<kBlocks, kThreads>>>(dcol, N, lambda, mode, centre, dpart);
   SCK(cudaMemcpy(part.data(), dpart, 2 * kBlocks * sizeof(double), cudaMemcpyDeviceToHost));
-  const double m = sum_fixed(part, 0, kBlocks) / (double)N;
-  k_col_moments<<<kBlocks, kThreads>>>(dcol, N, lambda, 1, m, dpart);
-  SCK(cudaMemcpy(part.data(), dpart, 2 * kBlocks * sizeof(double), cudaMemcpyDeviceToHost));
-  const double m2 = sum_fixed(part, 0, kBlocks) / (double)N;
-  const double m3 = sum_fixed(part, kBlocks, kBlocks) / (double)N;
+  *s1 = sum_fixed(part, 0, kBlocks);
+  *s2 = sum_fixed(part, kBlocks, kBlocks);
+  return SCFGP_OK;
+}
+
+int scfgp_scaler_column_sums(int device, const double* dcol, long long N, double lambda, int central, double centre,
+                             double* s1, double* s2) {
+  if (!dcol || N <= 0 || !s1 || !s2) return SCFGP_ERR_ARG;
+  return column_sums(device, dcol, N, lambda, central ? 1 : 0, centre, s1, s2);
+}
+
+int scfgp_scaler_column_moments(int device, const double* dcol, long long N, double lambda, double* mean,
+                                double* var, double* skew_g1) {
+  if (!dcol || N <= 0 || !mean || !var || !skew_g1) return SCFGP_ERR_ARG;
+  double a = 0, b = 0;
+  int rc = column_sums(device, dcol, N, lambda, 0, 0.0, &a, &b);
+  if (rc != SCFGP_OK) return rc;
+  const double m = a / (double)N;
+  rc = column_sums(device, dcol, N, lambda, 1, m, &a, &b);
+  if (rc != SCFGP_OK) return rc;
+  const double m2 = a / (double)N;
+  const double m3 = b / (double)N;
   *mean = m;
   *var = m2;
   *skew_g1 = m2 > 0 ? m3 / (m2 * std::sqrt(m2)) : 0.0;
   return SCFGP_OK;
 }
 
-int scfgp_scaler_column_distinct(int device, const double* dcol, long long N, int cap, int* ndistinct) {
+int scfgp_scaler_column_distinct_values(int device, const double* dcol, long long N, int cap, int* ndistinct,
+                                        double* values) {
   if (!dcol || N <= 0 || cap < 1 || cap > 15 || !ndistinct) return SCFGP_ERR_ARG;
   SCK(cudaSetDevice(device));
   const int nb = 64, nt = 128;
@@ -233,7 +250,12 @@ int scfgp_scaler_column_distinct(int device, const double* dcol, long long N, in
   std::sort(vals.begin(), vals.end());
   const int nd = (int)(std::unique(vals.begin(), vals.end()) - vals.begin());
   *ndistinct = std::min(nd, cap + 1);
+  if (values && nd <= cap) std::copy(vals.begin(), vals.begin() + nd, values);
   return SCFGP_OK;
+}
+
+int scfgp_scaler_column_distinct(int device, const double* dcol, long long N, int cap, int* ndistinct) {
+  return scfgp_scaler_column_distinct_values(device, dcol, N, cap, ndistinct, nullptr);
 }
 
 int scfgp_scaler_forward(int device, int algo, const double* dX, long long N, long long ld, const int* cols, int ncols,

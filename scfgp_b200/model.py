@@ -53,7 +53,8 @@ class SCFGP(object):
 
     def __init__(self, rank=None, feature_size=None, fftype=None, msg=None, *, sparsity=None, nfeats=None,
                  evals=None, X_scaling_method='auto-inv-normal', y_scaling_method='auto-normal',
-                 verbose=None, device=None, chunk_rows=None, precision=None, scaler_device='cpu'):
+                 verbose=None, device=None, chunk_rows=None, precision=None, scaler_device='cpu',
+                 presharded=False):
         # G2 spelling: SCFGP(sparsity=20, nfeats=18, ...) (SCFGP.py:33-35);
         # G1 spelling: SCFGP(rank, feature_size, fftype, msg) (README.md:47-50).
         if device is None:             # one process per GPU under torchrun: LOCAL_RANK picks the device
@@ -74,10 +75,16 @@ class SCFGP(object):
         # N >= 1e6 rows where the reference's per-column host search dominates set_data
         if scaler_device not in ('cpu', 'gpu'):
             raise ValueError("scaler_device must be 'cpu' or 'gpu'")
+        # presharded=True (torch.distributed, one process per GPU): set_data receives THIS rank's rows of a
+        # table that is sharded by rows (too large to replicate); the scalers then combine their statistics
+        # over the ranks, which needs the streaming GPU scalers
+        self.presharded = bool(presharded)
+        if self.presharded and scaler_device != 'gpu':
+            raise ValueError("presharded=True needs scaler_device='gpu' (the scalers all-reduce their statistics)")
         if scaler_device == 'gpu':
             from .gpu_scaler import GpuScaler
-            self.X_scaler = GpuScaler(X_scaling_method, device)
-            self.y_scaler = GpuScaler(y_scaling_method, device)
+            self.X_scaler = GpuScaler(X_scaling_method, device, distributed=self.presharded)
+            self.y_scaler = GpuScaler(y_scaling_method, device, distributed=self.presharded)
         else:
             self.X_scaler = Scaler(X_scaling_method)
             self.y_scaler = Scaler(y_scaling_method)
@@ -164,7 +171,9 @@ class SCFGP(object):
         if self._engine_data_id != key:
             rank, world = self._ranks()
             n = int(X.shape[0])
-            if world > 1:
+            if world > 1 and self.presharded:
+                n = int(getattr(self.X_scaler, "n_total", n))      # rows of all ranks (all-reduced by the scaler)
+            elif world > 1:
                 lo, hi = shard_bounds(n, rank, world)
                 X, y = X[lo:hi], y[lo:hi]
             if self._is_cuda_tensor(X):
@@ -230,6 +239,8 @@ class SCFGP(object):
             self.y = np.ascontiguousarray(self.y_scaler.forward_transform(y))
         self.message("done.")
         self.N, self.D = (int(v) for v in self.X.shape)
+        if self.presharded:
+            self.N = int(getattr(self.X_scaler, "n_total", self.N))     # rows of all ranks
         if self.S_requested <= 0:
             self.S = self.D
             self.NAME = "SCFGP (Sparsity=%d, Fourier Features=%d)" % (self.S, self.M)

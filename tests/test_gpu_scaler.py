@@ -148,3 +148,42 @@ def test_facade_device_resident_training_set():
     assert mu.shape == (40, 1) and np.all(np.isfinite(mu)) and np.all(sd > 0)
     with pytest.raises(ValueError):
         SCFGP(rank=3, feature_size=20).set_data(Xt, yt)           # CUDA tensors need the GPU scalers
+
+
+def test_shard_level_sums_and_distinct_values():
+    """The entry points a row-sharded table uses (GpuScaler(distributed=True)): raw power sums of two row
+    shards add up to the whole column's moments, and the distinct-value sets can be merged."""
+    import ctypes as C
+    import torch
+    from scfgp_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    col = rng.random(50001) * 0.98 + 0.01
+    t = torch.as_tensor(col).cuda()
+    lam = 0.37
+
+    def sums(tt, central, centre):
+        a, b = C.c_double(), C.c_double()
+        assert lib.scfgp_scaler_column_sums(0, C.c_void_p(tt.data_ptr()), tt.numel(), lam, central, centre,
+                                            C.byref(a), C.byref(b)) == _lib.OK
+        return a.value, b.value
+
+    parts = (t[:20000].contiguous(), t[20000:].contiguous())
+    mean = sum(sums(p, 0, 0.0)[0] for p in parts) / col.size
+    m2 = sum(sums(p, 1, mean)[0] for p in parts) / col.size
+    m3 = sum(sums(p, 1, mean)[1] for p in parts) / col.size
+    mw, vw, gw = C.c_double(), C.c_double(), C.c_double()
+    assert lib.scfgp_scaler_column_moments(0, C.c_void_p(t.data_ptr()), col.size, lam, C.byref(mw), C.byref(vw),
+                                           C.byref(gw)) == _lib.OK
+    z = (col ** lam - 1) / lam
+    assert abs(mean - z.mean()) < 1e-12 and abs(mean - mw.value) < 1e-13
+    assert abs(m2 - z.var()) < 1e-12 and abs(m2 - vw.value) < 1e-13
+    assert abs(m3 / m2 ** 1.5 - gw.value) < 1e-10
+    few = torch.as_tensor(np.array([0.5, 0.25, 0.5, 0.75, 0.25] * 1000)).cuda()
+    nd, vals = C.c_int(), np.zeros(9)
+    assert lib.scfgp_scaler_column_distinct_values(0, C.c_void_p(few.data_ptr()), few.numel(), 9, C.byref(nd),
+                                                   _lib.dptr(vals)) == _lib.OK
+    assert nd.value == 3 and list(vals[:3]) == [0.25, 0.5, 0.75]
+    assert lib.scfgp_scaler_column_distinct_values(0, C.c_void_p(t.data_ptr()), t.numel(), 9, C.byref(nd),
+                                                   _lib.dptr(vals)) == _lib.OK
+    assert nd.value == 10

@@ -45,7 +45,24 @@ def facade_fit():
     return np.array(m.evals["COST"][1]), m.params.copy(), mu, sd
 
 
+def facade_fit_presharded(shard):
+    """Table sharded by rows BEFORE the facade sees it (presharded=True, GPU scalers all-reduce their statistics);
+    shard=False: the whole table in one process."""
+    rng = np.random.default_rng(6)
+    X = rng.lognormal(size=(4001, 6)); X[:, 2] = np.round(X[:, 2])[:] % 4          # one column with < 10 distinct values
+    y = (np.tanh(X @ rng.standard_normal(6) / 4) * 5 + 20 + 0.3 * rng.standard_normal(4001))[:, None]
+    Xte, yte = X[3500:], y[3500:]
+    lo, hi = shard_bounds(3500, rank, world) if shard else (0, 3500)
+    np.random.seed(23 + rank)
+    m = SCFGP(rank=3, feature_size=60, fftype="phase", msg=False, device=lr, scaler_device="gpu", presharded=shard)
+    m.fit(X[lo:hi], y[lo:hi], Xte, yte, max_iter=10)
+    mu, sd = m.predict(Xte)
+    return (np.array(m.evals["COST"][1]), np.asarray(m.X_scaler.data["boxcox"]), np.asarray(m.X_scaler.data["mu"]),
+            np.asarray(mu), np.asarray(sd), m.N)
+
+
 fit_sharded = facade_fit()
+fit_pre = facade_fit_presharded(True)
 dist.barrier()
 if rank == 0:
     # now evaluate the same problems on one GPU with no process group in play
@@ -64,5 +81,12 @@ if rank == 0:
                       "cost_traj_rel": float(np.abs(c0 - c1).max() / np.abs(c1).max()),
                       "params_abs": float(np.abs(p0 - p1).max()), "mu_abs": float(np.abs(mu0 - mu1).max()),
                       "sd_abs": float(np.abs(sd0 - sd1).max())}), flush=True)
+    c1, l1, m1, mu1, sd1, n1 = facade_fit_presharded(False)
+    c0, l0, m0, mu0, sd0, n0 = fit_pre
+    print(json.dumps({"facade_fit_presharded": "SCFGP(scaler_device='gpu', presharded=True).fit, 3500 rows over the ranks",
+                      "world": world, "rows_seen": [n0, n1], "boxcox_lambda_abs": float(np.abs(l0 - l1).max()),
+                      "scaler_mu_abs": float(np.abs(m0 - m1).max()),
+                      "cost_traj_rel": float(np.abs(c0 - c1).max() / np.abs(c1).max()),
+                      "mu_abs": float(np.abs(mu0 - mu1).max()), "sd_abs": float(np.abs(sd0 - sd1).max())}), flush=True)
 else:
     dist.destroy_process_group()
