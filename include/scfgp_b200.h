@@ -133,6 +133,11 @@ int scfgp_eval(scfgp_handle* h, const double* params, double* cost, double* grad
  * use the factors of the last evaluation still resident on the device. */
 int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long long T,
                   const double* alpha, const double* Li, double* mu, double* std);
+/* alpha (K) and Li (K x K row-major) from the host become the device-resident factors that
+ * scfgp_predict(.., NULL, NULL, ..) and scfgp_predict_device use: the (alpha, Li) arguments of the reference's
+ * pred_func (SCFGP/SCFGP.py:145-148) for callers whose test rows already live on the device, e.g. a model
+ * restored from a checkpoint (SCFGP.py:303-310) predicting in row shards. */
+int scfgp_set_factors(scfgp_handle* h, const double* alpha, const double* Li);
 /* same with device-resident inputs/outputs (batched predict over shards) */
 int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dXs, long long T,
                          double* dmu, double* dstd);

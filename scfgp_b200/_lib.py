@@ -44,6 +44,7 @@ PROTOTYPES = {
     "scfgp_set_data_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, _ll, _ll]),
     "scfgp_eval": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp]),
     "scfgp_predict": (C.c_int, [_h, _dp, _dp, _ll, _dp, _dp, _dp, _dp]),
+    "scfgp_set_factors": (C.c_int, [_h, _dp, _dp]),
     "scfgp_predict_device": (C.c_int, [_h, _dp, C.c_void_p, _ll, C.c_void_p, C.c_void_p]),
     "scfgp_eval_begin": (C.c_int, [_h, _dp, C.c_int]),
     "scfgp_eval_pass1": (C.c_int, [_h]),

@@ -800,6 +800,20 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
   return join_streams(h);
 }
 
+int scfgp_set_factors(scfgp_handle* h, const double* alpha, const double* Li) {
+  if (!h || !alpha || !Li) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  const int K = h->K;
+  CK(cudaMemcpyAsync(h->alpha, alpha, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(h->Li, h->ldk * sizeof(double), Li, (size_t)K * sizeof(double), (size_t)K * sizeof(double), K,
+                       cudaMemcpyHostToDevice, h->stream));
+  h->have_factors = true;
+  int rc;
+  if (h->prec == SCFGP_PREC_EMU_I8 && (rc = emu_prepare_li(h))) return rc;
+  CK(cudaStreamSynchronize(h->stream));   // the host arrays may go away once this returns
+  return SCFGP_OK;
+}
+
 int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long long T, const double* alpha,
                   const double* Li, double* mu, double* sd) {
   if (!h || !params || !Xs || !mu || !sd || T <= 0) return SCFGP_ERR_ARG;
@@ -807,12 +821,8 @@ int scfgp_predict(scfgp_handle* h, const double* params, const double* Xs, long 
   const int K = h->K;
   if ((alpha == nullptr) != (Li == nullptr)) { h->err = "pass both alpha and Li or neither"; return SCFGP_ERR_ARG; }
   if (alpha) {
-    CK(cudaMemcpyAsync(h->alpha, alpha, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpy2DAsync(h->Li, h->ldk * sizeof(double), Li, (size_t)K * sizeof(double),
-                         (size_t)K * sizeof(double), K, cudaMemcpyHostToDevice, h->stream));
-    h->have_factors = true;
-    int rcl;
-    if (h->prec == SCFGP_PREC_EMU_I8 && (rcl = emu_prepare_li(h))) return rcl;
+    int rcl = scfgp_set_factors(h, alpha, Li);
+    if (rcl) return rcl;
   }
   double *dXs = nullptr, *dout = nullptr;
   CK(cudaMalloc((void**)&dXs, (size_t)T * h->D * sizeof(double)));

@@ -258,6 +258,16 @@ class Engine:
                                            _lib.dptr(mu), _lib.dptr(sd)))
         return mu.reshape(-1, 1), sd
 
+    def set_factors(self, alpha, Li):
+        """Make host ``alpha`` (K,) / (K,1) and ``Li`` (K,K) the device-resident factors that ``predict_device`` /
+        ``predict_sharded`` / ``predict(..., None, None)`` use (the (alpha, Li) arguments of the reference's
+        pred_func, SCFGP/SCFGP.py:145-148)."""
+        alpha = _lib.as_f64(np.asarray(alpha).reshape(-1))
+        Li = _lib.as_f64(Li)
+        if alpha.shape[0] != self.K or Li.shape != (self.K, self.K):
+            raise ValueError(f"alpha/Li must have K={self.K} rows")
+        self._check(self.lib.scfgp_set_factors(self._h, _lib.dptr(alpha), _lib.dptr(Li)))
+
     def predict_device(self, params, Xs_t):
         """Device-resident batched predict: returns (mu, std) CUDA tensors of length T."""
         import torch

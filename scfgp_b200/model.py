@@ -347,16 +347,31 @@ class SCFGP(object):
 
     # ------------------------------------------------------------------ prediction (SCFGP.py:278-294)
     def predict(self, Xs, ys=None):
-        self.Xs = np.ascontiguousarray(self.X_scaler.forward_transform(np.asarray(Xs, dtype=np.float64)))
+        """``Xs`` (T, D): a NumPy array, or -- with ``scaler_device='gpu'`` -- a float64 CUDA tensor; the test rows
+        then stay on the device and, under ``torch.distributed``, are predicted in row shards over the ranks
+        (every rank passes the same ``Xs`` and gets the full result).  Returns NumPy (T, 1) mean and std."""
         if self.pred_func is None:
             self.build_models()
-        mu_f, std_f = self.pred_func(self.Xs, self.alpha, self.Li)
+        if self._is_cuda_tensor(Xs):
+            if not hasattr(self.X_scaler, "device"):
+                raise ValueError("CUDA tensors need scaler_device='gpu'")
+            self.Xs = self.X_scaler.forward_transform(Xs).contiguous()
+            eng = self._engine
+            eng.set_factors(self.alpha, self.Li)            # pred_func(Xs, alpha, Li): SCFGP.py:280
+            if self._ranks()[1] > 1:
+                mu_t, sd_t = eng.predict_sharded(self.params, self.Xs)
+            else:
+                mu_t, sd_t = eng.predict_device(self.params, self.Xs)
+            mu_f, std_f = mu_t.cpu().numpy().reshape(-1, 1), sd_t.cpu().numpy().reshape(-1)
+        else:
+            self.Xs = np.ascontiguousarray(self.X_scaler.forward_transform(np.asarray(Xs, dtype=np.float64)))
+            mu_f, std_f = self.pred_func(self.Xs, self.alpha, self.Li)
         mu_y = self.y_scaler.backward_transform(mu_f)
         up_bnd_y = self.y_scaler.backward_transform(mu_f + std_f[:, None])
         dn_bnd_y = self.y_scaler.backward_transform(mu_f - std_f[:, None])
         std_y = 0.5 * (up_bnd_y - dn_bnd_y)
         if ys is not None:
-            ys = np.asarray(ys, dtype=np.float64)
+            ys = np.asarray(ys.cpu().numpy() if self._is_cuda_tensor(ys) else ys, dtype=np.float64)
             if ys.ndim == 1:
                 ys = ys[:, None]
             ev = self.evals

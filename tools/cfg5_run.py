@@ -25,6 +25,41 @@ from bench import make_device_problem  # noqa: E402
 from scfgp_b200 import Engine, Optimizer, shard_bounds  # noqa: E402
 
 
+def facade(a, X, y, N, D, S, M, rank, world, lr, say, sync):
+    """The same job through the reference-shaped API: every rank hands ITS rows to SCFGP.fit (the GPU scalers
+    combine their statistics over the ranks), validation and test rows are CUDA tensors every rank holds."""
+    from scfgp_b200 import SCFGP
+    Xv, yv = X[:8192].clone(), y[:8192].clone()          # rank 0's first rows serve as the validation set
+    if world > 1:
+        dist.broadcast(Xv, src=0); dist.broadcast(yv, src=0)
+    m = SCFGP(rank=S, feature_size=M, fftype="phase", msg=False, device=lr, precision=a.precision,
+              scaler_device="gpu", presharded=world > 1)
+    sync(); t0 = time.time()
+    m.set_data(X, y)
+    sync(); t_scale = time.time() - t0
+    say(stage="facade.set_data", seconds=round(t_scale, 2), rows_total=m.N,
+        boxcox_objective_evals=m.X_scaler.objective_evals + m.y_scaler.objective_evals)
+    del X, y
+    sync(); t0 = time.time()
+    m.optimize(Xv, yv, None, None, max_iter=a.iters)
+    sync(); t_fit = time.time() - t0
+    costs = [float(c) for c in m.evals["COST"][1]]
+    say(stage="facade.optimize", iters=a.iters, seconds=round(t_fit, 2), costs=costs, nmse=m.evals["NMSE"][1],
+        mnlp=m.evals["MNLP"][1], decreasing=bool(costs[-1] < costs[0]))
+    Xs = torch.rand((a.test_rows, D), dtype=torch.float64, device="cuda",
+                    generator=torch.Generator(device="cuda").manual_seed(5))
+    sync(); t0 = time.time()
+    mu, sd = m.predict(Xs)
+    sync(); dt = time.time() - t0
+    chk = torch.tensor([float(mu.sum()), float(sd.sum())], dtype=torch.float64, device="cuda")
+    lst = [torch.zeros_like(chk) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(lst, chk)
+    say(stage="facade.predict", test_rows=a.test_rows, seconds=round(dt, 3), rows_per_sec=round(a.test_rows / dt, 1),
+        shapes=[list(mu.shape), list(sd.shape)], finite=bool(np.isfinite(mu).all() and np.isfinite(sd).all()),
+        ranks_identical=all(bool((x == chk).all()) for x in lst) if world > 1 else True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=100_000_000)
@@ -33,6 +68,8 @@ def main():
     ap.add_argument("--test-rows", type=int, default=2_000_000)
     ap.add_argument("--precision", default="emu5")
     ap.add_argument("--fp64", action="store_true", help="also evaluate once on the FP64 path and report parity")
+    ap.add_argument("--facade", action="store_true",
+                    help="run through SCFGP(scaler_device='gpu', presharded=True).fit / .predict instead of Engine")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     lr = int(os.environ.get("LOCAL_RANK", 0))
@@ -56,6 +93,12 @@ def main():
     sync()
     say(stage="data", rows=N, D=D, S=S, M=M, K=2 * (S + M), world=world, rows_per_rank=hi - lo,
         x_gb_per_rank=round((hi - lo) * D * 8 / 1e9, 2), seconds=round(time.time() - t0, 2))
+
+    if a.facade:
+        facade(a, X, y, N, D, S, M, rank, world, lr, say, sync)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     eng = Engine(D, S, M, device=lr, precision=a.precision)
     eng.set_data_device(X, y, n_global=N)
