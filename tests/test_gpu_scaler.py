@@ -146,8 +146,37 @@ def test_facade_device_resident_training_set():
     np.testing.assert_allclose(m.X.cpu().numpy(), m2.X, rtol=0, atol=2e-3)
     mu, sd = m.predict(X[:40])
     assert mu.shape == (40, 1) and np.all(np.isfinite(mu)) and np.all(sd > 0)
+    # test rows as a CUDA tensor: they stay on the device (scfgp_set_factors + scfgp_predict_device), same numbers
+    mu_t, sd_t = m.predict(Xt[:40], yt[:40])
+    np.testing.assert_allclose(mu_t, mu, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(sd_t, sd, rtol=0, atol=1e-9)
+    assert np.isfinite(m.TsNMSE)
     with pytest.raises(ValueError):
         SCFGP(rank=3, feature_size=20).set_data(Xt, yt)           # CUDA tensors need the GPU scalers
+    with pytest.raises(ValueError):
+        SCFGP(rank=3, feature_size=20, presharded=True)           # row-sharded tables need the GPU scalers
+
+
+def test_set_factors_feeds_device_predict():
+    """Engine.set_factors: host (alpha, Li) become the factors of the device-resident predict."""
+    import torch
+    from scfgp_b200 import Engine, synth
+    N, D, S, M = 900, 5, 3, 30
+    X, y, h = synth.make_problem(N, D, S, M, seed=4)
+    e1 = Engine(D, S, M); e1.set_data(X, y)
+    c, g, al, Li = e1.eval(h)
+    Xs = np.random.default_rng(2).random((257, D))
+    mu0, sd0 = e1.predict(h, Xs, al, Li)
+    e2 = Engine(D, S, M)                                            # fresh handle: no evaluation ever ran on it
+    with pytest.raises(ValueError):
+        e2.predict_device(h, torch.as_tensor(Xs, device="cuda"))
+    e2.set_factors(al, Li)
+    mu1, sd1 = e2.predict_device(h, torch.as_tensor(Xs, device="cuda"))
+    np.testing.assert_array_equal(mu1.cpu().numpy(), mu0.reshape(-1))
+    np.testing.assert_array_equal(sd1.cpu().numpy(), sd0.reshape(-1))
+    with pytest.raises(ValueError):
+        e2.set_factors(al[:-1], Li)
+    e1.close(); e2.close()
 
 
 def test_shard_level_sums_and_distinct_values():
