@@ -427,11 +427,11 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 }
 
 // ------------------------------------------------------------------------------------
-// v_n partials of T = Phi.LiT:  vpart[2 nb + half][n] = sum over 32 columns of T[n, .]^2
+// v_n partials of T = Phi.LiT:  vpart[2 nb + half][n] = sum over the TNW / 2 columns of that half of T[n, .]^2
 //   A: row digits of Phi (scale sA), B: row digits of Li with per-row scales liscale
-//   grid = (nblocks of 64 Li rows, row blocks of 128); deepest reduction (last nb) first
+//   tiles = (blocks of TNW Li rows, row blocks of 128); deepest reduction (last nb) first
 // ------------------------------------------------------------------------------------
-template <int KS>
+template <int KS, int TNW = TN>
 __global__ void __maxnreg__(umma::MAX_REGS)
 k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int row0, int rows,
            int K, int ntiles, const double* __restrict__ liscale, double sA, double* __restrict__ vpart,
@@ -440,10 +440,10 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   // The B operand has K + 1 rows: rows 0..K-1 are Li, row K is alpha, so column K of the product is
   // mu_n = Phi_n . alpha (SCFGP.py:111) and never enters the sum of squares.
   extern __shared__ uint8_t smem_raw[];
-  umma::Pipe p = umma::pipe_init<KS>(smem_raw);
+  umma::Pipe p = umma::pipe_init<KS, TNW>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
   const bool front = (threadIdx.x >> 5) < umma::EPI_WARP0;
-  const int nnb = (K + 1 + TN - 1) / TN;
+  const int nnb = (K + 1 + TNW - 1) / TNW;
   int it0 = 0, seq = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
     // Column-block major, deepest reduction first: tile k goes to CTA k mod gridDim, so every round of
@@ -454,23 +454,23 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     umma::Tile t;
     const int rb0 = (tile % nrb) * TM;   // chunk-local first row of the tile
     t.m0 = row0 + rb0;
-    t.n0 = nb * TN;
+    t.n0 = nb * TNW;
     t.c_begin = 0;
-    t.c_end = min(K, t.n0 + TN);  // Li is lower triangular
+    t.c_end = min(K, t.n0 + TNW);  // Li is lower triangular
     if (front) {
-      umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapLi, t, it0, seq);
+      umma::run_mainloop<KS, false, TNW>(p, tmem_base, &mapA, &mapLi, t, it0, seq);
       it0 += umma::tile_stages(t);
       continue;
     }
-    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, seq & 1);
+    const umma::EpiPos e = umma::epilogue_wait<TNW>(p, tmem_base, seq & 1);
     const double sc = sA * umma::PROD_SCALE;
     const int r = rb0 + e.row;
     double sq = 0;
 #pragma unroll 1
-    for (int h16 = 0; h16 < 2; ++h16) {
+    for (int h16 = 0; h16 < TNW / 32; ++h16) {
       double v[16];
-      umma::epilogue_load16<KS>(e, e.col0 + 16 * h16, v);
-      if (h16 == 1) umma::epilogue_release(p);
+      umma::epilogue_load16<KS, TNW>(e, e.col0 + 16 * h16, v);
+      if (h16 == TNW / 32 - 1) umma::epilogue_release(p);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int j = t.n0 + e.col0 + 16 * h16 + c;
@@ -479,18 +479,18 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         else sq = fma(tv, tv, sq);
       }
     }
-    if (r < rows) vpart[(long long)(2 * nb + (e.col0 >> 5)) * ldv + r] = sq * sc * sc;
+    if (r < rows) vpart[(long long)(2 * nb + (e.col0 ? 1 : 0)) * ldv + r] = sq * sc * sc;
   }
-  umma::pipe_teardown<KS>(p, tmem_base);
+  umma::pipe_teardown<KS, TNW>(p, tmem_base);
 }
 
 // ------------------------------------------------------------------------------------
-// backward tile: 128 rows x 32 features (64 permuted columns: cos/sin interleaved)
+// backward tile: 128 rows x TNW / 2 features (TNW permuted columns: cos/sin interleaved)
 //   Phibar = sA 2^-14 cscale[j] * sum_c [Phi|Psi'] digits . Cmat digits  + y pbarT + gmu alphaT
 //   Zbar = -Phibar_c * Phi_s + Phibar_s * Phi_c ;  slots[cta] += <Phibar, Phi>
-//   grid = (feature blocks of 32, row blocks of 128)
+//   tiles = (feature blocks of TNW / 2, row blocks of 128)
 // ------------------------------------------------------------------------------------
-template <int KS>
+template <int KS, int TNW = TN>
 __global__ void __maxnreg__(umma::MAX_REGS)
 k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
               const __grid_constant__ CUtensorMap mapC, int seg1_stages, int row0, const int8_t* __restrict__ dphi,
@@ -502,17 +502,18 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   // dphi_part[row block][f] += column sums of the tile's Zbar (dphi = colsum(Zbar), A.5)
   extern __shared__ uint8_t smem_raw[];
   __shared__ double sh[8];
-  __shared__ double shcol[8][16];
-  umma::Pipe p = umma::pipe_init<KS>(smem_raw);
+  __shared__ double shcol[8][TNW / 4];   // per epilogue warp: column sums of its TNW / 4 features
+  umma::Pipe p = umma::pipe_init<KS, TNW>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool front = warp < umma::EPI_WARP0;
-  const int nfb = (J + 31) / 32;
+  constexpr int FPT = TNW / 2;             // features per tile (cos/sin column pairs)
+  const int nfb = (J + FPT - 1) / FPT;
   int it0 = 0, seq = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
     umma::Tile t;
     t.m0 = (tile / nfb) * TM;     // row-block major: consecutive tiles share the A operand in L2
-    t.n0 = (tile % nfb) * TN;
+    t.n0 = (tile % nfb) * TNW;
     t.c_begin = 0;
     t.c_end = depth2;
     // digit cache: the Phi half of [Phi | Psi'] (the first seg1_stages stages) comes from the cache
@@ -521,11 +522,11 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     t.seg1_stages = seg1_stages;
     t.seg1_row_off = row0;
     if (front) {
-      umma::run_mainloop<KS>(p, tmem_base, &mapA, &mapC, t, it0, seq);
+      umma::run_mainloop<KS, false, TNW>(p, tmem_base, &mapA, &mapC, t, it0, seq);
       it0 += umma::tile_stages(t);
       continue;
     }
-    const umma::EpiPos e = umma::epilogue_wait(p, tmem_base, seq & 1);
+    const umma::EpiPos e = umma::epilogue_wait<TNW>(p, tmem_base, seq & 1);
     const int r = t.m0 + e.row;
     const bool rvalid = r < rows;
     const double sc = sA * umma::PROD_SCALE;
@@ -534,11 +535,11 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     double sacc = 0;
     asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");   // sh[], shcol[] of the previous tile consumed
 #pragma unroll 1
-    for (int h16 = 0; h16 < 2; ++h16) {
+    for (int h16 = 0; h16 < TNW / 32; ++h16) {
       double v[16];
       const int pcol = e.col0 + 16 * h16;                 // permuted tile column of v[0]
-      umma::epilogue_load16<KS>(e, pcol, v);
-      if (h16 == 1) umma::epilogue_release(p);
+      umma::epilogue_load16<KS, TNW>(e, pcol, v);
+      if (h16 == TNW / 32 - 1) umma::epilogue_release(p);
       double zb[8];
       const int f0 = (t.n0 + pcol) >> 1;
       // Phi of this row's 8 features (cos and sin halves).  With the digit cache they are rebuilt from
@@ -605,17 +606,19 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         slots[tile] += sum;
       }
       // warps w and w+4 hold column halves 0 / 1; their 4 lane quarters are the 4 row groups
-      const int half = lane >> 4, k = lane & 15;          // 32 features of the tile: half*16 + k
-      const int f = (t.n0 >> 1) + half * 16 + k;
-      if (f < J) {
-        double cs = 0;
+      for (int fi = lane; fi < FPT; fi += 32) {           // features of the tile: half * (FPT / 2) + k
+        const int half = fi / (FPT / 2), k = fi % (FPT / 2);
+        const int f = (t.n0 >> 1) + fi;
+        if (f < J) {
+          double cs = 0;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) cs += shcol[half * 4 + qd][k];   // the 4 row quarters, fixed order
-        dphi_part[(long long)(tile / nfb) * ldpart + f] += cs;
+          for (int qd = 0; qd < 4; ++qd) cs += shcol[half * 4 + qd][k];   // the 4 row quarters, fixed order
+          dphi_part[(long long)(tile / nfb) * ldpart + f] += cs;
+        }
       }
     }
   }
-  umma::pipe_teardown<KS>(p, tmem_base);
+  umma::pipe_teardown<KS, TNW>(p, tmem_base);
 }
 
 // generic C[m][n] = sum_c A[m,c] B[n,c] with per-row scales on both sides (self-test hook)

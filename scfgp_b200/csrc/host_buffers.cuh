@@ -93,6 +93,17 @@ int emu_check_depths(scfgp_handle* h) {
 }
 
 // (re)allocate everything that depends on the chunk size R / number of streams
+// 96-column tiles for the two K-major products (Phi.LiT, backward): 20 % fewer operand bytes per digit product (the
+// kernels are bound by operand delivery, profiles/r1_umma_stream_and_load_ceilings.txt); tensor memory holds at most
+// 5 digits x 96 columns.  SCFGP_TILE_N=64|96 overrides the default.
+inline void select_tile_width(scfgp_handle* h) {
+  h->tnw = 64;
+  if (h->prec == SCFGP_PREC_EMU_I8 && h->ks2 <= 5) {
+    h->tnw = kWideTile;
+    if (const char* e = getenv("SCFGP_TILE_N")) h->tnw = atoi(e) == 96 ? 96 : 64;
+  }
+}
+
 int alloc_chunk_buffers(scfgp_handle* h) {
   for (int i = 0; i < kMaxStreams; ++i) {
     Ctx& c = h->ctx[i];
@@ -132,7 +143,8 @@ int alloc_chunk_buffers(scfgp_handle* h) {
   if ((rc = upload_items(h, bw, &h->bwd))) return rc;
   const bool emu_on = h->prec == SCFGP_PREC_EMU_I8;
   const int emu_bwd_ctas = emu_on ? nrb * cdiv(h->J, 32) : 0;
-  h->vparts = emu_on ? 2 * cdiv(K + 1, umma::TN) : nkb;
+  select_tile_width(h);
+  h->vparts = emu_on ? 2 * cdiv(K + 1, h->tnw) : nkb;
   h->slot_stride =
       (std::max<long long>(std::max(std::max(2 * kSeedBlocks, (int)bw.size()), emu_bwd_ctas), 256) + 1) / 2 * 2;
   const size_t KK = (size_t)K * h->ldk, DJ = (size_t)h->D * h->ldj;
@@ -203,6 +215,7 @@ void free_emu_static(scfgp_handle* h) {
 int alloc_emu_static(scfgp_handle* h) {
   free_emu_static(h);
   if (h->prec != SCFGP_PREC_EMU_I8) return SCFGP_OK;
+  select_tile_width(h);
   const int K = h->K, ks = h->ks2;
   const long long Kp = h->Kp;
   int rc;
@@ -212,8 +225,8 @@ int alloc_emu_static(scfgp_handle* h) {
     if ((rc = dalloc(h, p, K + 1))) return rc;
   if ((rc = dalloc(h, &h->sigg, 2))) return rc;
   if ((rc = dalloc(h, &h->gvmax, 1))) return rc;
-  if ((rc = make_tmap_digits(h, &h->mapLiB, h->digLi, K, K + 1, Kp, ks, umma::TN))) return rc;
-  if ((rc = make_tmap_digits(h, &h->mapCB, h->digC, Kp + K, K, 2 * Kp, ks, umma::TN))) return rc;
+  if ((rc = make_tmap_digits(h, &h->mapLiB, h->digLi, K, K + 1, Kp, ks, h->tnw))) return rc;
+  if ((rc = make_tmap_digits(h, &h->mapCB, h->digC, Kp + K, K, 2 * Kp, ks, h->tnw))) return rc;
   // Gram tiles (128 x 64) of the lower triangle.  When the last 128-row block holds at most 64 valid rows
   // (K = 2080: 32), it is computed with the roles swapped -- 17 tiles (all feature blocks x the border's
   // 64-wide block) instead of 33 three-quarters-empty ones -- and stored transposed (item.z = 1); at

@@ -89,33 +89,45 @@ int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows, long long r0, boo
   return gemm_leave(h, c);
 }
 
+// launch `kern<KS, 64>` or, with wide tiles (h->tnw == 96, at most 5 digits), `kern<KS, 96>`
+#define EMU_TILE_LAUNCH(kern, grid, ...)                                                                           \
+  do {                                                                                                             \
+    if (h->tnw == 96) {                                                                                            \
+      switch (h->ks2) {                                                                                            \
+        case 4: emu::kern<4, 96><<<grid, umma::THREADS, umma::Geo<4, 96>::SMEM, c.sg>>>(__VA_ARGS__); break;       \
+        case 5: emu::kern<5, 96><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(__VA_ARGS__); break;       \
+        default: h->err = "wide tiles need at most 5 digits"; return SCFGP_ERR_ARG;                                \
+      }                                                                                                            \
+    } else {                                                                                                       \
+      EMU_KS_SWITCH(h->ks2, emu::kern<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(__VA_ARGS__));       \
+    }                                                                                                              \
+  } while (0)
+
 int emu_tgemm(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
-  const int ntiles = cdiv(h->K + 1, umma::TN) * cdiv(rows, umma::TM);
+  const int ntiles = cdiv(h->K + 1, h->tnw) * cdiv(rows, umma::TM);
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
-  EMU_KS_SWITCH(h->ks2, emu::k_tgemm_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           use_cache ? h->mapCacheK : c.mapRowsA, h->mapLiB, use_cache ? (int)r0 : 0, rows, h->K, ntiles,
-                           h->liscale, h->s2, c.vpart, h->R, c.mu));
+  EMU_TILE_LAUNCH(k_tgemm_i8, std::min(ntiles, h->num_sms), use_cache ? h->mapCacheK : c.mapRowsA, h->mapLiB,
+                  use_cache ? (int)r0 : 0, rows, h->K, ntiles, h->liscale, h->s2, c.vpart, h->R, c.mu);
   prof_end(h, SCFGP_FAM_TGEMM, c.sg);
   CKL();
   return gemm_leave(h, c);
 }
 
 int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
-  const int ntiles = cdiv(h->J, 32) * cdiv(rows, umma::TM);
+  const int ntiles = cdiv(h->J, h->tnw / 2) * cdiv(rows, umma::TM);
   // the epilogue rebuilds Phi from the cached digits (8-byte loads: needs J % 8 == 0), else reads the slab
   const bool phi_from_digits = use_cache && h->J % 8 == 0;
   const double recon = h->s2 * std::ldexp(1.0, -(8 * std::max(h->cache_ks, 1) - 1));
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
-  EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS><<<std::min(ntiles, h->num_sms), umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(
-                           c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA, h->mapCB,
-                           use_cache ? (int)(h->Kp / umma::KB) : 0, use_cache ? (int)r0 : 0,
-                           phi_from_digits ? h->phi_cache : nullptr, h->Kc, h->cache_rows * h->Kc, recon, rows, h->J,
-                           (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0,
-                           h->pbar, h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K));
+  EMU_TILE_LAUNCH(k_backward_i8, std::min(ntiles, h->num_sms), c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA,
+                  h->mapCB, use_cache ? (int)(h->Kp / umma::KB) : 0, use_cache ? (int)r0 : 0,
+                  phi_from_digits ? h->phi_cache : nullptr, h->Kc, h->cache_rows * h->Kc, recon, rows, h->J,
+                  (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0, h->pbar,
+                  h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K);
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
   return gemm_leave(h, c);

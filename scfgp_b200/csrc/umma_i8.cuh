@@ -34,8 +34,12 @@
 namespace scfgp {
 namespace umma {
 
+#ifndef UMMA_TN
+#define UMMA_TN 64       // 96 (experimental, tools/umma_probe.cu "tn"): 20 % fewer operand bytes per product, <= 5 digits
+#endif
 constexpr int TM = 128;  // tile rows  (M of the instruction, TMEM lanes)
-constexpr int TN = 64;   // tile columns per class
+constexpr int TN = UMMA_TN;   // tile columns per class (default of the TNW template parameters below)
+static_assert(TN % 32 == 0 && TN >= 64 && TN <= 128, "tile columns");
 constexpr int KB = 64;   // contraction bytes per pipeline stage (one 64-byte swizzle atom)
 constexpr int DIGIT_BITS = 8;
 constexpr double PROD_SCALE = 1.0 / 16384.0;  // 2^-14: product of the two leading-digit weights 2^-7
@@ -44,10 +48,13 @@ constexpr int EPI_WARP0 = 2;
 constexpr int EPI_THREADS = 256;
 constexpr int MAX_REGS = 96;  // per thread: 320 x 96 leaves more than half of the register file to co-resident kernels
 
-template <int KS>
+// TNW: tile columns per class.  64: four B digits per instruction (N = 256), every digit count; 96: two B digits
+// per instruction (N = 192), 20 % fewer operand bytes per digit product, at most 5 digits (480 class columns).
+template <int KS, int TNW = TN>
 struct Geo {
+  static constexpr int MAXCNT = 256 / TNW;  // B digits one instruction may span (N = TNW * cnt <= 256)
   static constexpr int A_BYTES = KS * TM * KB;
-  static constexpr int B_BYTES = KS * TN * KB;
+  static constexpr int B_BYTES = KS * TNW * KB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (224 * 1024) / STAGE_BYTES;
 #ifndef UMMA_A_TMEM
@@ -60,10 +67,12 @@ struct Geo {
 #define UMMA_MAX_STAGES 4
 #endif
   static constexpr int STAGES = STAGES_RAW > UMMA_MAX_STAGES ? UMMA_MAX_STAGES : STAGES_RAW;
-  static constexpr int CLASS_COLS = KS * TN;
+  static constexpr int CLASS_COLS = KS * TNW;
   static constexpr int TMEM_COLS = (CLASS_COLS <= 256 && !UMMA_A_TMEM) ? 256 : 512;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(KS >= 2 && KS <= 8, "2..8 digits");
+  static_assert(CLASS_COLS <= 512, "all classes must fit tensor memory");
+  static_assert(TNW % 32 == 0 && TNW >= 64 && TNW <= 128, "tile columns");
   static_assert(STAGES >= 2, "need a double buffer");
 };
 
@@ -234,9 +243,9 @@ struct Pipe {
   uint32_t* tmem_slot;
 };
 
-template <int KS>
+template <int KS, int TNW = TN>
 __device__ __forceinline__ Pipe pipe_init(uint8_t* smem_raw) {
-  using G = Geo<KS>;
+  using G = Geo<KS, TNW>;
   Pipe p;
   const uint32_t off = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   p.stages = smem_raw + off;
@@ -261,13 +270,13 @@ __device__ __forceinline__ Pipe pipe_init(uint8_t* smem_raw) {
   return p;
 }
 
-template <int KS>
+template <int KS, int TNW = TN>
 __device__ __forceinline__ void pipe_teardown(const Pipe& p, uint32_t tmem_base) {
   tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Geo<KS>::TMEM_COLS);
+    tmem_dealloc(tmem_base, Geo<KS, TNW>::TMEM_COLS);
   }
 }
 
@@ -289,10 +298,12 @@ __device__ __forceinline__ int tile_stages(const Tile& t) { return (t.c_end - t.
 // TR = false: K-major operands (tensor maps (contraction, row, digit), tile rows m0 / n0);
 // TR = true : MN-major operands (tensor maps (M-or-N index, contraction row, digit)): m0 / n0 are
 //             coordinates of dimension 0, the contraction range [c_begin, c_end) of dimension 1.
-template <int KS, bool TR = false>
+template <int KS, bool TR = false, int TNW = TN>
 __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, const CUtensorMap* mapA,
                                              const CUtensorMap* mapB, const Tile& t, int it0, int seq = 0) {
-  using G = Geo<KS>;
+  using G = Geo<KS, TNW>;
+  constexpr int MAXCNT = G::MAXCNT;
+  static_assert(!TR || TNW == 64, "MN-major B boxes are 64 bytes wide");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (t.c_end - t.c_begin + KB - 1) / KB;
   if (warp == 0) {
@@ -334,7 +345,7 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         const uint32_t sb = sa + G::A_BYTES;
 #if UMMA_A_TMEM
         // A digits staged into tensor memory behind the class accumulators (double-buffered per stage)
-        const uint32_t abuf = tmem_base + (uint32_t)(TN * KS + (it & 1) * (KS * 16));
+        const uint32_t abuf = tmem_base + (uint32_t)(TNW * KS + (it & 1) * (KS * 16));
         if (!TR) {
 #pragma unroll
           for (int ks = 0; ks < KB / 32; ++ks)
@@ -349,7 +360,7 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
           // probe: the same number of output columns, but as uniform N = 256 (mode 3) or N = 64 (mode 4)
           // instructions -- separates the per-instruction overhead from the shared-memory read volume
           {
-            constexpr int COLS = TN * KS * (KS + 1) / 2;
+            constexpr int COLS = TNW * KS * (KS + 1) / 2;
             constexpr int NI = UMMA_PROBE_MODE == 3 ? 256 : 64;
 #pragma unroll
             for (int m = 0; m < (COLS + NI - 1) / NI; ++m) {
@@ -366,31 +377,31 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
             const uint64_t adesc = TR ? smem_desc_mn(sa + i * (TM * KB) + ks * 32 * TM, 0, 8 * TM, 2 /*SWIZZLE_128B*/)
                                       : smem_desc_sw64(sa + i * (TM * KB) + ks * 32);
 #pragma unroll
-            for (int j0 = 0; j0 < KS - i; j0 += 4) {
-              const int cnt = (KS - i - j0) < 4 ? (KS - i - j0) : 4;
+            for (int j0 = 0; j0 < KS - i; j0 += MAXCNT) {
+              const int cnt = (KS - i - j0) < MAXCNT ? (KS - i - j0) : MAXCNT;
               const uint64_t bdesc =
-                  TR ? smem_desc_mn(sb + j0 * (TN * KB) + ks * 32 * TN, TN * KB, 8 * TN, 4 /*SWIZZLE_64B*/)
-                     : smem_desc_sw64(sb + j0 * (TN * KB) + ks * 32);
+                  TR ? smem_desc_mn(sb + j0 * (TNW * KB) + ks * 32 * TNW, TNW * KB, 8 * TNW, 4 /*SWIZZLE_64B*/)
+                     : smem_desc_sw64(sb + j0 * (TNW * KB) + ks * 32);
               const uint32_t acc = (kb == 0 && ks == 0 && i == 0) ? 0u : 1u;
 #if UMMA_PROBE_MODE != 1
 #if UMMA_A_TMEM
               if (!TR)
-                mma_i8_ts(tmem_base + (uint32_t)(TN * (i + j0)), abuf + (uint32_t)((ks * KS + i) * 8), bdesc,
-                          idesc_i8(TN * cnt), acc);
+                mma_i8_ts(tmem_base + (uint32_t)(TNW * (i + j0)), abuf + (uint32_t)((ks * KS + i) * 8), bdesc,
+                          idesc_i8(TNW * cnt), acc);
               else
 #endif
 #if UMMA_COLLECTOR
               if (KS - i > 4) {   // two instructions share this A slice
                 if (j0 == 0)
-                  mma_i8_coll<1>(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
-                                 TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
+                  mma_i8_coll<1>(tmem_base + (uint32_t)(TNW * (i + j0)), adesc, bdesc,
+                                 TR ? idesc_i8_mn(TNW * cnt) : idesc_i8(TNW * cnt), acc);
                 else
-                  mma_i8_coll<2>(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
-                                 TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
+                  mma_i8_coll<2>(tmem_base + (uint32_t)(TNW * (i + j0)), adesc, bdesc,
+                                 TR ? idesc_i8_mn(TNW * cnt) : idesc_i8(TNW * cnt), acc);
               } else
 #endif
-              mma_i8(tmem_base + (uint32_t)(TN * (i + j0)), adesc, bdesc,
-                     TR ? idesc_i8_mn(TN * cnt) : idesc_i8(TN * cnt), acc);
+              mma_i8(tmem_base + (uint32_t)(TNW * (i + j0)), adesc, bdesc,
+                     TR ? idesc_i8_mn(TNW * cnt) : idesc_i8(TNW * cnt), acc);
 #else
               (void)adesc; (void)bdesc; (void)acc;
 #endif
@@ -422,16 +433,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // share the SM with a resident tensor-core CTA).
 struct EpiPos {
   int row;    // tile row of this thread (0..127)
-  int col0;   // first of its 32 tile columns (0 or 32)
+  int col0;   // first of its TN / 2 tile columns (0 or TN / 2)
   uint32_t lane_base;  // TMEM address of lane quarter, column 0
 };
+template <int TNW = TN>
 __device__ __forceinline__ EpiPos epilogue_wait(const Pipe& p, uint32_t tmem_base, uint32_t acc_parity) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
-  const int half = (warp - EPI_WARP0) >> 2;  // which 32 of the 64 columns
+  const int half = (warp - EPI_WARP0) >> 2;  // which half of the TN columns
   EpiPos e;
   e.row = quarter * 32 + lane;
-  e.col0 = half * 32;
+  e.col0 = half * (TNW / 2);
   e.lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
   mbar_wait_long(p.acc_full, acc_parity);
   tc_fence_after();
@@ -444,14 +456,14 @@ __device__ __forceinline__ void epilogue_release(const Pipe& p) {
   if ((threadIdx.x & 31) == 0) mbar_arrive(p.acc_empty);
 }
 // v[c] = sum_q 2^(-8q) acc_q[row][col + c], c < 16   (col = tile column, multiple of 16)
-template <int KS>
+template <int KS, int TNW = TN>
 __device__ __forceinline__ void epilogue_load16(const EpiPos& e, int col, double (&v)[16]) {
 #pragma unroll
   for (int c = 0; c < 16; ++c) v[c] = 0.0;
 #pragma unroll
   for (int q = KS - 1; q >= 0; --q) {  // least significant class first
     uint32_t r[16];
-    tmem_ld16(e.lane_base + (uint32_t)(q * TN + col), r);
+    tmem_ld16(e.lane_base + (uint32_t)(q * TNW + col), r);
     const double w = __longlong_as_double((long long)(1023 - DIGIT_BITS * q) << 52);  // 2^(-8q)
 #pragma unroll
     for (int c = 0; c < 16; ++c) v[c] = fma((double)(int)r[c], w, v[c]);

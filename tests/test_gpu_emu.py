@@ -377,6 +377,33 @@ def test_digit_cache_on_and_off_agree(monkeypatch):
     assert rel(a[1], b[1]) <= 1e-7
 
 
+@pytest.mark.parametrize("shape", [(3000, 13, 5, 50), (2500, 8, 4, 100), (1500, 64, 16, 120), (900, 1, 100, 50)])
+def test_tile_widths_agree(monkeypatch, shape):
+    """The two K-major products run on 128 x 96 tiles by default (at most 5 digits) and on 128 x 64 tiles with
+    SCFGP_TILE_N=64: the same exact integer sums; only float64 partial sums over tile halves are grouped differently."""
+    N, D, S, M = shape
+    X, y, h = synth.make_problem(N, D, S, M, seed=N + 1)
+    Xs = np.random.default_rng(3).random((200, D))
+    res = {}
+    for width in ("96", "64"):
+        monkeypatch.setenv("SCFGP_TILE_N", width)
+        eng = Engine(D, S, M, precision="emu5")
+        eng.set_data(X, y)
+        c, g, al, Li = eng.eval(h)
+        mu, sd = eng.predict(h, Xs)
+        res[width] = (c, g, al, Li, mu, sd)
+        eng.close()
+    a, b = res["96"], res["64"]
+    np.testing.assert_array_equal(a[2], b[2])              # pass 1 does not depend on the tile width: same alpha, Li
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[4], b[4])              # mu = Phi.alpha: one exact digit sum per row
+    assert abs(a[0] - b[0]) <= 1e-14 * abs(b[0])           # row sums of T^2 are grouped by tile half
+    np.testing.assert_allclose(a[5], b[5], rtol=1e-13)
+    assert rel(a[1], b[1]) <= 1e-12
+    c0, g0, al0, Li0 = O.streaming_eval(h, X, y, S, M)
+    assert abs(a[0] - c0) <= 1e-7 * abs(c0) and rel(a[1], g0) <= 1e-6
+
+
 @pytest.mark.parametrize("prec,amp,gtol", [("emu5", 30.0, 1e-5), ("emu6", 1000.0, 1e-6)])
 def test_outliers_in_y(prec, amp, gtol):
     """Outlier rows stretch the range of the per-row seeds gv (one power-of-two scale per chunk /

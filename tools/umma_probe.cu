@@ -79,7 +79,7 @@ k_probe(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
   } else {
     const EpiPos e = epilogue_wait(p, tmem_base, 0);
     const int gr = t.m0 + e.row;
-    for (int h16 = 0; h16 < 2; ++h16) {
+    for (int h16 = 0; h16 < TN / 32; ++h16) {
       double v[16];
       epilogue_load16<KS>(e, e.col0 + 16 * h16, v);
       if (gr < M)
@@ -89,15 +89,16 @@ k_probe(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
         }
     }
     if (raw) {
-      for (int q = 0; q < KS; ++q) {
-        uint32_t r[32];
-        tmem_ld32(e.lane_base + (uint32_t)(q * TN + e.col0), r);  // warp-collective
-        if (gr < M)
-          for (int c = 0; c < 32; ++c) {
-            const int gc = t.n0 + e.col0 + c;
-            if (gc < Nn) raw[((size_t)q * M + gr) * Nn + gc] = (int)r[c];
-          }
-      }
+      for (int q = 0; q < KS; ++q)
+        for (int h16 = 0; h16 < TN / 32; ++h16) {
+          uint32_t r[16];
+          tmem_ld16(e.lane_base + (uint32_t)(q * TN + e.col0 + 16 * h16), r);  // warp-collective
+          if (gr < M)
+            for (int c = 0; c < 16; ++c) {
+              const int gc = t.n0 + e.col0 + 16 * h16 + c;
+              if (gc < Nn) raw[((size_t)q * M + gr) * Nn + gc] = (int)r[c];
+            }
+        }
     }
   }
   pipe_teardown<KS>(p, tmem_base);
@@ -261,12 +262,27 @@ static int run_case_mn(int M, int Nn, int depth, int c_begin, int c_end, bool ve
 
 int main(int argc, char** argv) {
   setvbuf(stdout, nullptr, _IOLBF, 0);
+#if UMMA_TN == 64
   if (argc > 1 && !strcmp(argv[1], "sustain")) {
     // seconds-long back-to-back launches: the rate under the power cap (compare with "perf" = burst)
     run_case<5>(8192, 2080, 4160, 0, 4160, false, 20);
     run_case<5>(8192, 2080, 4160, 0, 4160, false, 3000);
     run_case<6>(8192, 2080, 4160, 0, 4160, false, 2000);
     return 0;
+  }
+#endif
+  if (argc > 1 && !strcmp(argv[1], "tn")) {
+    // tile-width experiment (build with -DUMMA_TN=96; at most 5 digits): exactness, burst, sustained
+    int bad = 0;
+    bad += run_case<2>(128, 96, 64, 0, 64, true, 0);
+    bad += run_case<4>(256, 100, 512, 0, 512, true, 0);
+    bad += run_case<5>(300, 200, 520, 64, 520, true, 0);
+    bad += run_case<5>(256, 192, 1000, 128, 960, true, 0);
+    printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
+    run_case<5>(8192, 2080, 4160, 0, 4160, false, 5);
+    run_case<5>(8192, 2080, 4160, 0, 4160, false, 20);
+    run_case<5>(8192, 2080, 4160, 0, 4160, false, 2500);
+    return bad ? 1 : 0;
   }
   if (argc > 1 && !strcmp(argv[1], "ts")) {
     // A-in-tensor-memory experiment (build with -DUMMA_A_TMEM=1; at most 5 digits): exactness, burst, sustained
@@ -282,6 +298,10 @@ int main(int argc, char** argv) {
     run_case<4>(8192, 2080, 4160, 0, 4160, false, 20);
     return bad ? 1 : 0;
   }
+#if UMMA_TN != 64
+  printf("built with UMMA_TN=%d: only the \"tn\" mode is available\n", UMMA_TN);
+  return 2;
+#else
   const bool perf = argc > 1 && !strcmp(argv[1], "perf");
   int bad = 0;
   if (!perf) {
@@ -312,4 +332,5 @@ int main(int argc, char** argv) {
     run_case_mn<5>(2080, 2080, 8192, 0, 8192, false, 5);   // one chunk's full (unsymmetrised) Gram
   }
   return bad ? 1 : 0;
+#endif
 }
