@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one 8192-row k_backward_i8 launch (ncu --set full), by digits
-TRAFFIC_BACKWARD_I8 = {5: 535.4e6}   # profiles/r1_prof_backward_i8_ncu_full.txt
+TRAFFIC_BACKWARD_I8 = {5: 557.3e6}   # profiles/r1_prof_backward_i8_ncu_full.txt
 
 WORKLOAD = dict(name="cfg4: synthetic N=10M, D=64, rank=16, feature_size=1024", N=10_000_000, D=64, S=16, M=1024)
 
@@ -387,8 +387,9 @@ def main():
             "traffic": TRAFFIC_BACKWARD_I8.get(digits),
             "traffic_note": "dram__bytes_read+write of one 8192-row k_backward_i8 launch from ncu --set full "
                             "(profiles/r1_prof_backward_i8_ncu_full.txt); algorithmic operand bytes per launch: "
-                            "A digits rows*2K*digits (170 MB) + C digits K*2K*digits (44 MB) + Phi slab read (136 MB) "
-                            "+ Zbar write (68 MB) = 418 MB; the rest is A-operand re-reads that miss L2 (hit rate 86 %)",
+                            "A digits rows*2K*digits (170 MB) + C digits K*2K*digits (44 MB) + Phi digits re-read by the "
+                            "epilogue (85 MB) + Zbar write (68 MB) = 367 MB; the rest is A-operand re-reads that miss L2 "
+                            "(hit rate 87 %)",
             "how": f"int8 digit-product operations of pass 3 (4 N K^2 x {nprod} digit products) / pass-3 device time "
                    "(CUDA events on the launching stream) averaged over the timed steps; the pass includes the feature "
                    "map, digit extraction and dW kernels, so the GEMM kernel alone is faster than this",
@@ -401,6 +402,11 @@ def main():
                             if peaks else "fallback 2 x 1.4 PFLOP/s sustained bf16 (MEASURED_PEAKS.json absent)"),
             "fp64_equivalent_tflops_pass3": achieved_f64,
             "fp64_equivalent_vs_dgemm_peak": achieved_f64 / dgemm_peak,
+            # not measured in this run: what the tensor pipe sustains on this very instruction mix when nothing
+            # else happens (no operand traffic, no epilogue), 148 SMs for a second, random int8 operands
+            "int8_mma_stream_only": {"sustained_tops": 3655.0, "burst_tops": 4233.0,
+                                     "frac_of_it": achieved / 3655.0,
+                                     "source": "profiles/r1_umma_stream_and_load_ceilings.txt (tools/umma_pair_probe.cu)"},
         })
     else:
         roofline = dict(common, **{
