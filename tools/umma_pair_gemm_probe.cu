@@ -1,4 +1,4 @@
-// CTA-pair version of the digit-product mainloop (first item) as a stand-alone probe:
+// CTA-pair version of the digit-product mainloop ("what bounds it") as a stand-alone probe:
 // tcgen05.mma.cta_group::2.kind::i8 (M = 256 over the two CTAs of a cluster), 96-column tiles, all classes resident in
 // tensor memory, B operand SPLIT over the pair:
 //   * an instruction over two B digits (N = 192): CTA 0 holds digit j (96 rows), CTA 1 digit j + 1, at the same offset;
