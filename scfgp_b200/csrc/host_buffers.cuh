@@ -95,10 +95,10 @@ int emu_check_depths(scfgp_handle* h) {
 // (re)allocate everything that depends on the chunk size R / number of streams
 // 96-column tiles for the two K-major products (Phi.LiT, backward): 20 % fewer operand bytes per digit product (the
 // kernels are bound by operand delivery, profiles/r1_umma_stream_and_load_ceilings.txt); tensor memory holds at most
-// 5 digits x 96 columns.  SCFGP_TILE_N=64|96 overrides the default.
+// 5 digits x 96 columns, and the wide tile is built and tested for exactly 5.  SCFGP_TILE_N=64|96 overrides the default.
 inline void select_tile_width(scfgp_handle* h) {
   h->tnw = 64;
-  if (h->prec == SCFGP_PREC_EMU_I8 && h->ks2 <= 5) {
+  if (h->prec == SCFGP_PREC_EMU_I8 && h->ks2 == 5) {   // the default digit count (6+ digits do not fit tensor memory)
     h->tnw = kWideTile;
     if (const char* e = getenv("SCFGP_TILE_N")) h->tnw = atoi(e) == 96 ? 96 : 64;
   }

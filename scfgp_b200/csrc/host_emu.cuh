@@ -89,14 +89,13 @@ int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows, long long r0, boo
   return gemm_leave(h, c);
 }
 
-// launch `kern<KS, 64>` or, with wide tiles (h->tnw == 96, at most 5 digits), `kern<KS, 96>`
+// launch `kern<KS, 64>` or, with wide tiles (h->tnw == 96: 5 digits), `kern<5, 96>`
 #define EMU_TILE_LAUNCH(kern, grid, ...)                                                                           \
   do {                                                                                                             \
     if (h->tnw == 96) {                                                                                            \
       switch (h->ks2) {                                                                                            \
-        case 4: emu::kern<4, 96><<<grid, umma::THREADS, umma::Geo<4, 96>::SMEM, c.sg>>>(__VA_ARGS__); break;       \
         case 5: emu::kern<5, 96><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(__VA_ARGS__); break;       \
-        default: h->err = "wide tiles need at most 5 digits"; return SCFGP_ERR_ARG;                                \
+        default: h->err = "wide tiles are built for 5 digits"; return SCFGP_ERR_ARG;                               \
       }                                                                                                            \
     } else {                                                                                                       \
       EMU_KS_SWITCH(h->ks2, emu::kern<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(__VA_ARGS__));       \

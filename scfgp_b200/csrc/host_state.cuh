@@ -8,7 +8,7 @@ constexpr double kEps = 1e-6;  // jitter, SCFGP/SCFGP.py:93
 constexpr int kColSplit = 64;  // row splits of the column-sum kernels (parallelism: ceil(K/256) x 64 CTAs)
 constexpr int kSeedBlocks = 296;
 constexpr int kGramSplit = 1;  // row splits of one chunk's Gram tiles in the emulated mode (work items = tiles x splits)
-constexpr int kWideTile = 96;  // default tile width of Phi.LiT / backward in the emulated mode with <= 5 digits (64 otherwise)
+constexpr int kWideTile = 96;  // default tile width of Phi.LiT / backward in the emulated mode with 5 digits (64 otherwise)
 constexpr int kDwSplit = 16;   // row splits of the dW = XT.Zbar contraction (partial buffers per chunk stream)
 
 struct ItemList {
@@ -107,7 +107,7 @@ struct scfgp_handle {
   int4* gram_items = nullptr;
   int gram_count = 0;
   int vparts = 0;              // partial rows of vpart per chunk
-  int tnw = 64;                // tile width of the K-major digit products (Phi.LiT, backward): 64, or 96 (<= 5 digits)
+  int tnw = 64;                // tile width of the K-major digit products (Phi.LiT, backward): 64, or 96 (5 digits)
   int gsplit = 1;              // partial Gram accumulators per chunk stream (kGramSplit in the emulated mode)
   int csplit = kColSplit;      // partial rows of the column-sum buffers per chunk stream (>= R/128)
 

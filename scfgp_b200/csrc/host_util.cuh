@@ -254,7 +254,7 @@ int set_emu_attrs(scfgp_handle* h) {
   CK(cudaFuncSetAttribute(emu::k_digits_rows<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CK(cudaFuncSetAttribute((emu::k_digits_slab<KS, false>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CK(cudaFuncSetAttribute((emu::k_digits_slab<KS, true>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-  if constexpr (KS <= 5) {   // wide (96-column) tiles of the two K-major products
+  if constexpr (KS == 5) {   // wide (96-column) tiles of the two K-major products
     const int smw = (int)umma::Geo<KS, 96>::SMEM;
     CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
     CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
