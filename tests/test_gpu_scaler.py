@@ -11,6 +11,8 @@ from scfgp_b200.scaler import _boxcox
 pytestmark = pytest.mark.gpu
 
 ALGOS = ["min-max", "normal", "inv-normal", "auto-normal", "auto-inv-normal"]
+LAMBDA_ATOL = 2e-3   # Box-Cox exponent: SLSQP with ftol 1e-8 on a flat objective, see DESIGN.md row f3
+XFORM_ATOL = 2e-3
 
 
 def make_table(n=6000, seed=0):
@@ -216,3 +218,46 @@ def test_shard_level_sums_and_distinct_values():
     assert lib.scfgp_scaler_column_distinct_values(0, C.c_void_p(t.data_ptr()), t.numel(), 9, C.byref(nd),
                                                    _lib.dptr(vals)) == _lib.OK
     assert nd.value == 10
+
+
+# ------------------------------------------------------------------ against the reference's own Scaler
+REF_FIXTURES = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)),
+                                          "golden", "reference_scaler_fixtures.npz")
+
+
+@pytest.fixture(scope="module")
+def ref_fx():
+    with np.load(REF_FIXTURES, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("table", ["mixed", "target", "wide"])
+def test_gpu_scaler_against_reference_scaler_outputs(ref_fx, table, algo):
+    """GpuScaler vs outputs of /root/reference/SCFGP/Scaler.py itself (fit state and transforms;
+    fixtures from tests/golden/make_reference_scaler_fixtures.py)."""
+    key = f"{table}_{algo}"
+    Xfit, Xnew = ref_fx[f"{table}_Xfit"], ref_fx[f"{table}_Xnew"]
+    gpu = GpuScaler(algo)
+    gpu.fit(Xfit)
+    assert list(gpu.data["cols"]) == list(ref_fx[key + "_cols"])
+    for k in ("min", "max"):
+        if f"{key}_{k}" in ref_fx:
+            np.testing.assert_array_equal(gpu.data[k], ref_fx[f"{key}_{k}"])
+    if algo.startswith("auto"):
+        np.testing.assert_allclose(gpu.data["boxcox"], ref_fx[key + "_boxcox"], rtol=0, atol=LAMBDA_ATOL)
+        np.testing.assert_allclose(gpu.data["mu"], ref_fx[key + "_mu"], rtol=0, atol=5 * LAMBDA_ATOL)
+        np.testing.assert_allclose(gpu.data["std"], ref_fx[key + "_std"], rtol=0, atol=5 * LAMBDA_ATOL)
+        tol = XFORM_ATOL
+    else:
+        for k in ("mu", "std"):
+            if f"{key}_{k}" in ref_fx:
+                np.testing.assert_allclose(gpu.data[k], ref_fx[f"{key}_{k}"], rtol=1e-12, atol=1e-14)
+        tol = 1e-11
+    np.testing.assert_allclose(gpu.forward_transform(Xfit), ref_fx[key + "_fwd_fit"], rtol=0, atol=tol)
+    np.testing.assert_allclose(gpu.forward_transform(Xnew), ref_fx[key + "_fwd_new"], rtol=0, atol=tol)
+    # with the reference's fitted state the transform kernel reproduces the reference elementwise
+    state = {"algo": algo, "cols": ref_fx[key + "_cols"].tolist()}
+    state.update({k: ref_fx[f"{key}_{k}"] for k in ("min", "max", "mu", "std", "boxcox") if f"{key}_{k}" in ref_fx})
+    same = GpuScaler.from_state_dict(state)
+    np.testing.assert_allclose(same.forward_transform(Xnew), ref_fx[key + "_fwd_new"], rtol=1e-12, atol=1e-13)
