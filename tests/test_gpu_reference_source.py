@@ -1,0 +1,82 @@
+"""The CUDA path against outputs of the reference's own sources (SCFGP.py, Optimizer.py, Scaler.py run
+on oracle/theano_shim.py; fixtures tests/golden/reference_source_fixtures.npz): kernels and facade vs
+reference-produced numbers, no oracle in the loop.  Tolerances: north_star's (cost 1e-6 relative;
+gradient, alpha / Li, predictions 1e-5)."""
+import os
+
+import numpy as np
+import pytest
+
+from scfgp_b200 import Engine, SCFGP
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = os.path.join(HERE, "golden", "reference_source_fixtures.npz")
+SHAPES = ["boston", "kin8nm", "abalone", "co2"]
+METRICS = ["SCORE", "COST", "MAE", "NMAE", "MSE", "NMSE", "MNLP"]
+
+
+@pytest.fixture(scope="module")
+def fx():
+    with np.load(FIXTURES, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def blocks(D, S, M):
+    P = 3 + D * S + M * S + S + M
+    return {"abc": slice(0, 3), "l_f": slice(3, 3 + D * S), "r_f": slice(3 + D * S, 3 + D * S + M * S),
+            "phase": slice(3 + D * S + M * S, P)}
+
+
+@pytest.mark.parametrize("precision", ["fp64", "emu5"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_eval_and_predict_match_reference_source(fx, shape, precision):
+    k = f"eval_{shape}_"
+    S, M = (int(v) for v in fx[k + "SM"])
+    X, y, h = fx[k + "X"], fx[k + "y"].ravel(), fx[k + "params"]
+    D = X.shape[1]
+    eng = Engine(D, S, M, device=0, precision=precision)
+    try:
+        eng.set_data(X, y)
+        cost, grad, alpha, Li = eng.eval(h)
+        mu, std = eng.predict(h, fx[k + "Xs"], fx[k + "alpha"], fx[k + "Li"])
+    finally:
+        eng.close()
+    ref = float(fx[k + "cost"])
+    assert abs(cost - ref) <= 1e-6 * abs(ref)
+    g0 = fx[k + "grad"]
+    for name, sl in blocks(D, S, M).items():
+        if name == "phase":                                   # analytically zero
+            assert np.abs(grad[sl] - g0[sl]).max() <= 1e-5
+        else:
+            assert np.linalg.norm(grad[sl] - g0[sl]) <= 1e-5 * np.linalg.norm(g0[sl]), name
+    assert np.abs(alpha - fx[k + "alpha"]).max() <= 1e-5 * max(1, np.abs(fx[k + "alpha"]).max())
+    assert np.abs(Li - fx[k + "Li"]).max() <= 1e-5 * max(1, np.abs(fx[k + "Li"]).max())
+    assert np.abs(mu - fx[k + "mu"]).max() <= 1e-5 and np.abs(std - fx[k + "std"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp64", "emu5"])
+@pytest.mark.parametrize("tag", ["fit_boston", "minibatch"])
+def test_facade_fit_on_gpu_reproduces_reference_run(fx, tag, precision):
+    """The reference's public API end to end (set_data -> optimize -> predict, SCFGP.py:153-294), same
+    seed, same table: every metric history of the reference run, the final alpha and the predictions."""
+    k = tag + "_"
+    S, M = (int(v) for v in fx[k + "SM"])
+    opt = {s.split("=")[0]: int(s.split("=")[1]) for s in fx[k + "opt"]}
+    np.random.seed(int(fx[k + "seed"]))
+    m = SCFGP(sparsity=S, nfeats=M, precision=precision)
+    m.set_data(fx[k + "Xtr"], fx[k + "ytr"])
+    np.testing.assert_array_equal(m.params, fx[k + "params0"])
+    m.optimize(fx[k + "Xva"], fx[k + "yva"], **opt)
+    for metric in METRICS:
+        ours, ref = np.array(m.evals[metric][1], dtype=float), fx[k + "evals_" + metric]
+        assert ours.shape == ref.shape, metric
+        np.testing.assert_allclose(ours, ref, rtol=1e-5, atol=1e-7, err_msg=metric)
+    np.testing.assert_allclose(np.array(m.evals["COST"][1], dtype=float), fx[k + "evals_COST"], rtol=1e-6)
+    nph = m.params.size - (S + M)
+    assert np.abs(m.params[:nph] - fx[k + "params_final"][:nph]).max() <= 1e-5
+    assert np.abs(m.alpha - fx[k + "alpha"]).max() <= 1e-4 * max(1, np.abs(fx[k + "alpha"]).max())
+    mu_y, std_y = m.predict(fx[k + "Xva"])
+    np.testing.assert_allclose(mu_y, fx[k + "mu_y"], rtol=1e-5)
+    np.testing.assert_allclose(std_y, fx[k + "std_y"], rtol=1e-5)

@@ -1,0 +1,160 @@
+"""Pins against outputs of the reference's own, unmodified sources (SCFGP.py, Optimizer.py, Scaler.py)
+executed on ``oracle/theano_shim.py`` -- fixtures ``tests/golden/reference_source_fixtures.npz`` from
+``tests/golden/make_reference_source_fixtures.py``.  On CPU: the oracle (a3-a10, a12), the host update
+rules (f1) and the facade's loop / metrics / minibatch logic (f1, f2, f5; evaluation through an
+oracle-backed test double, exactly as tests/test_facade_cpu.py does).  The CUDA path is checked against
+the same file in tests/test_gpu_reference_source.py."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import scfgp_oracle as O
+from scfgp_b200 import SCFGP
+from scfgp_b200.optimizer import Optimizer as OPT
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = os.path.join(HERE, "golden", "reference_source_fixtures.npz")
+REFERENCE = "/root/reference/SCFGP/SCFGP.py"
+SHAPES = ["boston", "kin8nm", "abalone", "co2"]
+ALGOS = ["sgd", "adagrad", "adadelta", "adam", "adamax"]
+METRICS = ["SCORE", "COST", "MAE", "NMAE", "MSE", "NMSE", "MNLP"]
+
+
+@pytest.fixture(scope="module")
+def fx():
+    with np.load(FIXTURES, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def kwargs_of(arr):
+    return {s.split("=")[0]: float(s.split("=")[1]) for s in arr}
+
+
+class OracleEngine:
+    """Test double for scfgp_b200.Engine (CPU only; the product never uses it)."""
+
+    def __init__(self, D, S, M):
+        self.D, self.S, self.M = D, S, M
+
+    def set_data(self, X, y, n_global=None):
+        self.X, self.y = X, np.asarray(y).reshape(-1)
+
+    def eval(self, h, want_grad=True, **_):
+        return O.streaming_eval(h, self.X, self.y, self.S, self.M, want_grad=want_grad)
+
+    def predict(self, h, Xs, a, L):
+        return O.literal_predict(h, Xs, a, L, self.S, self.M)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_oracle_matches_reference_source_eval(fx, shape):
+    """cost, TT.grad, alpha, Li, pred_func of the reference source at the cfg1-3 geometries."""
+    k = f"eval_{shape}_"
+    S, M = (int(v) for v in fx[k + "SM"])
+    X, y, h = fx[k + "X"], fx[k + "y"], fx[k + "params"]
+    cost, grad, alpha, Li = O.streaming_eval(h, X, y.ravel(), S, M, chunk=501)
+    ref = float(fx[k + "cost"])
+    assert abs(cost - ref) <= 1e-11 * abs(ref)
+    assert np.linalg.norm(grad - fx[k + "grad"]) <= 1e-9 * np.linalg.norm(fx[k + "grad"])
+    assert np.abs(alpha - fx[k + "alpha"]).max() <= 1e-9 * max(1, np.abs(alpha).max())
+    assert np.abs(Li - fx[k + "Li"]).max() <= 1e-10 * max(1, np.abs(Li).max())
+    c2, g2, _, _ = O.literal_cost_grad(h, X, y, S, M, threads=2)
+    assert abs(c2 - ref) <= 1e-12 * abs(ref)
+    assert np.linalg.norm(g2 - fx[k + "grad"]) <= 1e-9 * np.linalg.norm(g2)
+    mu, std = O.literal_predict(h, fx[k + "Xs"], fx[k + "alpha"], fx[k + "Li"], S, M)
+    assert mu.shape == fx[k + "mu"].shape and std.shape == fx[k + "std"].shape
+    assert np.abs(mu - fx[k + "mu"]).max() <= 1e-11 and np.abs(std - fx[k + "std"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_update_rules_follow_reference_trajectories(fx, algo):
+    """f1: six train_iter_func steps of the reference (update rule + Nesterov wrapper acting on
+    ``list(updates.keys())[0]``, Optimizer.py:62-97) vs scfgp_b200.optimizer driven by oracle gradients."""
+    S, M = (int(v) for v in fx["algo_SM"])
+    X, y, h = fx["algo_X"], fx["algo_y"].ravel(), fx["algo_params0"].copy()
+    rule = OPT.build(algo, kwargs_of(fx[f"algo_{algo}_kw"]), nesterov=0.9)
+    for step in range(6):
+        cost, grad, _, _ = O.streaming_eval(h, X, y, S, M)
+        assert abs(cost - fx[f"algo_{algo}_cost"][step]) <= 1e-9 * max(1, abs(cost))
+        h = rule.step(h, grad)
+        # The last S+M entries (phases) have an analytically zero gradient (finding 2):
+        # what reaches the rule there is round-off (~1e-13), which adam / adamax / adadelta normalise
+        # into steps of 1e-8 ... 1e-6.  Cost and predictions do not depend on them.
+        ref, nph = fx[f"algo_{algo}_traj"][step], h.size - (S + M)
+        assert np.abs(h[:nph] - ref[:nph]).max() <= 1e-9, (algo, step)
+        assert np.abs(h[nph:] - ref[nph:]).max() <= 1e-4, (algo, step)
+
+
+def test_rmsprop_is_broken_in_the_reference(fx):
+    assert str(fx["algo_rmsprop_raises"]).startswith("NameError")
+
+
+@pytest.mark.parametrize("tag", ["fit_boston", "minibatch"])
+def test_facade_fit_reproduces_reference_run(fx, tag):
+    """set_data (scalers, RNG draw order of ID + init_params), optimize (loop, metric bookkeeping,
+    minibatch shuffles), predict (un-scaling, std_y) -- SCFGP.py:153-294 -- against the reference run."""
+    k = tag + "_"
+    S, M = (int(v) for v in fx[k + "SM"])
+    opt = {s.split("=")[0]: int(s.split("=")[1]) for s in fx[k + "opt"]}
+    np.random.seed(int(fx[k + "seed"]))
+    m = SCFGP(sparsity=S, nfeats=M)
+    m.set_data(fx[k + "Xtr"], fx[k + "ytr"])
+    assert m.ID == str(fx[k + "ID"])
+    np.testing.assert_array_equal(m.X, fx[k + "X_scaled"])
+    np.testing.assert_array_equal(m.y, fx[k + "y_scaled"])
+    np.testing.assert_array_equal(m.params, fx[k + "params0"])
+    m._engine = OracleEngine(m.D, m.S, m.M)
+    m.optimize(fx[k + "Xva"], fx[k + "yva"], **opt)
+    for metric in METRICS:
+        ours, ref = np.array(m.evals[metric][1], dtype=float), fx[k + "evals_" + metric]
+        assert ours.shape == ref.shape, metric
+        np.testing.assert_allclose(ours, ref, rtol=2e-7, atol=1e-9, err_msg=metric)
+    nph = m.params.size - (S + M)                       # phases: round-off driven, see the rule test
+    assert np.abs(m.params[:nph] - fx[k + "params_final"][:nph]).max() <= 1e-7
+    assert np.abs(m.params[nph:] - fx[k + "params_final"][nph:]).max() <= 1e-5
+    assert np.abs(m.alpha - fx[k + "alpha"]).max() <= 1e-6 * max(1, np.abs(fx[k + "alpha"]).max())
+    mu_y, std_y = m.predict(fx[k + "Xva"])
+    np.testing.assert_allclose(mu_y, fx[k + "mu_y"], rtol=1e-7)
+    np.testing.assert_allclose(std_y, fx[k + "std_y"], rtol=1e-7)
+
+
+# --------------------------------------------------------------------------------------
+# live (build container): the shim backend against Theano's own compiled graph
+# --------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.exists(REFERENCE), reason="/root/reference not present")
+def test_shim_run_matches_pickled_theano_graph():
+    """The reference source executed on the torch shim returns what the pickled, Theano-compiled
+    train_func / pred_func return on the same inputs (geometry of the checkpoint: D=13, S=20, M=50)."""
+    from oracle import theano_shim
+    from oracle.theano_graph import ReferenceFunctions
+    pkg = theano_shim.import_reference()
+    R = ReferenceFunctions()
+    rng = np.random.default_rng(17)
+    X, y = rng.random((300, 13)), rng.standard_normal((300, 1))
+    np.random.seed(0)
+    m = pkg.SCFGP(sparsity=20, nfeats=50)
+    m.X, m.y = X, y
+    m.N, m.D = X.shape
+    m.init_params()
+    m.build_theano_models("adam", {"learning_rate": 0.01})
+    for h in (R.trained_params, m.params.get_value()):
+        m.params.set_value(h)
+        cost, alpha, Li = m.train_func(X, y)
+        c2, a2, L2 = R.train_func(X, y, h)
+        assert abs(float(cost) - c2) <= 1e-12 * abs(c2)
+        assert np.abs(alpha - a2).max() <= 1e-9 * max(1, np.abs(a2).max())
+        assert np.abs(Li - L2).max() <= 1e-10 * max(1, np.abs(L2).max())
+        Xs = rng.random((20, 13))
+        mu, std = m.pred_func(Xs, alpha, Li)
+        mu2, std2 = R.pred_func(Xs, alpha, Li, h)
+        assert np.abs(mu - mu2).max() <= 1e-11 and np.abs(std - std2).max() <= 1e-12
+    # the shim's autograd gradient vs central differences of the Theano graph's cost
+    h = R.trained_params
+    m.params.set_value(h)
+    m.build_theano_models("sgd", {"learning_rate": 1e-3})
+    m.train_iter_func(X, y)
+    grad = (h - m.train_func.givens[0][1].get_value()) / 1.9e-3
+    idx = [0, 1, 2, 40, 700, 1300]
+    fd = R.cost_gradient_fd(X, y, h, index=idx)
+    assert np.abs(grad[idx] - fd).max() <= 2e-7 * max(1, np.abs(fd).max())
