@@ -158,6 +158,17 @@ int scfgp_eval_pass3(scfgp_handle* h);     /* dW, dphi, sbar                    
 int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha, double* Li);
 /* Device pointer + element count (doubles) of the contiguous buffer a phase reduces. */
 int scfgp_reduce_buffer(scfgp_handle* h, int which, void** dptr, long long* count);
+/* Stream-ordered hand-off between the handle's stream and the stream the caller runs its collective on
+ * (no host synchronisation).  SCFGP_HANDOFF_TO_OTHER: `other_stream` waits for everything this handle has
+ * queued so far (call it after a pass, before the all-reduce).  SCFGP_HANDOFF_FROM_OTHER: the handle's
+ * stream waits for everything queued on `other_stream` so far (call it after the all-reduce). */
+enum { SCFGP_HANDOFF_TO_OTHER = 0, SCFGP_HANDOFF_FROM_OTHER = 1 };
+int scfgp_stream_handoff(scfgp_handle* h, void* other_stream, int direction);
+/* After scfgp_eval_factor: start copying alpha (K) / Li (K x K) to the host destinations on the copy stream
+ * while passes 2 and 3 run; scfgp_eval_finish with the same pointers then only waits for that copy.  Only
+ * page-locked destinations are filled early (a pageable copy would block the calling thread); others are
+ * left to scfgp_eval_finish.  Either pointer may be NULL.  scfgp_eval does this itself. */
+int scfgp_eval_prefetch_factors(scfgp_handle* h, double* alpha, double* Li);
 
 /* Device-resident results of the last evaluation (valid until the next one). */
 int scfgp_device_factors(scfgp_handle* h, void** d_alpha, void** d_Li, long long* ld_Li);

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "scfgp_eval_pass3": (C.c_int, [_h]),
     "scfgp_eval_finish": (C.c_int, [_h, _dp, _dp, _dp, _dp]),
     "scfgp_reduce_buffer": (C.c_int, [_h, C.c_int, C.POINTER(C.c_void_p), C.POINTER(_ll)]),
+    "scfgp_stream_handoff": (C.c_int, [_h, C.c_void_p, C.c_int]),
+    "scfgp_eval_prefetch_factors": (C.c_int, [_h, _dp, _dp]),
     "scfgp_device_factors": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(_ll)]),
     "scfgp_launch_count": (_ll, [_h]),
     "scfgp_last_pass_ms": (C.c_int, [_h, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -128,6 +128,10 @@ struct scfgp_handle {
   long long launches = 0;
   cudaEvent_t ev[8] = {};
   float ms_pass[4] = {0, 0, 0, 0};
+  // stream hand-off with a caller's stream (NCCL all-reduce between phases) and the early copy-out of
+  // alpha / Li on the copy stream while passes 2 and 3 run
+  cudaEvent_t ev_out = nullptr, ev_in = nullptr, ev_factor = nullptr;
+  double *pre_alpha = nullptr, *pre_Li = nullptr;   // host destinations already being filled
 
   // optional launch trace (CUDA event pair around every streaming-kernel launch)
   struct TraceRec { const char* name; int lane; cudaEvent_t e0, e1; };

@@ -196,11 +196,14 @@ int launch_gemm(scfgp_handle* h, const double* A, long long lda, int a_rows, con
   if (items.count == 0) return SCFGP_OK;
   if (!use_st) st = h->stream;
   constexpr size_t smem = SmemSize<Cfg, AK, BKM>::BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // cudaFuncSetAttribute applies to the current device only: one flag per device ordinal, so a
+  // second engine on another GPU of the same process also gets the > 48 KB opt-in
+  static std::atomic<unsigned long long> attr_done_mask{0};
+  const int dev = h->device;
+  if (dev < 0 || dev >= 64 || !((attr_done_mask.load() >> dev) & 1ull)) {
     CK(cudaFuncSetAttribute(k_gemm<Cfg, AK, BKM, AVEC, BVEC>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done_mask.fetch_or(1ull << dev);
   }
   k_gemm<Cfg, AK, BKM, AVEC, BVEC><<<items.count, Cfg::NT, smem, st>>>(
       A, lda, a_rows, B, ldb, b_rows, C, ldc, alpha, beta, items.d, depth_arg);

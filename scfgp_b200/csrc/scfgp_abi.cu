@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 #include <functional>
+#include <atomic>
 
 #include <cuda_runtime.h>
 
@@ -96,6 +97,9 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
     CK(cudaEventCreateWithFlags(&h->ctx[i].ev_gs, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_factor, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
   if ((rc = dalloc(h, &h->trslots, K))) return rc;
   if ((rc = dalloc(h, &h->info, 1))) return rc;
@@ -132,6 +136,53 @@ long long scfgp_launch_count(const scfgp_handle* h) { return h ? h->launches : 0
 int scfgp_set_stream(scfgp_handle* h, void* cuda_stream) {
   if (!h) return SCFGP_ERR_ARG;
   h->stream = (cudaStream_t)cuda_stream;
+  return SCFGP_OK;
+}
+
+int scfgp_stream_handoff(scfgp_handle* h, void* other_stream, int direction) {
+  if (!h || (direction != SCFGP_HANDOFF_TO_OTHER && direction != SCFGP_HANDOFF_FROM_OTHER)) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t other = (cudaStream_t)other_stream;
+  if (other == h->stream) return SCFGP_OK;   // same queue: already ordered
+  if (direction == SCFGP_HANDOFF_TO_OTHER) {
+    CK(cudaEventRecord(h->ev_out, h->stream));
+    CK(cudaStreamWaitEvent(other, h->ev_out, 0));
+  } else {
+    CK(cudaEventRecord(h->ev_in, other));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
+  }
+  return SCFGP_OK;
+}
+
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int scfgp_eval_prefetch_factors(scfgp_handle* h, double* alpha, double* Li) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (!h->have_factors) { h->err = "prefetch_factors before factor"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  h->pre_alpha = h->pre_Li = nullptr;
+  // A device -> pageable-host cudaMemcpyAsync blocks the calling thread until the copy is done, which
+  // would keep the host from queueing pass 2; only page-locked destinations are filled early.
+  const bool a_ok = alpha && is_pinned_host(alpha), l_ok = Li && is_pinned_host(Li);
+  if (!a_ok && !l_ok) return SCFGP_OK;
+  const int K = h->K;
+  CK(cudaStreamWaitEvent(h->cstream, h->ev_factor, 0));
+  if (a_ok) {
+    CK(cudaMemcpyAsync(alpha, h->alpha, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, h->cstream));
+    h->pre_alpha = alpha;
+  }
+  if (l_ok) {
+    if (h->ldk == K)
+      CK(cudaMemcpyAsync(Li, h->Li, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToHost, h->cstream));
+    else
+      CK(cudaMemcpy2DAsync(Li, (size_t)K * sizeof(double), h->Li, h->ldk * sizeof(double), (size_t)K * sizeof(double),
+                           K, cudaMemcpyDeviceToHost, h->cstream));
+    h->pre_Li = Li;
+  }
   return SCFGP_OK;
 }
 
@@ -275,6 +326,7 @@ int scfgp_eval_begin(scfgp_handle* h, const double* params, int want_grad) {
   h->want_grad = want_grad;
   h->have_factors = false;
   h->pivot = -1;
+  h->pre_alpha = h->pre_Li = nullptr;
   int rcc;
   if ((rcc = ensure_phi_cache(h))) return rcc;
   return unpack_and_upload(h, params);
@@ -378,6 +430,7 @@ int scfgp_eval_factor(scfgp_handle* h) {
   long long info = 0;
   CK(cudaMemcpyAsync(&info, h->info, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev[7], h->stream));
+  CK(cudaEventRecord(h->ev_factor, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (info != 0) {
     h->pivot = info - 1;
@@ -611,10 +664,19 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
     g3.resize((size_t)D * h->ldj + h->ldj + 1);
     CK(cudaMemcpyAsync(g3.data(), h->red3, g3.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
-  if (alpha) CK(cudaMemcpyAsync(alpha, h->alpha, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (Li) CK(cudaMemcpy2DAsync(Li, (size_t)K * sizeof(double), h->Li, h->ldk * sizeof(double),
-                               (size_t)K * sizeof(double), K, cudaMemcpyDeviceToHost, h->stream));
+  // (alpha / Li may already be on their way on the copy stream: scfgp_eval_prefetch_factors)
+  if (alpha && alpha != h->pre_alpha)
+    CK(cudaMemcpyAsync(alpha, h->alpha, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (Li && Li != h->pre_Li) {
+    if (h->ldk == K)
+      CK(cudaMemcpyAsync(Li, h->Li, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else
+      CK(cudaMemcpy2DAsync(Li, (size_t)K * sizeof(double), h->Li, h->ldk * sizeof(double),
+                           (size_t)K * sizeof(double), K, cudaMemcpyDeviceToHost, h->stream));
+  }
   CK(cudaStreamSynchronize(h->stream));
+  if (h->pre_alpha || h->pre_Li) CK(cudaStreamSynchronize(h->cstream));
+  h->pre_alpha = h->pre_Li = nullptr;
   prof_collect(h);
   for (int i = 0; i < 3; ++i) {
     float ms = 0;
@@ -680,6 +742,7 @@ int scfgp_eval(scfgp_handle* h, const double* params, double* cost, double* grad
   if ((rc = scfgp_eval_begin(h, params, grad != nullptr))) return rc;
   if ((rc = scfgp_eval_pass1(h))) return rc;
   if ((rc = scfgp_eval_factor(h))) return rc;
+  if ((rc = scfgp_eval_prefetch_factors(h, alpha, Li))) return rc;
   if ((rc = scfgp_eval_pass2(h))) return rc;
   if (grad) {
     if ((rc = scfgp_eval_backward(h))) return rc;

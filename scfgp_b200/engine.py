@@ -222,15 +222,21 @@ class Engine:
 
             class _Api:
                 def pass1(s): eng._check(lib.scfgp_eval_pass1(h))
-                def factor(s): eng._check(lib.scfgp_eval_factor(h))
+                def factor(s):
+                    eng._check(lib.scfgp_eval_factor(h))
+                    eng._check(lib.scfgp_eval_prefetch_factors(h, ap, lp))   # alpha / Li leave during passes 2-3
                 def pass2(s): eng._check(lib.scfgp_eval_pass2(h))
                 def backward(s): eng._check(lib.scfgp_eval_backward(h))
                 def pass3(s): eng._check(lib.scfgp_eval_pass3(h))
                 def reduce_buffer(s, which): return eng._reduce_tensor(which)
 
             def _allreduce(buf):
+                # stream-ordered, no host synchronisation: torch's current stream (which NCCL orders its
+                # own stream against) waits for the pass, the handle's stream waits for the reduction
+                ts = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+                eng._check(lib.scfgp_stream_handoff(h, ts, 0))
                 dist.all_reduce(buf, group=group)
-                torch.cuda.current_stream().synchronize()
+                eng._check(lib.scfgp_stream_handoff(h, ts, 1))
 
             self._check(lib.scfgp_eval_begin(h, _lib.dptr(params), int(want_grad)))
             run_eval_phases(_Api(), _allreduce, want_grad)

@@ -97,7 +97,8 @@ class SCFGP(object):
         self.train_func = self.train_iter_func = self.pred_func = None
         self._engine = None
         self._engine_data_id = None
-        self._rule = None
+        self._engine_data_held = None
+        self._rule, self._rule_cfg, self._rule_resumed = None, None, False
         self.min_obj_ind = 0
         self.generate_ID()
 
@@ -163,12 +164,31 @@ class SCFGP(object):
         td.broadcast(t, src=0)
         self.params = t.cpu().numpy().copy()
 
+    @staticmethod
+    def _fingerprint(a):
+        """Cheap content fingerprint of a training array: address, layout and a strided sample of the
+        values (host arrays) or the in-place version counter (CUDA tensors)."""
+        if hasattr(a, "data_ptr"):
+            return ("t", a.data_ptr(), tuple(a.shape), tuple(a.stride()), a._version)
+        a = np.asarray(a)
+        flat = a.reshape(-1)
+        sample = flat[::max(1, flat.size // 509)]
+        edge = (flat[:64].tobytes(), flat[-64:].tobytes())
+        return ("n", a.__array_interface__["data"][0], a.shape, a.strides, sample.tobytes(), edge)
+
     def _upload(self, X, y):
         """Hand the (scaled) training set to the engine.  Under ``torch.distributed`` every rank holds the
         same X, y and uploads only its own contiguous row shard (``shard_bounds``); the evaluation then
-        all-reduces the three partial reductions."""
-        key = (id(X), id(y), tuple(X.shape))
-        if self._engine_data_id != key:
+        all-reduces the three partial reductions.
+
+        The reference's Theano functions evaluate whatever arrays they are passed (SCFGP.py:132-137).  The
+        device copy is reused only while the SAME array objects (held here, so their ids cannot be
+        recycled) still carry the same fingerprint; anything else is uploaded again.
+        ``invalidate_data()`` forces the next call to upload."""
+        key = (self._fingerprint(X), self._fingerprint(y))
+        held = self._engine_data_held
+        if held is None or held[0] is not X or held[1] is not y or self._engine_data_id != key:
+            held_new = (X, y)
             rank, world = self._ranks()
             n = int(X.shape[0])
             if world > 1 and self.presharded:
@@ -181,12 +201,22 @@ class SCFGP(object):
             else:
                 self._engine.set_data(np.ascontiguousarray(X), np.ascontiguousarray(y), n_global=n)
             self._engine_data_id = key
+            self._engine_data_held = held_new
+
+    def invalidate_data(self):
+        """Forget the device copy of the training set: the next train_func / train_iter_func call uploads."""
+        self._engine_data_id = None
+        self._engine_data_held = None
 
     def build_models(self, algo='adam', algo_params=None, engine=None):
         """Counterpart of ``build_theano_models`` (SCFGP.py:92-148): binds the three callables."""
         eng = self._ensure_engine(engine)
-        self._engine_data_id = None
-        self._rule = OPT.build(algo, algo_params, nesterov=0.9)
+        self.invalidate_data()
+        cfg = (algo, dict(algo_params or {}))
+        if getattr(self, "_rule_resumed", False) and self._rule_cfg == cfg:
+            self._rule_resumed = False          # checkpointed slots / step counter carry on (load())
+        else:
+            self._rule, self._rule_cfg = OPT.build(algo, algo_params, nesterov=0.9), cfg
 
         def train_func(X, y):
             self._upload(X, y)
@@ -401,10 +431,15 @@ class SCFGP(object):
 
     # ------------------------------------------------------------------ checkpoint (SCFGP.py:296-310)
     def save(self, path):
-        """``.npz`` checkpoint: unlike the reference's pickle it also stores S, D and the optimiser
-        slots and does not contain compiled functions."""
-        out = dict(ID=self.ID, M=self.M, S=self.S, D=self.D, fftype=self.fftype, params=self.params,
-                   alpha=self.alpha, Li=self.Li)
+        """``.npz`` checkpoint: unlike the reference's pickle (SCFGP.py:296-302) it also stores S, D, the
+        update rule (name, settings, slots, step counter) and the scaler kind, and it contains no compiled
+        functions.  Fields that do not exist yet (alpha / Li before the first evaluation) are left out."""
+        out = dict(ID=self.ID, M=self.M, S=self.S, D=self.D, fftype=self.fftype,
+                   scaler_device='gpu' if hasattr(self.X_scaler, "device") else 'cpu')
+        for k in ("params", "alpha", "Li"):
+            v = getattr(self, k)
+            if v is not None:
+                out[k] = np.asarray(v.cpu().numpy() if self._is_cuda_tensor(v) else v, dtype=np.float64)
         for k, v in self.X_scaler.state_dict().items():
             out["xs_" + k] = v
         for k, v in self.y_scaler.state_dict().items():
@@ -412,6 +447,9 @@ class SCFGP(object):
         for k, v in self.evals.items():
             out["evals_" + k] = np.asarray(v[1], dtype=np.float64)
         if self._rule is not None:
+            out["optcfg_algo"] = self._rule_cfg[0]
+            for k, v in (self._rule_cfg[1] or {}).items():
+                out["optkw_" + k] = float(v)
             for k, v in self._rule.state_dict().items():
                 out["opt_" + k] = v
         with open(path, "wb") as f:
@@ -424,14 +462,28 @@ class SCFGP(object):
         self.M, self.S, self.D = int(d["M"]), int(d["S"]), int(d["D"])
         self.S_requested = self.S
         self.fftype = int(d.get("fftype", _lib.FF_PHASE))
-        self.params, self.alpha, self.Li = d["params"], d["alpha"], d["Li"]
-        self.X_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("xs_")})
-        self.y_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("ys_")})
+        self.params, self.alpha, self.Li = d.get("params"), d.get("alpha"), d.get("Li")
+        scaler_cls = Scaler
+        if str(d.get("scaler_device", "cpu")) == "gpu":
+            from .gpu_scaler import GpuScaler
+            scaler_cls = GpuScaler
+        self.X_scaler = scaler_cls.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("xs_")})
+        self.y_scaler = scaler_cls.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("ys_")})
         for k in self.evals:
             if "evals_" + k in d:
                 self.evals[k][1] = list(d["evals_" + k])
         self._engine = None
+        self.invalidate_data()
         self.train_func = self.train_iter_func = self.pred_func = None
+        # the update rule resumes where it stopped: build_models() picks this up instead of a fresh rule
+        self._rule, self._rule_cfg, self._rule_resumed = None, None, False
+        if "optcfg_algo" in d:
+            algo = str(d["optcfg_algo"])
+            kw = {k[6:]: float(v) for k, v in d.items() if k.startswith("optkw_")}
+            self._rule = OPT.build(algo, kw, nesterov=0.9)
+            self._rule_cfg = (algo, kw)
+            self._rule.load_state_dict({k[4:]: v for k, v in d.items() if k.startswith("opt_")})
+            self._rule_resumed = True
         self.NAME = "SCFGP (Sparsity=%d, Fourier Features=%d)" % (self.S, self.M)
         return self
 
@@ -446,6 +498,7 @@ class SCFGP(object):
         self.X_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("xs_")})
         self.y_scaler = Scaler.from_state_dict({k[3:]: v for k, v in d.items() if k.startswith("ys_")})
         self._engine = None
+        self.invalidate_data()
         self.train_func = self.train_iter_func = self.pred_func = None
         return self
 

@@ -148,11 +148,11 @@ class _Adam(_Rule):
         v = self.b2 * self._slot("v", p) + (1 - self.b2) * g ** 2
         return p - a_t * m / (np.sqrt(v) + self.eps), {"m": m, "v": v}
 
-    def state_dict(self):
-        d = super().state_dict(); d["t"] = np.array(self.t); return d
+    def state_dict(self):          # shared with _Adamax below, hence no zero-argument super()
+        d = _Rule.state_dict(self); d["t"] = np.array(self.t); return d
 
     def load_state_dict(self, d):
-        d = dict(d); self.t = float(d.pop("t", 0.0)); super().load_state_dict(d)
+        d = dict(d); self.t = float(d.pop("t", 0.0)); _Rule.load_state_dict(self, d)
 
 
 class _Adamax(_Rule):

@@ -108,3 +108,81 @@ def test_load_reference_golden(golden, tmp_path):
     mu, sd = m.predict(Xs)
     assert mu.shape == (30, 1) and np.all(np.isfinite(mu)) and np.all(sd > 0)
     assert 0 < mu.mean() < 60                            # Boston house prices (k$)
+
+
+class CountingEngine(OracleEngine):
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.uploads = 0
+
+    def set_data(self, X, y, n_global=None):
+        self.uploads += 1
+        super().set_data(np.array(X, copy=True), np.array(y, copy=True), n_global)
+
+
+def test_upload_cache_sees_in_place_updates_and_new_arrays():
+    """The compiled functions evaluate the arrays they are passed (SCFGP.py:132-137): the device copy is
+    reused only for the same, unchanged array objects."""
+    np.random.seed(5)
+    Xtr, ytr, _, _ = _data()
+    m = SCFGP(sparsity=2, nfeats=6)
+    m.set_data(Xtr, ytr)
+    m._engine = eng = CountingEngine(m.D, m.S, m.M)
+    m.build_models()
+    c0 = m.train_func(m.X, m.y)[0]
+    c1 = m.train_func(m.X, m.y)[0]
+    assert eng.uploads == 1 and c0 == c1                      # unchanged arrays: one upload
+    m.y[3, 0] += 0.5                                          # in-place edit of a training target
+    c2 = m.train_func(m.X, m.y)[0]
+    assert eng.uploads == 2 and c2 != c0
+    X2, y2 = m.X.copy(), m.y.copy()                           # equal content, new objects
+    m.train_func(X2, y2)
+    assert eng.uploads == 3
+    del X2, y2
+    X3, y3 = m.X.copy() * 0.5, m.y.copy()                     # may recycle the ids of X2 / y2
+    c3 = m.train_func(X3, y3)[0]
+    assert eng.uploads == 4 and c3 != c2
+    m.invalidate_data()
+    m.train_func(X3, y3)
+    assert eng.uploads == 5
+
+
+@pytest.mark.parametrize("algo", ["adam", "adamax", "adadelta", "sgd"])
+def test_checkpoint_resumes_the_update_rule(tmp_path, algo):
+    """save()/load() carry the optimiser slots and step counter: 4 + 4 iterations across a checkpoint
+    equal 8 uninterrupted iterations."""
+    Xtr, ytr, _, _ = _data()
+    opt = dict(algo={"algo": algo, "algo_params": {"learning_rate": 0.02}})
+
+    def fresh():
+        np.random.seed(6)
+        m = SCFGP(sparsity=2, nfeats=6)
+        m.set_data(Xtr, ytr)
+        m._engine = OracleEngine(m.D, m.S, m.M)
+        return m
+
+    ref = fresh()
+    ref.optimize(max_iter=8, **opt)
+    a = fresh()
+    a.optimize(max_iter=4, **opt)
+    path = str(tmp_path / "ckpt.npz")
+    a.save(path)
+    b = SCFGP().load(path)
+    b.set_data(Xtr, ytr)                                      # same table -> same scalers; params kept
+    np.testing.assert_array_equal(b.params, a.params)
+    b._engine = OracleEngine(b.D, b.S, b.M)
+    b.optimize(max_iter=4, **opt)
+    np.testing.assert_allclose(b.params, ref.params, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(b.evals["COST"][1][-1], ref.evals["COST"][1][-1], rtol=1e-12)
+
+
+def test_save_before_training(tmp_path):
+    np.random.seed(8)
+    Xtr, ytr, _, _ = _data()
+    m = SCFGP(sparsity=2, nfeats=6)
+    m.set_data(Xtr, ytr)
+    path = str(tmp_path / "early.npz")
+    m.save(path)                                              # alpha / Li do not exist yet
+    m2 = SCFGP().load(path)
+    assert m2.alpha is None and m2.Li is None
+    np.testing.assert_array_equal(m2.params, m.params)
