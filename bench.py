@@ -30,8 +30,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one 8192-row k_backward_i8 launch (ncu --set full), by digits
-TRAFFIC_BACKWARD_I8 = {5: 557.3e6}   # profiles/r1_prof_backward_i8_ncu_full.txt
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: read from the committed
+# summary of the ncu --set full capture (tools/ncu_traffic.py writes it from the raw CSV export)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+
+# CPU arms: a FIXED row sample of the cfg4 geometry, identical in `cpu_baseline` and `--impl reference`, at every
+# --gpus N, so that the driver's ratios are reproducible (50 000 rows: the dense K^3 work is ~5 % of an evaluation)
+CPU_SAMPLE_ROWS = 50_000
 
 WORKLOAD = dict(name="cfg4: synthetic N=10M, D=64, rank=16, feature_size=1024", N=10_000_000, D=64, S=16, M=1024)
 
@@ -141,10 +146,13 @@ def make_device_problem(n_local, D, S, M, seed, device, dist=None):
 # ---------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle's reference-shaped evaluation on host cores
 # ---------------------------------------------------------------------------------------
-def cpu_reference_run(D, S, M, steps, warmup, target_seconds=12.0):
+def cpu_reference_run(D, S, M, steps, warmup, rows=CPU_SAMPLE_ROWS, slope=True):
     """Times the literal float64 restatement of the reference's Theano graph (materialised
     Phi, Gauss-Hermite term, LAPACK Cholesky + inverse, reverse-mode gradient) with all host
-    threads on a bounded row sample of the workload.  Returns (rows/s, info dict)."""
+    threads on a FIXED row sample of the workload.  Returns (rows/s, s/eval, info dict).
+
+    ``slope``: one more evaluation at half the rows gives the per-row cost with the N-independent
+    dense K^3 work excluded (two-point fit) -- the rate the CPU path would approach at N = 1e7."""
     import torch
     from oracle import scfgp_oracle as O
     from scfgp_b200 import synth
@@ -154,12 +162,13 @@ def cpu_reference_run(D, S, M, steps, warmup, target_seconds=12.0):
     except Exception:
         pass
     torch.set_num_threads(cores)
-    # size the sample: probe at 2000 rows, then scale to ~target_seconds per step (cap by memory)
-    n_probe = 2000
-    X, y, h = synth.make_problem(n_probe, D, S, M, seed=1)
-    t0 = time.perf_counter(); O.cpu_eval_reference_shaped(h, X, y, S, M, threads=cores); t_probe = time.perf_counter() - t0
-    n = int(min(60000, max(n_probe, n_probe * target_seconds / max(t_probe, 1e-3))))
-    n = max(2000, (n // 1000) * 1000)
+    n = int(rows)
+    try:                                     # Phi and its autograd copies need ~0.2 MB per row at K = 2080
+        avail = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
+        while n > 5000 and n * 2.5e5 > 0.6 * avail:
+            n //= 2
+    except Exception:
+        pass
     X, y, h = synth.make_problem(n, D, S, M, seed=1)
     for _ in range(warmup):
         O.cpu_eval_reference_shaped(h, X, y, S, M, threads=cores)
@@ -169,11 +178,20 @@ def cpu_reference_run(D, S, M, steps, warmup, target_seconds=12.0):
         O.cpu_eval_reference_shaped(h, X, y, S, M, threads=cores)
         ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    info = {"cores": cores, "kind": "port",
-            "sample": f"{n} rows of the cfg4 geometry (D={D}, S={S}, M={M}; K={2 * (S + M)}); literal float64 "
+    info = {"cores": cores, "kind": "port", "sample_rows": n,
+            "sample": f"{n} rows (fixed) of the cfg4 geometry (D={D}, S={S}, M={M}; K={2 * (S + M)}); literal float64 "
                       f"restatement of SCFGP.py:92-129 (materialised Phi + autograd), torch-CPU {cores} threads; "
-                      f"{sec:.2f} s/eval; dense K^3 work is not amortised at this N, so rows/s at N=1e7 would be higher "
-                      f"by at most the K^3 share"}
+                      f"{sec:.2f} s/eval including the N-independent dense K^3 work"}
+    if slope and n >= 10000:
+        half = n // 2
+        t0 = time.perf_counter()
+        O.cpu_eval_reference_shaped(h, X[:half], y[:half], S, M, threads=cores)
+        sec_half = time.perf_counter() - t0
+        per_row = max((min(ts) - sec_half) / (n - half), 1e-12)
+        info["rows_per_sec_asymptotic"] = 1.0 / per_row
+        info["fixed_seconds_per_eval"] = max(min(ts) - per_row * n, 0.0)
+        info["sample"] += (f"; two-point fit with {half} rows: {per_row * 1e6:.1f} us/row + "
+                           f"{info['fixed_seconds_per_eval']:.2f} s fixed => {1.0 / per_row:.0f} rows/s as N grows")
     return n / sec, sec, info
 
 
@@ -210,6 +228,7 @@ def main():
         if rank != 0:
             return 0
         rows_s, sec, info = cpu_reference_run(D, S, M, max(1, args.steps), args.warmup)
+        config = dict(config, reference_sample_rows=info["sample_rows"])
         line = {"impl": "reference", "metric": "nlml_grad_rows_per_sec", "value": rows_s, "unit": "rows/s",
                 "evals_per_sec_at_N": rows_s / N, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -240,10 +259,14 @@ def main():
                  pinned_results=True)   # results land in page-locked host buffers owned by the engine
     eng.set_data_device(Xd, yd, n_global=N)
     emulated = eng.precision.startswith("emu")
-    digits = int(eng.precision[3:]) if emulated else 0
-    config["precision"] = (f"float64 emulated on the int8 tensor cores: {digits} base-256 digits per operand "
-                           f"({8 * digits - 2} fractional bits of each row's power-of-two scale), "
-                           f"{digits * (digits + 1) // 2} digit products, exact int32 accumulation (tcgen05.mma kind::i8); "
+    # 'emu5' or 'emu5/4' (Gram digits / digits of the other products)
+    digits_gram, _, digits_rest = eng.precision[3:].partition("/") if emulated else ("0", "", "")
+    digits_gram = int(digits_gram or 0)
+    digits = int(digits_rest or digits_gram)          # pass 3 (the roofline kernel) runs with these
+    config["precision"] = (f"float64 emulated on the int8 tensor cores: {digits_gram} base-256 digits per operand for the "
+                           f"Gram that feeds the Cholesky, {digits} for the other products "
+                           f"({8 * digits - 2} fractional bits of each row's power-of-two scale, "
+                           f"{digits * (digits + 1) // 2} digit products), exact int32 accumulation (tcgen05.mma kind::i8); "
                            "feature map, Cholesky, inverse and small dense backward in true FP64"
                            if emulated else "FP64 tensor path (DMMA.8x8x4)")
 
@@ -284,6 +307,30 @@ def main():
     ms_step = ms_total / args.steps
     rows_per_s = N / (ms_step * 1e-3)
 
+    # ---- the same evaluation without the digit cache of Phi (emulated mode keeps Phi's int8 digits of all rows
+    #      in HBM when they fit; without it passes 2 and 3 recompute the feature map): 2 timed steps
+    phi_cache = None
+    if emulated:
+        cache_bytes = eng.phi_cache_bytes
+        eng.set_phi_cache(False)
+        eng.eval(params0)
+        barrier()
+        c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(2):
+            eng.eval(params0)
+        c1.record()
+        barrier()
+        tc = torch.tensor([c0.elapsed_time(c1) / 2], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        eng.set_phi_cache(True)
+        eng.eval(params0)                                    # (re-build it for what follows)
+        phi_cache = {"bytes_per_gpu": cache_bytes, "in_use_for_value": cache_bytes > 0,
+                     "ms_per_step_without_cache": float(tc[0]), "ms_per_step_with_cache": ms_step if cache_bytes > 0 else None,
+                     "note": "digits x ceil128(rows) x ceil16(K) bytes of HBM per GPU; bounded by SCFGP_PHI_CACHE_MAX_GB "
+                             "(default 120) and free memory; declined caches are reported on stderr"}
+
     # ---- end to end through the public call with HOST buffers (train_func(X, y) semantics):
     #      pinned host X/y -> device inside the timed region, results read back to host
     e2e = None
@@ -292,7 +339,7 @@ def main():
         yh = torch.empty((n_local,), dtype=torch.float64, pin_memory=True); yh.copy_(yd)
         Xn, yn = Xh.numpy(), yh.numpy()
         eng.set_data(Xn, yn, n_global=N)
-        nrep = max(1, min(2, args.steps))
+        nrep = max(1, args.steps)                            # the same K steps as the device-timed value
         barrier()
         t0 = time.perf_counter()
         for _ in range(nrep):
@@ -381,15 +428,34 @@ def main():
         bf16_burst = peaks.get("bf16_tflops") or 1590.0
         peak_i8 = 2.0 * bf16_sus
         achieved = int8_ops_p3 / (p3_ms * 1e-3) * 1e-12
+        # measured in this run: what the tensor pipe sustains on this very instruction mix when nothing else
+        # happens (no operand traffic, no epilogue): every SM for ~0.5 s, random int8 operands (power-capped)
+        import ctypes as C
+        stream_only = None
+        tile_n = 96 if digits == 5 else 64
+        tops, clk, mhz = C.c_double(), C.c_double(), C.c_double()
+        if digits in (4, 5, 6) and eng.lib.scfgp_dbg_mma_stream_peak(
+                local_rank, digits, tile_n, 1_200_000, 1, C.byref(tops), C.byref(clk), C.byref(mhz)) == 0:
+            stream_only = {"sustained_tops": tops.value, "clk_per_k32_step": clk.value, "sm_mhz": mhz.value,
+                           "frac_of_it": achieved / tops.value,
+                           "how": f"scfgp_dbg_mma_stream_peak: the {digits}-digit / 128 x {tile_n} tile tcgen05.mma stream "
+                                  "of the product kernels without TMA traffic or epilogue, 1.2 M K=32 steps on every SM, "
+                                  "random int8 operands, measured in this run"}
+        traffic, traffic_note = None, "no ncu capture summarised in profiles/ncu_traffic.json"
+        try:
+            tj = json.load(open(TRAFFIC_FILE))
+            key = f"k_backward_i8<{digits},{tile_n}>"
+            if key in tj:
+                traffic = tj[key]["dram_bytes_per_launch"]
+                traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch of {key} "
+                                f"({tj[key]['rows']} rows) from {tj[key]['source']}; algorithmic bytes per launch "
+                                f"{tj[key].get('algorithmic_bytes')}: {tj[key].get('algorithmic_note', '')}")
+        except Exception:
+            pass
         roofline = dict(common, **{
             "bound": "tensor", "kernel": "k_backward_i8 (tcgen05.mma kind::i8, int32 accumulators in TMEM, TMA-fed)",
             "achieved": achieved, "peak": peak_i8, "unit": "TOP/s", "frac": achieved / peak_i8,
-            "traffic": TRAFFIC_BACKWARD_I8.get(digits),
-            "traffic_note": "dram__bytes_read+write of one 8192-row k_backward_i8 launch from ncu --set full "
-                            "(profiles/r1_prof_backward_i8_ncu_full.txt); algorithmic operand bytes per launch: "
-                            "A digits rows*2K*digits (170 MB) + C digits K*2K*digits (44 MB) + Phi digits re-read by the "
-                            "epilogue (85 MB) + Zbar write (68 MB) = 367 MB; the rest is A-operand re-reads that miss L2 "
-                            "(hit rate 87 %)",
+            "traffic": traffic, "traffic_note": traffic_note,
             "how": f"int8 digit-product operations of pass 3 (4 N K^2 x {nprod} digit products) / pass-3 device time "
                    "(CUDA events on the launching stream) averaged over the timed steps; the pass includes the feature "
                    "map, digit extraction and dW kernels, so the GEMM kernel alone is faster than this",
@@ -402,11 +468,8 @@ def main():
                             if peaks else "fallback 2 x 1.4 PFLOP/s sustained bf16 (MEASURED_PEAKS.json absent)"),
             "fp64_equivalent_tflops_pass3": achieved_f64,
             "fp64_equivalent_vs_dgemm_peak": achieved_f64 / dgemm_peak,
-            # not measured in this run: what the tensor pipe sustains on this very instruction mix when nothing
-            # else happens (no operand traffic, no epilogue), 148 SMs for a second, random int8 operands
-            "int8_mma_stream_only": {"sustained_tops": 3655.0, "burst_tops": 4233.0,
-                                     "frac_of_it": achieved / 3655.0,
-                                     "source": "profiles/r1_umma_stream_and_load_ceilings.txt (tools/umma_pair_probe.cu)"},
+            "int8_mma_stream_only": stream_only,
+            "frac_vs_measured_mma_stream": (achieved / stream_only["sustained_tops"]) if stream_only else None,
         })
     else:
         roofline = dict(common, **{
@@ -429,10 +492,12 @@ def main():
     if emulated and world == 1 and not args.no_fp64_compare:
         eng.set_precision("fp64")
         eng.eval(params0)
+        n64 = 3
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        c64, g64, a64, L64 = eng.eval(params0)
-        torch.cuda.synchronize(); sec64 = time.perf_counter() - t0
-        fp64_compare = {"ms_per_step": sec64 * 1e3, "rows_per_sec": N / sec64,
+        for _ in range(n64):
+            c64, g64, a64, L64 = eng.eval(params0)
+        torch.cuda.synchronize(); sec64 = (time.perf_counter() - t0) / n64
+        fp64_compare = {"ms_per_step": sec64 * 1e3, "steps": n64, "rows_per_sec": N / sec64,
                         "fp64_tflops": fpr * N / sec64 * 1e-12,
                         "speedup_of_emulated": sec64 * 1e3 / ms_step,
                         "parity_of_emulated": {
@@ -444,7 +509,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        rs, sec, info = cpu_reference_run(D, S, M, steps=1, warmup=0)
+        rs, sec, info = cpu_reference_run(D, S, M, steps=2, warmup=1)
         cpu_baseline = dict(info, value=rs, unit="rows/s")
 
     line = {"metric": "nlml_grad_rows_per_sec", "value": rows_per_s, "unit": "rows/s",
@@ -452,7 +517,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 emulated on int8 tensor cores (s8 x s8 -> s32 digit products)" if emulated else "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "roofline": roofline, "fp64_dmma_path": fp64_compare,
+            "gpu_launches": launches, "roofline": roofline, "phi_cache": phi_cache, "guard": eng.guard_info(),
+            "fp64_dmma_path": fp64_compare,
             "cpu_baseline": cpu_baseline,
             "cost": cost, "grad_norm": float(np.linalg.norm(grad))}
     print(json.dumps(line))

@@ -170,6 +170,32 @@ int scfgp_stream_handoff(scfgp_handle* h, void* other_stream, int direction);
  * left to scfgp_eval_finish.  Either pointer may be NULL.  scfgp_eval does this itself. */
 int scfgp_eval_prefetch_factors(scfgp_handle* h, double* alpha, double* Li);
 
+/* Digit cache of Phi (emulated mode): pass 1 keeps the int8 digits of Phi for ALL rows of this handle in HBM
+ * (digits x ceil128(N) x ceil16(K) bytes: 104 GB at cfg4 on one GPU, 13 GB per GPU on eight) so that passes 2
+ * and 3 read them instead of recomputing the feature map.  It is allocated by the first evaluation when it fits
+ * under max_gb (default 120, env SCFGP_PHI_CACHE_MAX_GB) and under the free device memory minus 6 GB; when it
+ * does not, the handle says so on stderr and runs without it.  on = 0 (env SCFGP_PHI_CACHE=0) never allocates it.
+ * scfgp_phi_cache_bytes: bytes currently held (0 = running without the cache). */
+int scfgp_set_phi_cache(scfgp_handle* h, int on, double max_gb);
+long long scfgp_phi_cache_bytes(const scfgp_handle* h);
+
+/* A-posteriori guard of the emulated arithmetic (on by default in SCFGP_PREC_EMU_I8; SCFGP_GUARD=0 or
+ * scfgp_set_guard(h, 0, ..) turns it off).  After every factor phase the handle measures the error of the emulated
+ * Gram on a sample of its rows (the same rows through the FP64 DMMA Gram and through the digit Gram) and pushes
+ * it through the first-order perturbation of the results with the factors just computed:
+ *   est_cost  = estimated absolute error of `cost`      (threshold cost_tol,  default 1e-7)
+ *   est_alpha = estimated max error of alpha / max(1, |alpha|_inf)   (threshold alpha_tol, default 1e-6)
+ * (north_star's tolerances are 1e-6 relative on the cost and 1e-5 on alpha; the defaults keep a factor 10).
+ * scfgp_eval escalates on its own when an estimate exceeds its threshold: 5 -> 6 digits -> FP64, restarting the
+ * evaluation, and the handle stays at the higher precision (scfgp_get_precision2 tells).  With the phase API the
+ * caller reads the estimates after scfgp_eval_factor (scfgp_guard_last), combines them over the ranks (max) and
+ * calls scfgp_guard_escalate + restarts from scfgp_eval_begin on every rank when they exceed the thresholds.
+ * Thresholds <= 0 keep the current value. */
+int scfgp_set_guard(scfgp_handle* h, int on, double cost_tol, double alpha_tol);
+int scfgp_guard_last(const scfgp_handle* h, double* est_cost, double* est_alpha, double* dg_fro,
+                     long long* sample_rows, int* exceeded, int* escalations);
+int scfgp_guard_escalate(scfgp_handle* h);
+
 /* Device-resident results of the last evaluation (valid until the next one). */
 int scfgp_device_factors(scfgp_handle* h, void** d_alpha, void** d_Li, long long* ld_Li);
 
@@ -245,6 +271,17 @@ int scfgp_dbg_gemm(int device, int layout, int m, int n, int k, const double* A,
 int scfgp_dbg_emu_gemm(int device, int digits, int m, int n, int k, const double* A, const double* B,
                        double* C);
 /* lower Cholesky + inverse factor of a symmetric K x K matrix (info = pivot+1 or 0) */
+/* Developer tool: per-CTA clock64() intervals of the tcgen05 kernels' roles (8 counters per CTA, see
+ * umma_i8.cuh).  enable != 0 starts recording into a fresh buffer for `max_ctas` CTAs; a later call
+ * (enable 0 or 1) first copies the counters recorded so far to `out` (max_ctas * 8 values; may be NULL). */
+int scfgp_dbg_tile_timing(int device, int enable, unsigned long long* out, int max_ctas);
+/* Measured ceiling of the int8 tensor pipe for the digit-product instruction mix of `digits` digits on
+ * 128 x `tile_n` tiles (5/96, 5/64, 6/64, 4/64): the product kernels' tcgen05.mma stream with no operand
+ * traffic and no epilogue, `steps` K = 32 steps on every SM at once (random_data != 0: full-range int8
+ * operands, the power-relevant case).  Returns chip-wide int8 TOP/s, clocks per step and the SM clock
+ * the run averaged.  bench.py runs it in-process for the second roofline denominator. */
+int scfgp_dbg_mma_stream_peak(int device, int digits, int tile_n, int steps, int random_data, double* tops,
+                              double* clk_per_step, double* sm_mhz);
 int scfgp_dbg_factor(int device, int K, const double* A, double* L, double* Li, long long* info);
 /* Phi (N x K) for given params through the feature kernel */
 int scfgp_dbg_features(scfgp_handle* h, const double* params, const double* X, long long N,

@@ -50,8 +50,9 @@ def value_of(digits, scale):
 
 def emu_gemm(A, B, ks):
     """C = A . B^T through per-row power-of-two scales, `ks` digits and the truncated digit
-    products (classes i + j < ks), combined exactly like the GPU epilogue:
-    v = fma(acc_q, 2^(-8q), v) for q = ks-1 .. 0, then C = v * (scaleA 2^-14) * scaleB."""
+    products (classes i + j < ks), combined exactly like the GPU epilogue (umma_i8.cuh):
+    ks <= 5: S = sum_q acc_q 256^(ks-1-q) exactly in int64, v = float64(S) 2^(-8 (ks-1)) (one rounding);
+    ks >= 6: v = fma(acc_q, 2^(-8q), v) for q = ks-1 .. 0;  then C = v * (scaleA 2^-14) * scaleB."""
     A = np.asarray(A, dtype=np.float64)
     B = np.asarray(B, dtype=np.float64)
     sa = pow2_scale(np.abs(A).max(axis=1))
@@ -59,10 +60,14 @@ def emu_gemm(A, B, ks):
     dA = digits_of(A * (1.0 / sa)[:, None], ks)          # scaling by a power of two is exact
     dB = digits_of(B * (1.0 / sb)[:, None], ks)
     v = np.zeros((A.shape[0], B.shape[0]))
+    total = np.zeros((A.shape[0], B.shape[0]), dtype=np.int64)
     for q in range(ks - 1, -1, -1):
         acc = np.zeros((A.shape[0], B.shape[0]), dtype=np.int64)
         for i in range(q + 1):
             acc += dA[i] @ dB[q - i].T
         assert np.abs(acc).max(initial=0) < 2 ** 31, "int32 accumulator would overflow"
         v = v + acc.astype(np.float64) * 2.0 ** (-DIGIT_BITS * q)   # product exact -> one rounding, like fma
+        total += acc << (DIGIT_BITS * (ks - 1 - q))
+    if ks <= 5:
+        v = total.astype(np.float64) * 2.0 ** (-DIGIT_BITS * (ks - 1))   # int64 -> float64 rounds to nearest even
     return v * (sa * PROD_SCALE)[:, None] * sb[None, :]

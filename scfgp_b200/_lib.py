@@ -56,6 +56,11 @@ PROTOTYPES = {
     "scfgp_reduce_buffer": (C.c_int, [_h, C.c_int, C.POINTER(C.c_void_p), C.POINTER(_ll)]),
     "scfgp_stream_handoff": (C.c_int, [_h, C.c_void_p, C.c_int]),
     "scfgp_eval_prefetch_factors": (C.c_int, [_h, _dp, _dp]),
+    "scfgp_set_phi_cache": (C.c_int, [_h, C.c_int, C.c_double]),
+    "scfgp_phi_cache_bytes": (_ll, [_h]),
+    "scfgp_set_guard": (C.c_int, [_h, C.c_int, C.c_double, C.c_double]),
+    "scfgp_guard_last": (C.c_int, [_h, _dp, _dp, _dp, C.POINTER(_ll), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "scfgp_guard_escalate": (C.c_int, [_h]),
     "scfgp_device_factors": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(_ll)]),
     "scfgp_launch_count": (_ll, [_h]),
     "scfgp_last_pass_ms": (C.c_int, [_h, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
@@ -75,6 +80,8 @@ PROTOTYPES = {
                                        _dp, _dp, _dp, _dp, _dp, C.c_void_p, _ll]),
     "scfgp_dbg_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
     "scfgp_dbg_emu_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
+    "scfgp_dbg_tile_timing": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]),
+    "scfgp_dbg_mma_stream_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
     "scfgp_dbg_factor": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, C.POINTER(_ll)]),
     "scfgp_dbg_features": (C.c_int, [_h, _dp, _dp, _ll, _dp]),
 }

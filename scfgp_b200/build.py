@@ -16,8 +16,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libscfgp_b200.so")
 SOURCES = ["scfgp_abi.cu", "scaler_abi.cu"]
 DEPS = ["scfgp_abi.cu", "scaler_abi.cu", "kernels.cuh", "gemm_dmma.cuh", "gemm_tma.cuh", "kernels_tma.cuh", "umma_i8.cuh",
-        "emu_kernels.cuh", "host_state.cuh", "host_util.cuh", "host_buffers.cuh", "host_fp64.cuh", "host_emu.cuh",
-        "host_dense.cuh", os.path.join("..", "..", "include", "scfgp_b200.h")]
+        "emu_kernels.cuh", "mma_peak.cuh", "host_state.cuh", "host_util.cuh", "host_buffers.cuh", "host_fp64.cuh", "host_emu.cuh",
+        "host_dense.cuh", "host_guard.cuh", os.path.join("..", "..", "include", "scfgp_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -346,6 +346,109 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
 }
 
 // ------------------------------------------------------------------------------------
+// Pass 1, emulated mode: feature map with the digit extraction fused into its epilogue.
+//   Z = X.W + phi (DMMA, as k_features), Phi = s [cos Z | sin Z]                     SCFGP.py:98-102
+//   out: dst[d][r][f], dst[d][r][J + f] = digit d of Phi / s2 (5 digits), rows [rows, ceil128(rows)) zero;
+//        cpart[row block][col] += sum_r wsum[r] Phi[r][col]   (p = PhiT.y, from the float64 values)
+// Neither the float64 Phi slab nor a second pass over it exists on this path.  Needs J % 4 == 0 (aligned
+// 4-feature words in both halves); the host falls back to k_features + k_digits_slab otherwise.
+//   grid = rowblocks(128) * featblocks(64), as k_features
+// ------------------------------------------------------------------------------------
+template <int XVEC>
+__global__ void __launch_bounds__(CfgFeat::NT, 2)
+k_features_digits5(const double* __restrict__ X, long long ldx, int rows, int D, const double* __restrict__ Wt,
+                   long long ldw, const double* __restrict__ phi, int J, double s, double inv_s2,
+                   int8_t* __restrict__ dst, long long pitch, long long plane, const double* __restrict__ wsum,
+                   double* __restrict__ cpart, long long ldpart, int nfb) {
+  using Cfg = CfgFeat;
+  extern __shared__ __align__(16) double smem[];
+  const int rb = blockIdx.x / nfb, fb = blockIdx.x % nfb;
+  const int m0 = rb * Cfg::BM, n0 = fb * Cfg::BN;
+  double acc[Cfg::MI][Cfg::NI][2];
+  zero_acc<Cfg>(acc);
+  IdentMap am{m0, rows}, bm{n0, J};
+  gemm_mainloop<Cfg, true, true, XVEC, 2>(acc, X, ldx, am, Wt, ldw, bm, D, smem);
+  __syncthreads();                                   // the stage buffers are free: reused for the column sums
+  double* colsum = smem;                             // [WARPS_M][2][BN]  (cos / sin halves)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wmi = warp / Cfg::WARPS_N;
+  const int wm0 = wmi * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+  const double mq = digit_mult<5>() * inv_s2;        // value -> 2^39 / s2 units
+  const bool odd = t & 1;
+#pragma unroll
+  for (int j = 0; j < Cfg::NI; ++j) {
+    const int fl = wn0 + 8 * j + 2 * t;              // tile-local feature of acc[.][j][0] (even)
+    const int f = n0 + fl;
+    const bool ok0 = f < J, ok1 = f + 1 < J;
+    const double ph0 = ok0 ? phi[f] : 0.0, ph1 = ok1 ? phi[f + 1] : 0.0;
+    double pc0 = 0, pc1 = 0, ps0 = 0, ps1 = 0;       // column sums over this thread's rows
+#pragma unroll
+    for (int i = 0; i < Cfg::MI; ++i) {
+      const int r = m0 + wm0 + 8 * i + g;
+      const bool rv = r < rows;
+      double sn0 = 0.0, cs0 = 0.0, sn1 = 0.0, cs1 = 0.0;
+      if (rv && ok0) { sincos(acc[i][j][0] + ph0, &sn0, &cs0); cs0 *= s; sn0 *= s; }
+      if (rv && ok1) { sincos(acc[i][j][1] + ph1, &sn1, &cs1); cs1 *= s; sn1 *= s; }
+      if (wsum != nullptr && rv) {
+        const double w = wsum[r];
+        pc0 = fma(w, cs0, pc0); pc1 = fma(w, cs1, pc1); ps0 = fma(w, sn0, ps0); ps1 = fma(w, sn1, ps1);
+      }
+      // q' fields of this thread's cos pair and sin pair; lane pairs (t, t ^ 1) hold 4 neighbouring features:
+      // the even lane assembles the cos word, the odd lane the sin word
+      uint32_t hi[4], lo[4], chi[2], clo[2], shi[2], slo[2];
+      quant5(cs0 * mq, chi[0], clo[0]); quant5(cs1 * mq, chi[1], clo[1]);
+      quant5(sn0 * mq, shi[0], slo[0]); quant5(sn1 * mq, shi[1], slo[1]);
+      // send what the partner assembles, keep what this lane assembles
+      const uint32_t give_lo0 = odd ? clo[0] : slo[0], give_lo1 = odd ? clo[1] : slo[1];
+      const uint32_t give_hi = odd ? ((chi[0] & 0xffu) | ((chi[1] & 0xffu) << 8)) : ((shi[0] & 0xffu) | ((shi[1] & 0xffu) << 8));
+      const uint32_t got_lo0 = __shfl_xor_sync(0xffffffffu, give_lo0, 1);
+      const uint32_t got_lo1 = __shfl_xor_sync(0xffffffffu, give_lo1, 1);
+      const uint32_t got_hi = __shfl_xor_sync(0xffffffffu, give_hi, 1);
+      const uint32_t* klo = odd ? slo : clo;
+      const uint32_t* khi = odd ? shi : chi;
+      if (!odd) { lo[0] = klo[0]; lo[1] = klo[1]; hi[0] = khi[0]; hi[1] = khi[1];
+                  lo[2] = got_lo0; lo[3] = got_lo1; hi[2] = got_hi & 0xffu; hi[3] = (got_hi >> 8) & 0xffu; }
+      else      { lo[2] = klo[0]; lo[3] = klo[1]; hi[2] = khi[0]; hi[3] = khi[1];
+                  lo[0] = got_lo0; lo[1] = got_lo1; hi[0] = got_hi & 0xffu; hi[1] = (got_hi >> 8) & 0xffu; }
+      uint32_t w5[5];
+      pack5x4(hi, lo, w5);
+      const int f4 = f & ~3;                          // first of the 4 features of this lane pair
+      if (f4 < J) {                                   // (J % 4 == 0: the word is entirely inside or outside)
+        int8_t* o = dst + (long long)r * pitch + (odd ? J + f4 : f4);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) *reinterpret_cast<uint32_t*>(o + (long long)d * plane) = w5[d];
+      }
+    }
+    if (wsum != nullptr) {
+      // reduce over the 8 row groups g of the warp (lanes with equal t), then over the warps of this column block
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        pc0 += __shfl_xor_sync(0xffffffffu, pc0, o); pc1 += __shfl_xor_sync(0xffffffffu, pc1, o);
+        ps0 += __shfl_xor_sync(0xffffffffu, ps0, o); ps1 += __shfl_xor_sync(0xffffffffu, ps1, o);
+      }
+      if (g == 0) {
+        double* cs = colsum + (size_t)wmi * 2 * Cfg::BN;
+        cs[fl] = pc0; cs[fl + 1] = pc1; cs[Cfg::BN + fl] = ps0; cs[Cfg::BN + fl + 1] = ps1;
+      }
+    }
+  }
+  if (wsum != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 2 * Cfg::BN) {
+      const int half = threadIdx.x / Cfg::BN, fl = threadIdx.x % Cfg::BN;
+      const int f = n0 + fl;
+      if (f < J) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS_M; ++w) v += colsum[(size_t)w * 2 * Cfg::BN + half * Cfg::BN + fl];   // fixed order
+        cpart[(long long)rb * ldpart + half * J + f] += v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Gram accumulation over one row chunk:  C[a][b] += sc * sum_r A[r,a] B[r,b]
 //   operands: row-major digit arrays [KS][rows][pitch] read MN-major (their rows are the contraction
 //   index); items (a block of 128, b block of 64) cover the lower triangle (blocks that cross the
@@ -431,8 +534,8 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 //   A: row digits of Phi (scale sA), B: row digits of Li with per-row scales liscale
 //   tiles = (blocks of TNW Li rows, row blocks of 128); deepest reduction (last nb) first
 // ------------------------------------------------------------------------------------
-template <int KS, int TNW = TN>
-__global__ void __maxnreg__(umma::MAX_REGS)
+template <int KS, int TNW = TN, bool TWO_PHASE = (KS <= 5)>
+__global__ void __maxnreg__(TWO_PHASE ? umma::MAX_REGS_2PHASE : umma::MAX_REGS)
 k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapLi, int row0, int rows,
            int K, int ntiles, const double* __restrict__ liscale, double sA, double* __restrict__ vpart,
            long long ldv, double* __restrict__ mu) {
@@ -466,17 +569,35 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     const double sc = sA * umma::PROD_SCALE;
     const int r = rb0 + e.row;
     double sq = 0;
-#pragma unroll 1
-    for (int h16 = 0; h16 < TNW / 32; ++h16) {
-      double v[16];
-      umma::epilogue_load16<KS, TNW>(e, e.col0 + 16 * h16, v);
-      if (h16 == TNW / 32 - 1) umma::epilogue_release(p);
+    if constexpr (TWO_PHASE) {
+      // two-phase: park the recombined accumulators, hand tensor memory back, then do the math
+      long long parked[TNW / 32][16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int j = t.n0 + e.col0 + 16 * h16 + c;
-        const double tv = j <= K ? v[c] * liscale[j] : 0.0;
-        if (j == K) { if (r < rows) mu[r] = tv * sc; }
-        else sq = fma(tv, tv, sq);
+      for (int h16 = 0; h16 < TNW / 32; ++h16) umma::epilogue_drain16<KS, TNW>(e, e.col0 + 16 * h16, parked[h16]);
+      umma::epilogue_release(p);
+#pragma unroll
+      for (int h16 = 0; h16 < TNW / 32; ++h16) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int j = t.n0 + e.col0 + 16 * h16 + c;
+          const double tv = j <= K ? umma::drained_value<KS>(parked[h16][c]) * liscale[j] : 0.0;
+          if (j == K) { if (r < rows) mu[r] = tv * sc; }
+          else sq = fma(tv, tv, sq);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int h16 = 0; h16 < TNW / 32; ++h16) {
+        double v[16];
+        umma::epilogue_load16<KS, TNW>(e, e.col0 + 16 * h16, v);
+        if (h16 == TNW / 32 - 1) umma::epilogue_release(p);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int j = t.n0 + e.col0 + 16 * h16 + c;
+          const double tv = j <= K ? v[c] * liscale[j] : 0.0;
+          if (j == K) { if (r < rows) mu[r] = tv * sc; }
+          else sq = fma(tv, tv, sq);
+        }
       }
     }
     if (r < rows) vpart[(long long)(2 * nb + (e.col0 ? 1 : 0)) * ldv + r] = sq * sc * sc;
@@ -490,8 +611,8 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 //   Zbar = -Phibar_c * Phi_s + Phibar_s * Phi_c ;  slots[cta] += <Phibar, Phi>
 //   tiles = (feature blocks of TNW / 2, row blocks of 128)
 // ------------------------------------------------------------------------------------
-template <int KS, int TNW = TN>
-__global__ void __maxnreg__(umma::MAX_REGS)
+template <int KS, int TNW = TN, bool TWO_PHASE = (KS <= 5)>
+__global__ void __maxnreg__(TWO_PHASE ? umma::MAX_REGS_2PHASE : umma::MAX_REGS)
 k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
               const __grid_constant__ CUtensorMap mapC, int seg1_stages, int row0, const int8_t* __restrict__ dphi,
               long long dpitch, long long dplane, double recon, int rows, int J,
@@ -526,20 +647,41 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       it0 += umma::tile_stages(t);
       continue;
     }
+    unsigned long long* const tt = (threadIdx.x == umma::EPI_WARP0 * 32) ? umma::g_tile_timing : nullptr;
+    const long long tt0 = tt ? clock64() : 0;
     const umma::EpiPos e = umma::epilogue_wait<TNW>(p, tmem_base, seq & 1);
+    const long long tt1 = tt ? clock64() : 0;
+    long long tt2 = 0;
     const int r = t.m0 + e.row;
     const bool rvalid = r < rows;
     const double sc = sA * umma::PROD_SCALE;
     const double yn = rvalid ? y[r] : 0.0, gm = rvalid ? gmu[r] : 0.0;
     const double* prow = Phi + (long long)(rvalid ? r : 0) * ldp;
     double sacc = 0;
+    // two-phase (KS <= 5): park the recombined accumulators of all TNW / 2 columns, hand tensor memory back to
+    // the MMA warp at once, and run the fused epilogue under the next tile's MMAs
+    long long parked[TWO_PHASE ? TNW / 32 : 1][16];
+    if constexpr (TWO_PHASE) {
+#pragma unroll
+      for (int h16 = 0; h16 < TNW / 32; ++h16) umma::epilogue_drain16<KS, TNW>(e, e.col0 + 16 * h16, parked[h16]);
+      umma::epilogue_release(p);
+      if (tt) tt2 = clock64();
+    }
     asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");   // sh[], shcol[] of the previous tile consumed
-#pragma unroll 1
+#pragma unroll
     for (int h16 = 0; h16 < TNW / 32; ++h16) {
       double v[16];
       const int pcol = e.col0 + 16 * h16;                 // permuted tile column of v[0]
-      umma::epilogue_load16<KS, TNW>(e, pcol, v);
-      if (h16 == TNW / 32 - 1) umma::epilogue_release(p);
+      if constexpr (TWO_PHASE) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = umma::drained_value<KS>(parked[h16][c]);
+      } else {
+        umma::epilogue_load16<KS, TNW>(e, pcol, v);
+        if (h16 == TNW / 32 - 1) {
+          umma::epilogue_release(p);
+          if (tt) tt2 = clock64();
+        }
+      }
       double zb[8];
       const int f0 = (t.n0 + pcol) >> 1;
       // Phi of this row's 8 features (cos and sin halves).  With the digit cache they are rebuilt from
@@ -616,6 +758,11 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           dphi_part[(long long)(tile / nfb) * ldpart + f] += cs;
         }
       }
+    }
+    if (tt) {
+      umma::tt_add(tt, 4, tt1 - tt0);
+      umma::tt_add(tt, 5, tt2 - tt1);
+      umma::tt_add(tt, 6, clock64() - tt2);
     }
   }
   umma::pipe_teardown<KS, TNW>(p, tmem_base);

@@ -46,6 +46,30 @@ int emu_digits_slab(scfgp_handle* h, Ctx& c, int nd, bool from_cache, long long 
   return SCFGP_OK;
 }
 
+// pass 1 of the emulated mode with 5 digits: feature map + digit extraction + p = PhiT.y in ONE kernel
+// (k_features_digits5); no float64 Phi slab is written.  Needs J % 4 == 0 (see the kernel).
+bool fused_features_ok(const scfgp_handle* h) { return h->fuse_features && h->ks == 5 && h->J % 4 == 0; }
+int run_features_digits(scfgp_handle* h, Ctx& c, const double* Xc, int xvec, int rows, int8_t* dst, long long pitch,
+                        long long plane, const double* wsum, double* cpart) {
+  const int nfb = cdiv(h->J, 64);
+  const int nrb = cdiv(rows, 128);
+  const size_t smem = SmemSize<CfgFeat, true, true>::BYTES;
+  prof_begin(h, SCFGP_FAM_FEATURES, c.st);
+  trace_begin(h, "features+digits", c.st);
+  if (xvec == 2)
+    emu::k_features_digits5<2><<<nrb * nfb, CfgFeat::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
+                                                                      h->s, 1.0 / h->s2, dst, pitch, plane, wsum, cpart,
+                                                                      (long long)h->K, nfb);
+  else
+    emu::k_features_digits5<1><<<nrb * nfb, CfgFeat::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
+                                                                      h->s, 1.0 / h->s2, dst, pitch, plane, wsum, cpart,
+                                                                      (long long)h->K, nfb);
+  trace_end(h, c.st);
+  prof_end(h, SCFGP_FAM_FEATURES, c.st);
+  CKL();
+  return SCFGP_OK;
+}
+
 // The GEMM kernels of a chunk stream run on its low-priority companion stream: enter = the
 // companion waits for everything queued on the chunk stream, leave = the chunk stream waits
 // for the GEMM.
@@ -90,15 +114,23 @@ int emu_gram(scfgp_handle* h, Ctx& c, bool a_is_psi, int rows, long long r0, boo
 }
 
 // launch `kern<KS, 64>` or, with wide tiles (h->tnw == 96: 5 digits), `kern<5, 96>`
+// (h->two_phase: the two-phase epilogue of umma_i8.cuh, available up to 5 digits; SCFGP_EPILOGUE=1 selects the
+// one-phase epilogue for A/B measurements)
 #define EMU_TILE_LAUNCH(kern, grid, ...)                                                                           \
   do {                                                                                                             \
     if (h->tnw == 96) {                                                                                            \
+      if (h->ks2 != 5) { h->err = "wide tiles are built for 5 digits"; return SCFGP_ERR_ARG; }                     \
+      if (h->two_phase)                                                                                            \
+        emu::kern<5, 96, true><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(__VA_ARGS__);                \
+      else                                                                                                         \
+        emu::kern<5, 96, false><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(__VA_ARGS__);               \
+    } else if (h->two_phase && h->ks2 <= 5) {                                                                      \
       switch (h->ks2) {                                                                                            \
-        case 5: emu::kern<5, 96><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(__VA_ARGS__); break;       \
-        default: h->err = "wide tiles are built for 5 digits"; return SCFGP_ERR_ARG;                               \
+        case 4: emu::kern<4, 64, true><<<grid, umma::THREADS, umma::Geo<4>::SMEM, c.sg>>>(__VA_ARGS__); break;     \
+        default: emu::kern<5, 64, true><<<grid, umma::THREADS, umma::Geo<5>::SMEM, c.sg>>>(__VA_ARGS__); break;    \
       }                                                                                                            \
     } else {                                                                                                       \
-      EMU_KS_SWITCH(h->ks2, emu::kern<KS><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(__VA_ARGS__));       \
+      EMU_KS_SWITCH(h->ks2, emu::kern<KS, 64, false><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(__VA_ARGS__)); \
     }                                                                                                              \
   } while (0)
 
@@ -147,16 +179,34 @@ int ensure_phi_cache(scfgp_handle* h) {
   if (!want) return SCFGP_OK;
   h->Kc = (h->K + 15) / 16 * 16;
   const size_t bytes = (size_t)h->ks * rows * h->Kc;
+  // The cache is an explicit trade of HBM for time (5 N K bytes: 104 GB at cfg4 on one GPU): it is bounded by
+  // SCFGP_PHI_CACHE_MAX_GB (default 120) and by the free memory minus 6 GB of head room, and the handle says on
+  // stderr when it runs without it (once per data set / precision), because passes 2 and 3 then recompute the
+  // feature map (~5 % slower at cfg4).
+  const double gb = (double)bytes / (1024.0 * 1024.0 * 1024.0);
+  const char* why = nullptr;
   size_t fr = 0, tot = 0;
   CK(cudaMemGetInfo(&fr, &tot));
-  if (bytes + ((size_t)6 << 30) > fr) return SCFGP_OK;   // keep 6 GB of head room for the caller
-  if (cudaMalloc((void**)&h->phi_cache, bytes) != cudaSuccess) {
+  if (gb > h->cache_max_gb) why = "above SCFGP_PHI_CACHE_MAX_GB";
+  else if (bytes + ((size_t)6 << 30) > fr) why = "not enough free device memory";
+  else if (cudaMalloc((void**)&h->phi_cache, bytes) != cudaSuccess) {
     (void)cudaGetLastError();
     h->phi_cache = nullptr;
+    why = "cudaMalloc failed";
+  }
+  if (why) {
+    if (h->cache_log)
+      fprintf(stderr, "[scfgp_b200] digit cache of Phi declined (%.1f GB wanted, %.1f GB free, cap %.0f GB: %s); "
+                      "passes 2 and 3 recompute the feature map\n", gb, (double)fr / (1 << 30), h->cache_max_gb, why);
     return SCFGP_OK;
   }
+  if (h->cache_log > 1)
+    fprintf(stderr, "[scfgp_b200] digit cache of Phi: %.1f GB (%d digits x %lld rows x %lld columns)\n", gb, h->ks,
+            rows, h->Kc);
   h->cache_rows = rows;
   h->cache_ks = h->ks;
+  // (the fused feature kernel never writes the pad columns [K, Kc): they must read as zero digits)
+  if (h->Kc != h->K) CK(cudaMemsetAsync(h->phi_cache, 0, bytes, h->stream));
   int rc;
   if ((rc = make_tmap_digits(h, &h->mapCacheK, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TM))) return rc;
   if ((rc = make_tmap_digits_mn(h, &h->mapCacheMN_A, h->phi_cache, h->K, rows, h->Kc, h->ks, umma::TM))) return rc;

@@ -103,10 +103,14 @@ struct scfgp_handle {
   long long cache_rows = 0, Kc = 0;
   int cache_ks = 0;
   int want_cache = 1;          // SCFGP_PHI_CACHE=0 disables
+  double cache_max_gb = 120.0; // SCFGP_PHI_CACHE_MAX_GB
+  int cache_log = 1;           // SCFGP_PHI_CACHE_LOG: 0 silent, 1 say when declined (default), 2 also when engaged
   CUtensorMap mapCacheK, mapCacheMN_A, mapCacheMN_B;
   int4* gram_items = nullptr;
   int gram_count = 0;
   int vparts = 0;              // partial rows of vpart per chunk
+  int fuse_features = 1;       // pass 1 (5 digits, J % 4 == 0): digits straight from the feature kernel; SCFGP_FUSED_FEATURES=0: two kernels
+  int two_phase = 1;           // two-phase epilogue of Phi.LiT / backward (up to 5 digits); SCFGP_EPILOGUE=1: one-phase
   int tnw = 64;                // tile width of the K-major digit products (Phi.LiT, backward): 64, or 96 (5 digits)
   int gsplit = 1;              // partial Gram accumulators per chunk stream (kGramSplit in the emulated mode)
   int csplit = kColSplit;      // partial rows of the column-sum buffers per chunk stream (>= R/128)
@@ -132,6 +136,13 @@ struct scfgp_handle {
   // alpha / Li on the copy stream while passes 2 and 3 run
   cudaEvent_t ev_out = nullptr, ev_in = nullptr, ev_factor = nullptr;
   double *pre_alpha = nullptr, *pre_Li = nullptr;   // host destinations already being filled
+  // a-posteriori guard of the emulated path (host_guard.cuh)
+  int guard_on = 1;
+  double guard_cost_tol = 1e-7, guard_alpha_tol = 1e-6;
+  long long guard_sample = 0;
+  double guard_est_cost = 0, guard_est_alpha = 0, guard_dg_fro = 0;
+  int guard_escalations = 0;      // since the handle was created
+  double* trslots2 = nullptr;     // 2 K scratch
 
   // optional launch trace (CUDA event pair around every streaming-kernel launch)
   struct TraceRec { const char* name; int lane; cudaEvent_t e0, e1; };

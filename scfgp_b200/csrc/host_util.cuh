@@ -220,6 +220,12 @@ int set_kernel_attrs(scfgp_handle* h) {
                           (int)SmemSize<CfgBig, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SmemSize<CfgBig, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(emu::k_features_digits5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgFeat, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(emu::k_features_digits5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SmemSize<CfgFeat, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(emu::k_features_digits5<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(emu::k_features_digits5<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
   CK(cudaFuncSetAttribute(k_dw_splitk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SmemSize<CfgDw, false, false>::BYTES));
@@ -247,22 +253,32 @@ template <int KS>
 int set_emu_attrs(scfgp_handle* h) {
   const int smem = (int)umma::Geo<KS>::SMEM;
   CK(cudaFuncSetAttribute(emu::k_gram_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(emu::k_tgemm_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(emu::k_backward_i8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 64, false>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 64, false>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  if constexpr (KS <= 5) {
+    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 64, true>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 64, true>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  }
   CK(cudaFuncSetAttribute(emu::k_gemm_i8_dbg<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int mx = (int)cudaSharedmemCarveoutMaxShared;
   CK(cudaFuncSetAttribute(emu::k_gram_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-  CK(cudaFuncSetAttribute(emu::k_tgemm_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-  CK(cudaFuncSetAttribute(emu::k_backward_i8<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CK(cudaFuncSetAttribute(emu::k_digits_rows<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CK(cudaFuncSetAttribute((emu::k_digits_slab<KS, false>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CK(cudaFuncSetAttribute((emu::k_digits_slab<KS, true>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   if constexpr (KS == 5) {   // wide (96-column) tiles of the two K-major products
     const int smw = (int)umma::Geo<KS, 96>::SMEM;
-    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
-    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
-    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
+    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, true>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96, true>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
+    CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, false>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96, false>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   }
   return SCFGP_OK;
 }

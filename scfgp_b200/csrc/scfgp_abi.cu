@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "kernels_tma.cuh"
 #include "emu_kernels.cuh"
+#include "mma_peak.cuh"
 
 using namespace scfgp;
 
@@ -25,6 +26,46 @@ using namespace scfgp;
 #include "host_fp64.cuh"
 #include "host_emu.cuh"
 #include "host_dense.cuh"
+#include "host_guard.cuh"
+
+template <int KS, int TNW>
+static int mma_stream_peak(int ctas, int steps, int random_data, double* tops, double* clk_per_step, double* sm_mhz) {
+  using G = umma::Geo<KS, TNW>;
+  long long* d = nullptr;
+  if (cudaMalloc((void**)&d, (size_t)ctas * 16) != cudaSuccess) return SCFGP_ERR_CUDA;
+  const int smem = G::STAGE_BYTES + 1024 + 256;
+  cudaFuncSetAttribute(umma::k_mma_stream<KS, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = SCFGP_OK;
+  float ms = 0;
+  std::vector<long long> hst((size_t)ctas * 2, 0);
+  for (int rep = 0; rep < 2 && rc == SCFGP_OK; ++rep) {   // rep 0 warms up (clocks, instruction cache)
+    cudaMemset(d, 0, (size_t)ctas * 16);
+    cudaEventRecord(e0);
+    umma::k_mma_stream<KS, TNW><<<ctas, 128, smem>>>(rep == 0 ? std::min(steps, 8192) : steps, random_data, d);
+    cudaEventRecord(e1);
+    if (cudaDeviceSynchronize() != cudaSuccess) { rc = SCFGP_ERR_CUDA; break; }
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaMemcpy(hst.data(), d, (size_t)ctas * 16, cudaMemcpyDeviceToHost);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (rc) return rc;
+  double clk = 0;
+  for (int i = 0; i < ctas; ++i) {
+    if (!hst[2 * i + 1]) return SCFGP_ERR_CUDA;   // a CTA timed out
+    clk += (double)hst[2 * i];
+  }
+  clk /= ctas;
+  const double cols = (double)TNW * KS * (KS + 1) / 2;   // output columns per K = 32 step
+  if (tops) *tops = 2.0 * 128 * cols * 32 * (double)steps * ctas / (ms * 1e9);
+  if (clk_per_step) *clk_per_step = clk / steps;
+  if (sm_mhz) *sm_mhz = clk / (ms * 1e3);
+  return SCFGP_OK;
+}
 
 // =====================================================================================
 // C ABI
@@ -47,6 +88,10 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   h->ldw = (D + 1) / 2 * 2;
   h->Kp = (h->K + 63) / 64 * 64;   // stage-aligned: the Psi half of [Phi | Psi] starts on a pipeline-stage boundary
   if (const char* e = getenv("SCFGP_PHI_CACHE")) h->want_cache = atoi(e) != 0;
+  if (const char* e = getenv("SCFGP_PHI_CACHE_MAX_GB")) h->cache_max_gb = atof(e);
+  if (const char* e = getenv("SCFGP_PHI_CACHE_LOG")) h->cache_log = atoi(e);
+  if (const char* e = getenv("SCFGP_EPILOGUE")) h->two_phase = atoi(e) != 1;
+  if (const char* e = getenv("SCFGP_FUSED_FEATURES")) h->fuse_features = atoi(e) != 0;
   if (const char* e = getenv("SCFGP_PRECISION")) {
     if (!strncmp(e, "emu", 3)) {
       h->prec = SCFGP_PREC_EMU_I8;
@@ -102,6 +147,8 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   CK(cudaEventCreateWithFlags(&h->ev_factor, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
   if ((rc = dalloc(h, &h->trslots, K))) return rc;
+  if ((rc = dalloc(h, &h->trslots2, 2 * K))) return rc;
+  if (const char* e = getenv("SCFGP_GUARD")) h->guard_on = atoi(e) != 0;
   if ((rc = dalloc(h, &h->info, 1))) return rc;
   if (const char* e = getenv("SCFGP_NO_TMA")) h->use_tma = atoi(e) ? 0 : 1;
   if (h->use_tma) {
@@ -357,19 +404,26 @@ int scfgp_eval_pass1(scfgp_handle* h) {
       const long long b = (r0 + rows - 1) / h->up_block;
       CK(cudaStreamWaitEvent(c.st, h->up_ev[b], 0));
     }
-    if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
     if (h->prec == SCFGP_PREC_EMU_I8) {
       // row digits of Phi -- into the cache (all rows stay resident for passes 2 and 3) or the chunk
-      // buffer; p = PhiT.y comes out of the same pass over the slab; the Gram reads them MN-major
+      // buffer -- and p = PhiT.y; the Gram reads the digits MN-major
       const bool cached = h->phi_cache != nullptr;
       int8_t* dst = cached ? h->phi_cache + r0 * h->Kc : c.digR;
       const long long pitch = cached ? h->Kc : 2 * h->Kp;
       const long long plane = cached ? h->cache_rows * h->Kc : (long long)h->R * 2 * h->Kp;
-      if ((rc = emu_digits_slab(h, c, h->ks, false, r0, rows, nullptr, nullptr, dst, nullptr, nullptr, nullptr,
-                                pitch, plane, h->dy + r0, c.colpart)))
-        return rc;
+      if (fused_features_ok(h)) {
+        // one kernel: X.W, sincos, digits, p -- the float64 Phi slab is never written
+        if ((rc = run_features_digits(h, c, h->dX + r0 * h->D, h->xvec, rows, dst, pitch, plane, h->dy + r0, c.colpart)))
+          return rc;
+      } else {
+        if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
+        if ((rc = emu_digits_slab(h, c, h->ks, false, r0, rows, nullptr, nullptr, dst, nullptr, nullptr, nullptr,
+                                  pitch, plane, h->dy + r0, c.colpart)))
+          return rc;
+      }
       if ((rc = emu_gram(h, c, false, rows, r0, cached))) return rc;
     } else {
+      if ((rc = run_features(h, c, h->dX + r0 * h->D, h->xvec, rows, nullptr, nullptr))) return rc;
       if ((rc = run_syrk(h, c, false, rows))) return rc;
       trace_begin(h, "colsum", c.st);
       k_colsum<<<dim3(cdiv(K, 256), kColSplit), 256, 0, c.st>>>(c.Phi, h->ldk, rows, K, h->dy + r0, c.colpart, K);
@@ -431,7 +485,12 @@ int scfgp_eval_factor(scfgp_handle* h) {
   CK(cudaMemcpyAsync(&info, h->info, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev[7], h->stream));
   CK(cudaEventRecord(h->ev_factor, h->stream));
+  // a-posteriori check of the emulated Gram on a row sample (host_guard.cuh); read back with the pivot flag
+  double g5[5] = {0, 0, 0, 0, 0};
+  if ((rc = guard_measure(h))) return rc;
+  if (h->guard_sample > 0) CK(cudaMemcpyAsync(g5, h->scal + 8, sizeof(g5), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  guard_finish(h, g5);
   if (info != 0) {
     h->pivot = info - 1;
     h->err = "matrix is not positive definite (leading minor " + std::to_string(info) + ")";
@@ -737,11 +796,25 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
   return SCFGP_OK;
 }
 
+int scfgp_guard_escalate(scfgp_handle* h) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (h->prec != SCFGP_PREC_EMU_I8) return SCFGP_OK;
+  h->guard_escalations++;
+  // 5 (or fewer) digits -> 6 digits -> FP64 DMMA; sticky
+  if (std::max(h->ks, h->ks2) < 6 && std::min(h->ks, h->ks2) < 6) return scfgp_set_precision2(h, SCFGP_PREC_EMU_I8, 6, 6);
+  return scfgp_set_precision2(h, SCFGP_PREC_FP64, 0, 0);
+}
+
 int scfgp_eval(scfgp_handle* h, const double* params, double* cost, double* grad, double* alpha, double* Li) {
   int rc;
-  if ((rc = scfgp_eval_begin(h, params, grad != nullptr))) return rc;
-  if ((rc = scfgp_eval_pass1(h))) return rc;
-  if ((rc = scfgp_eval_factor(h))) return rc;
+  for (;;) {
+    if ((rc = scfgp_eval_begin(h, params, grad != nullptr))) return rc;
+    if ((rc = scfgp_eval_pass1(h))) return rc;
+    if ((rc = scfgp_eval_factor(h))) return rc;
+    if (!guard_exceeded(h)) break;
+    // the emulated Gram is not accurate enough at these hyper-parameters: more digits, start over
+    if ((rc = scfgp_guard_escalate(h))) return rc;
+  }
   if ((rc = scfgp_eval_prefetch_factors(h, alpha, Li))) return rc;
   if ((rc = scfgp_eval_pass2(h))) return rc;
   if (grad) {
@@ -749,6 +822,41 @@ int scfgp_eval(scfgp_handle* h, const double* params, double* cost, double* grad
     if ((rc = scfgp_eval_pass3(h))) return rc;
   }
   return scfgp_eval_finish(h, cost, grad, alpha, Li);
+}
+
+long long scfgp_phi_cache_bytes(const scfgp_handle* h) {
+  return (h && h->phi_cache) ? (long long)h->cache_ks * h->cache_rows * h->Kc : 0;
+}
+
+int scfgp_set_phi_cache(scfgp_handle* h, int on, double max_gb) {
+  if (!h) return SCFGP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  h->upload_pending = false;
+  h->want_cache = on != 0;
+  if (max_gb > 0) h->cache_max_gb = max_gb;
+  free_phi_cache(h);   // re-decided by the next evaluation
+  return SCFGP_OK;
+}
+
+int scfgp_set_guard(scfgp_handle* h, int on, double cost_tol, double alpha_tol) {
+  if (!h) return SCFGP_ERR_ARG;
+  h->guard_on = on != 0;
+  if (cost_tol > 0) h->guard_cost_tol = cost_tol;
+  if (alpha_tol > 0) h->guard_alpha_tol = alpha_tol;
+  return SCFGP_OK;
+}
+
+int scfgp_guard_last(const scfgp_handle* h, double* est_cost, double* est_alpha, double* dg_fro, long long* sample_rows,
+                     int* exceeded, int* escalations) {
+  if (!h) return SCFGP_ERR_ARG;
+  if (est_cost) *est_cost = h->guard_est_cost;
+  if (est_alpha) *est_alpha = h->guard_est_alpha;
+  if (dg_fro) *dg_fro = h->guard_dg_fro;
+  if (sample_rows) *sample_rows = h->guard_sample;
+  if (exceeded) *exceeded = guard_exceeded(h) ? 1 : 0;
+  if (escalations) *escalations = h->guard_escalations;
+  return SCFGP_OK;
 }
 
 int scfgp_reduce_buffer(scfgp_handle* h, int which, void** dptr, long long* count) {
@@ -1004,6 +1112,41 @@ int scfgp_dbg_emu_gemm(int device, int digits, int m, int n, int k, const double
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(sc); cudaFree(gA); cudaFree(gB);
   if (rc) return rc;
   return e == cudaSuccess ? SCFGP_OK : SCFGP_ERR_CUDA;
+}
+
+int scfgp_dbg_mma_stream_peak(int device, int digits, int tile_n, int steps, int random_data, double* tops,
+                              double* clk_per_step, double* sm_mhz) {
+  if (steps <= 0) return SCFGP_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return SCFGP_ERR_CUDA;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return SCFGP_ERR_CUDA;
+  if (digits == 5 && tile_n == 96) return mma_stream_peak<5, 96>(sms, steps, random_data, tops, clk_per_step, sm_mhz);
+  if (digits == 5 && tile_n == 64) return mma_stream_peak<5, 64>(sms, steps, random_data, tops, clk_per_step, sm_mhz);
+  if (digits == 6 && tile_n == 64) return mma_stream_peak<6, 64>(sms, steps, random_data, tops, clk_per_step, sm_mhz);
+  if (digits == 4 && tile_n == 64) return mma_stream_peak<4, 64>(sms, steps, random_data, tops, clk_per_step, sm_mhz);
+  return SCFGP_ERR_ARG;
+}
+
+int scfgp_dbg_tile_timing(int device, int enable, unsigned long long* out, int max_ctas) {
+  // developer tool: clock64() intervals of the tcgen05 kernels' roles per CTA (umma_i8.cuh, g_tile_timing)
+  static unsigned long long* buf[64] = {};
+  if (device < 0 || device >= 64 || max_ctas <= 0) return SCFGP_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return SCFGP_ERR_CUDA;
+  if (cudaDeviceSynchronize() != cudaSuccess) return SCFGP_ERR_CUDA;
+  const size_t bytes = (size_t)max_ctas * umma::TT_SLOTS * sizeof(unsigned long long);
+  unsigned long long* nul = nullptr;
+  if (buf[device]) {
+    if (out && cudaMemcpy(out, buf[device], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return SCFGP_ERR_CUDA;
+    cudaMemcpyToSymbol(umma::g_tile_timing, &nul, sizeof(nul));
+    cudaFree(buf[device]);
+    buf[device] = nullptr;
+  }
+  if (enable) {
+    if (cudaMalloc((void**)&buf[device], bytes) != cudaSuccess) return SCFGP_ERR_CUDA;
+    cudaMemset(buf[device], 0, bytes);
+    if (cudaMemcpyToSymbol(umma::g_tile_timing, &buf[device], sizeof(nul)) != cudaSuccess) return SCFGP_ERR_CUDA;
+  }
+  return SCFGP_OK;
 }
 
 int scfgp_dbg_factor(int device, int K, const double* A, double* L, double* Li, long long* info) {

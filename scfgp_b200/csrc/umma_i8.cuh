@@ -47,6 +47,9 @@ constexpr int THREADS = 320;
 constexpr int EPI_WARP0 = 2;
 constexpr int EPI_THREADS = 256;
 constexpr int MAX_REGS = 96;  // per thread: 320 x 96 leaves more than half of the register file to co-resident kernels
+// two-phase epilogue (KS <= 5): a thread parks its TNW / 2 recombined accumulators as int64 (up to 96 registers at
+// TNW = 96) so that tensor memory goes back to the MMA warp before the fused epilogue math starts
+constexpr int MAX_REGS_2PHASE = 184;
 
 // TNW: tile columns per class.  64: four B digits per instruction (N = 256), every digit count; 96: two B digits
 // per instruction (N = 192), 20 % fewer operand bytes per digit product, at most 5 digits (480 class columns).
@@ -221,6 +224,18 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// Optional in-kernel tile timing (developer tool, scfgp_dbg_tile_timing): when the pointer is set, one thread of
+// each role adds its clock64() intervals per tile to 8 counters of its CTA:
+//   0 tiles   1 MMA warp waiting for acc_empty   2 MMA warp waiting for operand stages (full barriers)
+//   3 MMA warp: whole tile, first wait to last commit   4 epilogue waiting for acc_full
+//   5 epilogue: acc_full -> accumulators released   6 epilogue: release -> end of the tile's epilogue
+//   7 producer waiting for free stages
+__device__ unsigned long long* g_tile_timing = nullptr;
+constexpr int TT_SLOTS = 8;
+__device__ __forceinline__ void tt_add(unsigned long long* tt, int slot, long long v) {
+  if (tt) atomicAdd(tt + (size_t)blockIdx.x * TT_SLOTS + slot, (unsigned long long)v);
+}
+
 struct Tile {
   int m0;       // first row of the A tensor map (dimension 1)
   int n0;       // first row of the B tensor map (dimension 1)
@@ -306,13 +321,17 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
   static_assert(!TR || TNW == 64, "MN-major B boxes are 64 bytes wide");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (t.c_end - t.c_begin + KB - 1) / KB;
+  unsigned long long* const tt = g_tile_timing;
   if (warp == 0) {
     if (lane == 0) {
+      long long w_empty = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int it = it0 + kb;
         const int st = it % G::STAGES;
         const uint32_t use = it / G::STAGES;
+        const long long c0 = tt ? clock64() : 0;
         mbar_wait(&p.empty[st], (use & 1) ^ 1);
+        if (tt) w_empty += clock64() - c0;
         uint8_t* sa = p.stages + (size_t)st * G::STAGE_BYTES;
 #if UMMA_PROBE_MODE == 2
         if (it >= G::STAGES) { mbar_arrive(&p.full[st]); continue; }
@@ -328,18 +347,24 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
           tma_load_3d(sa + G::A_BYTES, mapB, c + t.c_off_b, t.n0, 0, &p.full[st]);
         }
       }
+      tt_add(tt, 7, w_empty);
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      const long long t_begin = tt ? clock64() : 0;
+      long long w_full = 0;
       if (seq > 0) {
         mbar_wait(p.acc_empty, (uint32_t)(seq - 1) & 1u);
         tc_fence_after();
       }
+      if (tt) tt_add(tt, 1, clock64() - t_begin);
       for (int kb = 0; kb < nkb; ++kb) {
         const int it = it0 + kb;
         const int st = it % G::STAGES;
         const uint32_t use = it / G::STAGES;
+        const long long c0 = tt ? clock64() : 0;
         mbar_wait(&p.full[st], use & 1);
+        if (tt) w_full += clock64() - c0;
         tc_fence_after();
         const uint32_t sa = smem_u32(p.stages + (size_t)st * G::STAGE_BYTES);
         const uint32_t sb = sa + G::A_BYTES;
@@ -411,6 +436,11 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         tc_commit(&p.empty[st]);  // stage reusable once these MMAs have read it
       }
       tc_commit(p.acc_full);  // accumulators complete
+      if (tt) {
+        tt_add(tt, 0, 1);
+        tt_add(tt, 2, w_full);
+        tt_add(tt, 3, clock64() - t_begin);
+      }
     }
   }
 }
@@ -456,8 +486,28 @@ __device__ __forceinline__ void epilogue_release(const Pipe& p) {
   if ((threadIdx.x & 31) == 0) mbar_arrive(p.acc_empty);
 }
 // v[c] = sum_q 2^(-8q) acc_q[row][col + c], c < 16   (col = tile column, multiple of 16)
+// KS <= 5: exact int64 recombination and one rounding (the same values the two-phase epilogue produces);
+// KS >= 6: float64 fma chain, least significant class first
 template <int KS, int TNW = TN>
 __device__ __forceinline__ void epilogue_load16(const EpiPos& e, int col, double (&v)[16]) {
+  if constexpr (KS <= 5) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.0;
+    long long a[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a[c] = 0;
+#pragma unroll
+    for (int q = 0; q < KS; ++q) {
+      uint32_t r[16];
+      tmem_ld16(e.lane_base + (uint32_t)(q * TNW + col), r);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a[c] = a[c] * 256 + (long long)(int)r[c];
+    }
+    const double w = __longlong_as_double((long long)(1023 - DIGIT_BITS * (KS - 1)) << 52);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = (double)a[c] * w;
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 16; ++c) v[c] = 0.0;
 #pragma unroll
@@ -468,6 +518,62 @@ __device__ __forceinline__ void epilogue_load16(const EpiPos& e, int col, double
 #pragma unroll
     for (int c = 0; c < 16; ++c) v[c] = fma((double)(int)r[c], w, v[c]);
   }
+}
+
+
+// ---- two-phase epilogue -------------------------------------------------------------------------------------
+// Phase 1 ("drain"): tcgen05.ld all KS class accumulators of 16 columns back to back (one wait), recombine
+// them EXACTLY in int64,  S = sum_q acc_q 256^(KS-1-q)  (|S| < 2^62 for KS <= 5: |acc_q| < 2^31), and keep S.
+// After the last drain of a tile the accumulators are released (epilogue_release) and the MMA warp starts the
+// next tile while phase 2 (scales, fused math, stores) runs on the parked values:  value = S 2^(-8 (KS-1)).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// the loaded registers become valid here: the in/out operands keep their consumers behind the wait
+__device__ __forceinline__ void tmem_ld16_landed(uint32_t (&r)[16], bool wait) {
+  if (wait)
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+  else
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+template <int KS, int TNW = TN>
+__device__ __forceinline__ void epilogue_drain16(const EpiPos& e, int col, long long (&s)[16]) {
+  static_assert(KS <= 5, "exact int64 recombination needs 8 (KS - 1) + 31 < 63");
+  uint32_t r[KS][16];
+#pragma unroll
+  for (int q = 0; q < KS; ++q) tmem_ld16_issue(e.lane_base + (uint32_t)(q * TNW + col), r[q]);
+#pragma unroll
+  for (int q = 0; q < KS; ++q) tmem_ld16_landed(r[q], q == 0);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    long long a = (long long)(int)r[KS - 1][c];
+#pragma unroll
+    for (int q = KS - 2; q >= 0; --q) {
+      const int sh = DIGIT_BITS * (KS - 1 - q);
+      if (sh < 31) a += (long long)(int)r[q][c] * (long long)(1 << sh);   // mul.wide.s32 + add
+      else a += (long long)(int)r[q][c] << sh;
+    }
+    s[c] = a;
+  }
+}
+// phase 2: the parked integer as a float64 (one rounding; exact below 2^53)
+template <int KS>
+__device__ __forceinline__ double drained_value(long long s) {
+  return (double)s * __longlong_as_double((long long)(1023 - DIGIT_BITS * (KS - 1)) << 52);
 }
 
 }  // namespace umma

@@ -121,6 +121,29 @@ class Engine:
             return "fp64"
         return f"emu{d.value}" if d2.value == d.value else f"emu{d.value}/{d2.value}"
 
+    def set_phi_cache(self, on: bool = True, max_gb: float = 0.0):
+        """Digit cache of Phi for all rows (emulated mode; see include/scfgp_b200.h): allow / forbid it and bound
+        its size; ``phi_cache_bytes`` tells what the last evaluation actually holds (0 = no cache)."""
+        self._check(self.lib.scfgp_set_phi_cache(self._h, int(bool(on)), float(max_gb)))
+
+    @property
+    def phi_cache_bytes(self) -> int:
+        return int(self.lib.scfgp_phi_cache_bytes(self._h))
+
+    def set_guard(self, on: bool = True, cost_tol: float = 0.0, alpha_tol: float = 0.0):
+        """A-posteriori guard of the emulated arithmetic (include/scfgp_b200.h, scfgp_set_guard): thresholds on the
+        estimated error of `cost` (absolute) and of alpha (relative to max(1, |alpha|_inf)); 0 keeps the default."""
+        self._check(self.lib.scfgp_set_guard(self._h, int(bool(on)), float(cost_tol), float(alpha_tol)))
+
+    def guard_info(self) -> dict:
+        """Estimates of the last factor phase and the escalations this engine has made so far."""
+        ec, ea, fro = C.c_double(), C.c_double(), C.c_double()
+        rows, exc, esc = C.c_longlong(), C.c_int(), C.c_int()
+        self.lib.scfgp_guard_last(self._h, C.byref(ec), C.byref(ea), C.byref(fro), C.byref(rows), C.byref(exc),
+                                  C.byref(esc))
+        return {"est_cost": ec.value, "est_alpha": ea.value, "dG_fro_sample": fro.value, "sample_rows": rows.value,
+                "exceeded": bool(exc.value), "escalations": esc.value, "precision": self.precision}
+
     def set_streams(self, n: int):
         self._check(self.lib.scfgp_set_streams(self._h, int(n)))
 
@@ -229,6 +252,18 @@ class Engine:
                 def backward(s): eng._check(lib.scfgp_eval_backward(h))
                 def pass3(s): eng._check(lib.scfgp_eval_pass3(h))
                 def reduce_buffer(s, which): return eng._reduce_tensor(which)
+
+                def needs_more_precision(s):
+                    # every rank measured its own row sample: the decision is taken on the maximum over ranks
+                    g = eng.guard_info()
+                    t = torch.tensor([1.0 if g["exceeded"] else 0.0], dtype=torch.float64, device=f"cuda:{eng.device}")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                    if float(t[0]) == 0.0:
+                        return False
+                    eng._red.clear()                                  # (buffers may be re-allocated)
+                    eng._check(lib.scfgp_guard_escalate(h))
+                    eng._check(lib.scfgp_eval_begin(h, _lib.dptr(params), int(want_grad)))
+                    return True
 
             def _allreduce(buf):
                 # stream-ordered, no host synchronisation: torch's current stream (which NCCL orders its

@@ -22,10 +22,18 @@ def shard_bounds(n_rows: int, rank: int, world: int):
 def run_eval_phases(api, allreduce, want_grad: bool):
     """Sequence: pass1 -> allreduce(RED1) -> factor -> pass2 -> allreduce(RED2)
     [-> backward -> pass3 -> allreduce(RED3)].  `api` exposes pass1/factor/pass2/backward/
-    pass3 and reduce_buffer(which); `allreduce(buf)` sums `buf` in place over ranks."""
-    api.pass1()
-    allreduce(api.reduce_buffer(1))
-    api.factor()
+    pass3 and reduce_buffer(which); `allreduce(buf)` sums `buf` in place over ranks.
+
+    Optional `api.needs_more_precision()`: called after the factor phase; when it returns True (the
+    a-posteriori guard of the emulated arithmetic fired on some rank and every rank has switched to the
+    next precision and re-begun the evaluation) the sequence starts over from pass 1."""
+    while True:
+        api.pass1()
+        allreduce(api.reduce_buffer(1))
+        api.factor()
+        again = getattr(api, "needs_more_precision", None)
+        if again is None or not again():
+            break
     api.pass2()
     allreduce(api.reduce_buffer(2))
     if want_grad:
