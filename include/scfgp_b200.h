@@ -142,6 +142,13 @@ int scfgp_set_factors(scfgp_handle* h, const double* alpha, const double* Li);
 int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dXs, long long T,
                          double* dmu, double* dstd);
 
+/* Minibatch mode (SCFGP.minibatches / optimize(nbatches > 1), SCFGP/SCFGP.py:172-182,226-235): evaluate on the rows
+ * idx[0..n) (host array of LOCAL row indices into the resident training set of this handle) -- gathered on the
+ * device, the training set is not uploaded again.  n_global = rows of the batch over all ranks (the N of the
+ * reference's cost for this batch; 0 = n).  n = 0 with idx != NULL is legal (a rank without rows of this batch).
+ * idx == NULL returns to the whole resident set.  A new scfgp_set_data_* call also ends the selection. */
+int scfgp_select_rows(scfgp_handle* h, const long long* idx, long long n, long long n_global);
+
 /* ---- phase API (multi-GPU: rows are sharded over ranks, the host all-reduces the
  * device buffer named by each phase between calls; every rank then runs the small
  * replicated phases on identical inputs).  Order:

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "scfgp_set_data_host": (C.c_int, [_h, _dp, _dp, _ll, _ll]),
     "scfgp_set_data_host_async": (C.c_int, [_h, _dp, _dp, _ll, _ll]),
     "scfgp_set_data_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, _ll, _ll]),
+    "scfgp_select_rows": (C.c_int, [_h, C.POINTER(_ll), _ll, _ll]),
     "scfgp_eval": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp]),
     "scfgp_predict": (C.c_int, [_h, _dp, _dp, _ll, _dp, _dp, _dp, _dp]),
     "scfgp_set_factors": (C.c_int, [_h, _dp, _dp]),

@@ -131,8 +131,10 @@ void free_all(scfgp_handle* h) {
   free_emu_static(h);
   for (double* p : {h->acc_all, h->dW_all, h->colpart_all, h->slots_all, h->Wt, h->phi, h->red1, h->red2, h->red3, h->L,
                     h->Li, h->Bm, h->BH, h->BHB, h->A2, h->B2, h->Dinv, h->tmpS, h->alpha, h->beta, h->tvec,
-                    h->pbar, h->scal, h->gmu, h->gv, h->colpart, h->slots, h->trslots, h->ownX, h->owny})
+                    h->pbar, h->scal, h->gmu, h->gv, h->colpart, h->slots, h->trslots, h->trslots2, h->ownX, h->owny,
+                    h->selX, h->sely})
     if (p) cudaFree(p);
+  if (h->selidx) cudaFree(h->selidx);
   if (h->info) cudaFree(h->info);
   for (int4* p : h->to_free) cudaFree(p);
   for (auto& e : h->ev)

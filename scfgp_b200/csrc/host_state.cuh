@@ -51,6 +51,14 @@ struct scfgp_handle {
   double* ownX = nullptr;
   double* owny = nullptr;
   long long own_cap = 0;                 // rows the owned buffers can hold
+  // minibatch mode (SCFGP.py:172-182,226-235): a row subset of the resident set, gathered on the device
+  const double* fullX = nullptr;         // the resident training set the subset is taken from
+  const double* fully = nullptr;
+  long long fullN = 0, fullNglobal = 0;
+  double *selX = nullptr, *sely = nullptr;
+  long long* selidx = nullptr;
+  long long sel_cap = 0;
+  bool subset_active = false;
   // host -> device upload in row blocks on a copy stream, overlapped with the first pass
   cudaStream_t cstream = nullptr;
   std::vector<cudaEvent_t> up_ev;        // one event per uploaded row block

@@ -196,6 +196,18 @@ __global__ void k_colsum(const double* __restrict__ S, long long lds, int rows, 
   part[(long long)blockIdx.y * ldpart + k] += (a0 + a1) + (a2 + a3);
 }
 
+// minibatch gather: Xout[i][:] = X[idx[i]][:], yout[i] = y[idx[i]]   (one warp per selected row)
+__global__ void k_gather_rows(const double* __restrict__ X, const double* __restrict__ y, int D,
+                              const long long* __restrict__ idx, long long n, double* __restrict__ Xout,
+                              double* __restrict__ yout) {
+  const int lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const long long r = idx[i];
+  for (int d = lane; d < D; d += 32) Xout[i * D + d] = X[r * D + d];
+  if (lane == 0) yout[i] = y[r];
+}
+
 // out[k] (+)= sum_rs part[rs][k]
 __global__ void k_sum_parts(const double* __restrict__ part, long long ldpart, int nsplit, int cols,
                             double* __restrict__ out) {

@@ -296,6 +296,8 @@ int scfgp_set_streams(scfgp_handle* h, int n) {
 static int set_data_common(scfgp_handle* h, long long N, long long n_global) {
   h->N = N;
   h->Nglobal = n_global > 0 ? n_global : N;
+  h->fullX = h->dX; h->fully = h->dy; h->fullN = N; h->fullNglobal = h->Nglobal;
+  h->subset_active = false;
   h->have_factors = false;
   h->xvec = (((uintptr_t)h->dX % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
   return ensure_row_arrays(h, N);
@@ -365,10 +367,50 @@ int scfgp_set_data_device(scfgp_handle* h, const double* dX, const double* dy, l
   return set_data_common(h, N, n_global);
 }
 
+int scfgp_select_rows(scfgp_handle* h, const long long* idx, long long n, long long n_global) {
+  if (!h || n < 0 || (n > 0 && !idx)) return SCFGP_ERR_ARG;
+  if (!h->fullX || h->fullN <= 0) { h->err = "select_rows before set_data"; return SCFGP_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = finish_upload(h))) return rc;
+  h->have_factors = false;
+  if (idx == nullptr) {                       // back to the whole resident set
+    h->dX = h->fullX; h->dy = h->fully; h->N = h->fullN; h->Nglobal = h->fullNglobal;
+    h->subset_active = false;
+    return SCFGP_OK;
+  }
+  for (long long i = 0; i < n; ++i)
+    if (idx[i] < 0 || idx[i] >= h->fullN) { h->err = "select_rows: row index out of range"; return SCFGP_ERR_ARG; }
+  if (n > h->sel_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    for (void* p : {(void*)h->selX, (void*)h->sely, (void*)h->selidx}) if (p) cudaFree(p);
+    h->selX = h->sely = nullptr; h->selidx = nullptr; h->sel_cap = 0;
+    const long long cap = std::max<long long>(n, 1024);
+    CK(cudaMalloc((void**)&h->selX, (size_t)cap * h->D * sizeof(double)));
+    CK(cudaMalloc((void**)&h->sely, (size_t)cap * sizeof(double)));
+    CK(cudaMalloc((void**)&h->selidx, (size_t)cap * sizeof(long long)));
+    h->sel_cap = cap;
+  }
+  if (n > 0) {
+    // (stream-ordered behind the previous evaluation, which may still read the old subset)
+    CK(cudaMemcpyAsync(h->selidx, idx, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    k_gather_rows<<<cdiv(n, 8), 256, 0, h->stream>>>(h->fullX, h->fully, h->D, h->selidx, n, h->selX, h->sely);
+    CKL();
+    CK(cudaStreamSynchronize(h->stream));     // idx may be a temporary of the caller
+  }
+  h->dX = h->selX; h->dy = h->sely;
+  h->N = n;
+  h->Nglobal = n_global > 0 ? n_global : n;
+  h->subset_active = true;
+  h->xvec = (((uintptr_t)h->dX % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
+  return ensure_row_arrays(h, std::max<long long>(n, 1));
+}
+
 // ---------------------------------------------------------------------------------
 int scfgp_eval_begin(scfgp_handle* h, const double* params, int want_grad) {
   if (!h || !params) return SCFGP_ERR_ARG;
-  if (!h->dX || h->N <= 0) { h->err = "no training data set"; return SCFGP_ERR_ARG; }
+  // (N == 0 is legal for a rank whose shard holds no row of the current minibatch: its partial sums are zero)
+  if (!h->dX || h->N < 0 || (h->N == 0 && !h->subset_active)) { h->err = "no training data set"; return SCFGP_ERR_ARG; }
   CK(cudaSetDevice(h->device));
   h->want_grad = want_grad;
   h->have_factors = false;

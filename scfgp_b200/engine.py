@@ -195,6 +195,17 @@ class Engine:
         self._check(self.lib.scfgp_set_data_device(self._h, C.c_void_p(X_t.data_ptr()),
                                                    C.c_void_p(y_t.data_ptr()), self.N, int(n_global or self.N)))
 
+    def select_rows(self, idx=None, n_global: int | None = None):
+        """Minibatch mode (SCFGP.py:172-182): evaluate on the rows ``idx`` (LOCAL indices into this engine's resident
+        training set; gathered on the device, nothing is uploaded again).  ``None`` returns to all rows."""
+        if idx is None:
+            self._check(self.lib.scfgp_select_rows(self._h, None, 0, 0))
+            return
+        idx = np.ascontiguousarray(idx, dtype=np.int64).reshape(-1)
+        buf = idx if idx.size else np.zeros(1, dtype=np.int64)
+        self._check(self.lib.scfgp_select_rows(self._h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), idx.size,
+                                               int(n_global or idx.size)))
+
     # ------------------------------------------------------------------ evaluation
     def _reduce_tensor(self, which: int):
         import torch

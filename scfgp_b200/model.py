@@ -284,13 +284,57 @@ class SCFGP(object):
             cost, self.alpha, self.Li = self.train_func(self.X, self.y)
 
     def minibatches(self, X, y, batchsize, shuffle=True):
+        """The reference's generator (SCFGP.py:172-182): yields host copies (X[batch], y[batch])."""
         assert len(X) == len(y)
-        if shuffle:
-            inds = np.arange(len(X))
-            np.random.shuffle(inds)
-        for start_ind in range(0, len(X) - batchsize + 1, batchsize):
-            batch = inds[start_ind:start_ind + batchsize] if shuffle else slice(start_ind, start_ind + batchsize)
+        for batch in self._minibatch_indices(len(X), batchsize, shuffle):
             yield np.ascontiguousarray(X[batch]), np.ascontiguousarray(y[batch])
+
+    def _minibatch_indices(self, n, batchsize, shuffle=True):
+        """Row indices of the batches of one sweep, drawn exactly as SCFGP.minibatches does (one
+        ``np.random.shuffle`` of arange(n) per sweep, SCFGP.py:174-176; trailing rows that do not fill a batch are
+        dropped).  Under ``torch.distributed`` rank 0's permutation is broadcast so that all ranks cut the same
+        batches."""
+        if shuffle:
+            inds = np.arange(n)
+            np.random.shuffle(inds)
+            rank, world = self._ranks()
+            if world > 1:
+                import torch
+                import torch.distributed as td
+                dev = f"cuda:{self.device}" if td.get_backend() == "nccl" else "cpu"
+                t = torch.as_tensor(inds).to(dev)
+                td.broadcast(t, src=0)
+                inds = t.cpu().numpy()
+        for start_ind in range(0, n - batchsize + 1, batchsize):
+            yield inds[start_ind:start_ind + batchsize] if shuffle else np.arange(start_ind, start_ind + batchsize)
+
+    def _row_range(self):
+        """[lo, hi) of the global row indices this rank's engine holds."""
+        rank, world = self._ranks()
+        n = int(self.X.shape[0])
+        if world == 1:
+            return 0, n
+        if self.presharded:                     # every rank passed its own rows: offsets from the row counts
+            import torch
+            import torch.distributed as td
+            dev = f"cuda:{self.device}" if td.get_backend() == "nccl" else "cpu"
+            counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            td.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev))
+            lo = int(sum(int(c) for c in counts[:rank]))
+            return lo, lo + n
+        return shard_bounds(n, rank, world)
+
+    def _train_iter_rows(self, batch):
+        """One ``train_iter_func`` step on the rows ``batch`` (global indices) of the resident training set: the
+        rows are gathered on the device (``scfgp_select_rows``), nothing is uploaded again."""
+        self._upload(self.X, self.y)
+        lo, hi = self._batch_range
+        local = batch[(batch >= lo) & (batch < hi)] - lo
+        self._engine.select_rows(local, n_global=len(batch))
+        cost, grad, alpha, Li = self._engine.eval(self.params, want_grad=True)
+        self.last_grad = grad
+        self.params = self._rule.step(self.params, grad)
+        return [np.float64(cost), alpha, Li]
 
     # ------------------------------------------------------------------ training loop (SCFGP.py:184-276)
     def optimize(self, Xv=None, yv=None, funcs=None, visualizer=None, **args):
@@ -329,18 +373,19 @@ class SCFGP(object):
         report_every = max(1, max_iter // 10)
         for it in range(max_iter):
             if nbatches > 1:
-                if self._is_cuda_tensor(self.X):
-                    raise NotImplementedError("minibatch mode needs host (NumPy) training data")
-                if self._ranks()[1] > 1:
-                    raise NotImplementedError("minibatch mode is single-process (its shuffles are per process)")
-                cost_sum, params_list, batch_count = 0, [], 0
-                for Xb, yb in self.minibatches(self.X, self.y, batchsize):
-                    params_list.append(self.params.copy())
-                    cost, self.alpha, self.Li = self.train_iter_func(Xb, yb)
+                # SCFGP.py:226-235 with the batches gathered on the device from the resident training set (host
+                # arrays or CUDA tensors, one process or one per GPU).  The reference's per-sweep median of the
+                # parameter snapshots is rebound to a variable its compiled functions never read:
+                # the effective iterate is the last one, which is what is kept here.
+                self._batch_range = self._row_range()
+                cost_sum, batch_count = 0, 0
+                for batch in self._minibatch_indices(self.N, batchsize):
+                    cost, self.alpha, self.Li = self._train_iter_rows(batch)
                     cost_sum += cost
                     batch_count += 1
                     if batch_count == nbatches:
                         break
+                self._engine.select_rows(None)
                 self.evals['COST'][1].append(np.double(cost_sum / batch_count))
             else:
                 cost, self.alpha, self.Li = self.train_iter_func(self.X, self.y)

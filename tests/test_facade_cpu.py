@@ -15,6 +15,10 @@ class OracleEngine:
 
     def set_data(self, X, y, n_global=None):
         self.X, self.y = X, np.asarray(y).reshape(-1)
+        self.fullX, self.fully = self.X, self.y
+
+    def select_rows(self, idx=None, n_global=None):
+        self.X, self.y = (self.fullX, self.fully) if idx is None else (self.fullX[idx], self.fully[idx])
 
     def eval(self, h, want_grad=True, **_):
         self.n_eval += 1

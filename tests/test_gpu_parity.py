@@ -402,3 +402,63 @@ def test_optimizer_trajectory_matches_oracle_driven_fit(precision, ptol, ctol):
     scale = float(np.std(yte))
     np.testing.assert_allclose(mu1, mu0, atol=1e-5 * scale if ptol else 1e-3 * scale)
     np.testing.assert_allclose(sd1, sd0, atol=1e-5 * scale if ptol else 1e-3 * scale)
+
+
+# ------------------------------------------------------------------ minibatch mode on the device (row f5)
+@pytest.mark.parametrize("precision", ["fp64", "emu5"])
+def test_select_rows_matches_oracle_on_the_batch(precision):
+    """scfgp_select_rows: per-batch cost / gradient / alpha / Li equal the oracle on (X[batch], y[batch])
+    (SCFGP.py:226-231: train_iter_func(X[batch], y[batch])); the resident set is not uploaded again."""
+    N, D, S, M = 3000, 8, 4, 40
+    X, y, h = synth.make_problem(N, D, S, M, seed=21)
+    eng = Engine(D, S, M, precision=precision)
+    eng.set_data(X, y)
+    rng = np.random.default_rng(5)
+    for nb in (150, 1, 1000):
+        idx = rng.permutation(N)[:nb]
+        eng.select_rows(idx)
+        c, g, al, Li = eng.eval(h)
+        c0, g0, al0, Li0 = O.streaming_eval(h, X[idx], y[idx], S, M)
+        assert abs(c - c0) <= COST_RTOL * abs(c0)
+        assert rel(g[:3 + D * S + M * S], g0[:3 + D * S + M * S]) <= GRAD_RTOL
+        assert np.abs(al - al0).max() <= PRED_TOL * max(1.0, np.abs(al0).max())
+        assert np.abs(Li - Li0).max() <= PRED_TOL * max(1.0, np.abs(Li0).max())
+    eng.select_rows(None)                                   # back to the whole set
+    c, _, _, _ = eng.eval(h)
+    c0 = O.streaming_eval(h, X, y, S, M, want_grad=False)[0]
+    assert abs(c - c0) <= COST_RTOL * abs(c0)
+    with pytest.raises(ValueError):
+        eng.select_rows(np.array([N]))                      # out of range
+    eng.close()
+
+
+def test_empty_local_batch_contributes_nothing():
+    """A rank whose shard holds no row of the current batch (n = 0): its three partial reductions are zero, so
+    the sum over shards is the other shard's -- checked through the phase API like test_shard_additivity."""
+    N, D, S, M = 600, 5, 3, 20
+    X, y, h = synth.make_problem(N, D, S, M, seed=23)
+    eng = Engine(D, S, M)
+    eng.set_data(X, y)
+    eng.select_rows(np.zeros(0, dtype=np.int64), n_global=100)
+    lib, hd = eng.lib, eng._h
+    eng._check(lib.scfgp_eval_begin(hd, _lib.dptr(_lib.as_f64(h)), 1))
+    eng._check(lib.scfgp_eval_pass1(hd))
+    red1 = eng._reduce_tensor(1).cpu().numpy()
+    assert np.all(red1 == 0.0)
+    eng.close()
+
+
+def test_facade_minibatch_with_device_resident_training_set():
+    """nbatches > 1 with CUDA tensors (scaler_device='gpu'): batches are gathered on the device."""
+    import torch
+    rng = np.random.default_rng(14)
+    N, D = 2000, 6
+    X = rng.lognormal(size=(N, D))
+    yraw = np.sin(X.sum(1) / 3) + 0.1 * rng.standard_normal(N)
+    np.random.seed(3)
+    m = SCFGP(rank=3, feature_size=20, scaler_device="gpu")
+    m.set_data(torch.as_tensor(X, device="cuda"), torch.as_tensor(yraw, device="cuda"))
+    m.optimize(max_iter=12, nbatches=3, batchsize=200)
+    costs = m.evals["COST"][1]
+    assert len(costs) == 13 and np.all(np.isfinite(costs)) and costs[-2] < costs[0]
+    assert m._engine.N == N                                  # the final train_func ran on the whole set

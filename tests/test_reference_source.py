@@ -39,6 +39,10 @@ class OracleEngine:
 
     def set_data(self, X, y, n_global=None):
         self.X, self.y = X, np.asarray(y).reshape(-1)
+        self.fullX, self.fully = self.X, self.y
+
+    def select_rows(self, idx=None, n_global=None):
+        self.X, self.y = (self.fullX, self.fully) if idx is None else (self.fullX[idx], self.fully[idx])
 
     def eval(self, h, want_grad=True, **_):
         return O.streaming_eval(h, self.X, self.y, self.S, self.M, want_grad=want_grad)
