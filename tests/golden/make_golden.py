@@ -18,110 +18,21 @@ Output (committed): ``tests/golden/boston_scfgp_golden.npz`` with
 Run from the repo root in the build container (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 """
-import collections
-import hashlib
-import io
 import os
-import pickle
 import sys
-import threading
 
 import numpy as np
 
-SRC = "/root/reference/experiments/boston_housing/boston_scfgp.pkl"
-DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "boston_scfgp_golden.npz")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
+from oracle.restricted_pickle import BOSTON_PKL as SRC, load_stub_tree, walk_arrays  # noqa: E402
 
-class _Stub:
-    """Inert stand-in for any non-NumPy class named by the pickle."""
-
-    def __new__(cls, *a, **k):
-        o = object.__new__(cls)
-        o.__dict__["_args"] = a
-        o.__dict__["_state"] = None
-        o.__dict__["_items"] = []
-        return o
-
-    def __init__(self, *a, **k):
-        pass
-
-    def __setstate__(self, st):
-        self.__dict__["_state"] = st
-
-    def __call__(self, *a, **k):
-        return _Stub()
-
-    def append(self, x):
-        self._items.append(x)
-
-    def extend(self, xs):
-        self._items.extend(xs)
-
-    def __setitem__(self, k, v):
-        self._items.append((k, v))
-
-    def __hash__(self):
-        return id(self)
-
-    def __eq__(self, o):
-        return self is o
-
-
-def _make_stub_class(module, name):
-    return type(name, (_Stub,), {"__module__": "stub." + module})
-
-
-_ALLOWED = {
-    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
-    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
-    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy", "float64"), ("numpy", "int64"),
-    ("numpy", "int8"), ("numpy", "bool_"),
-    ("builtins", "slice"), ("builtins", "set"), ("builtins", "frozenset"),
-    ("__builtin__", "slice"), ("__builtin__", "set"), ("__builtin__", "frozenset"),
-    ("collections", "OrderedDict"),
-}
-
-
-class RestrictedUnpickler(pickle.Unpickler):
-    def find_class(self, module, name):
-        if (module, name) in _ALLOWED:
-            if module.startswith("numpy.core"):
-                module = module.replace("numpy.core", "numpy._core")
-            if module == "__builtin__":
-                module = "builtins"
-            return super().find_class(module, name)
-        return _make_stub_class(module, name)
-
-
-def _walk(obj, seen, out, depth=0):
-    """Collect every ndarray reachable from the stub tree."""
-    if id(obj) in seen:
-        return
-    seen.add(id(obj))
-    if isinstance(obj, np.ndarray):
-        out.append(obj)
-        return
-    if isinstance(obj, _Stub):
-        for v in list(vars(obj).values()):
-            _walk(v, seen, out, depth + 1)
-    elif isinstance(obj, dict):
-        for k, v in obj.items():
-            _walk(k, seen, out, depth + 1)
-            _walk(v, seen, out, depth + 1)
-    elif isinstance(obj, (list, tuple, set, frozenset)):
-        for v in obj:
-            _walk(v, seen, out, depth + 1)
-
-
-def _load():
-    with open(SRC, "rb") as f:
-        raw = f.read()
-    print("sha256", hashlib.sha256(raw).hexdigest())
-    return RestrictedUnpickler(io.BytesIO(raw), encoding="latin1").load()
+DST = os.path.join(HERE, "boston_scfgp_golden.npz")
 
 
 def main():
-    top = _load()
+    top = load_stub_tree(SRC)      # restricted unpickler: NumPy arrays + inert stubs, nothing is executed
     assert isinstance(top, dict), type(top)
     print("keys:", sorted(top.keys()))
     Li = np.asarray(top["Li"], dtype=np.float64)
@@ -129,8 +40,7 @@ def main():
     M = int(top["M"])
     K = Li.shape[0]
     S = K // 2 - M
-    arrs = []
-    _walk(top["train_func"], set(), arrs)
+    arrs = walk_arrays(top["train_func"])
     cands = [a for a in arrs if a.dtype == np.float64 and a.ndim == 1 and a.size > 100]
     sizes = sorted({a.size for a in cands})
     print("1-D float64 arrays under train_func:", sizes)
@@ -166,8 +76,4 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.setrecursionlimit(1000000)
-    threading.stack_size(512 * 1024 * 1024)
-    t = threading.Thread(target=main)
-    t.start()
-    t.join()
+    main()
