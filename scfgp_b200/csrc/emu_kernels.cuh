@@ -96,6 +96,20 @@ __device__ __forceinline__ void unpack5x4(const uint32_t (&w)[5], double (&q)[4]
   }
 }
 
+// the same as exact integers (byte permutes and one 64-bit add per element; the caller converts once)
+__device__ __forceinline__ void unpack5x4_q(const uint32_t (&w)[5], long long (&q)[4]) {
+  const uint32_t u1 = fix_bytes(w[1]), u2 = fix_bytes(w[2]), u3 = fix_bytes(w[3]), u4 = fix_bytes(w[4]);
+  const uint32_t a = __byte_perm(u4, u3, 0x5140), b = __byte_perm(u4, u3, 0x7362);
+  const uint32_t c = __byte_perm(u2, u1, 0x5140), d = __byte_perm(u2, u1, 0x7362);
+  const uint32_t lo[4] = {__byte_perm(a, c, 0x5410), __byte_perm(a, c, 0x7632), __byte_perm(b, d, 0x5410),
+                          __byte_perm(b, d, 0x7632)};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const long long hi = (long long)(int8_t)(w[0] >> (8 * e));
+    q[e] = (hi << 32) + (long long)lo[e] - 2155905152ll;   // q' = q + 0x80808080
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // per-row power-of-two scales of [M1 | f2 * M2] (either may be absent)
 //   scale[p(r)] = pow2_ceil(max_c |row r|), inv[p(r)] = 1 / scale
@@ -694,16 +708,40 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         for (int i = 0; i < 8; ++i) qc[i] = qs[i] = 0;
         if (rvalid && f0 < J) {
           const int8_t* dp = dphi + (long long)(row0 + r) * dpitch + f0;
+          if constexpr (KS == 5) {
+            // five plane words per 4 features: byte permutes instead of a 5-step Horner chain per value
+            uint32_t wc0[5], wc1[5], ws0[5], ws1[5];
 #pragma unroll
-          for (int d = 0; d < KS; ++d) {
-            const uint2 wc = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane);
-            const uint2 ws = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane + J);
+            for (int d = 0; d < 5; ++d) {
+              const uint2 wc = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane);
+              const uint2 ws = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane + J);
+              wc0[d] = wc.x; wc1[d] = wc.y; ws0[d] = ws.x; ws1[d] = ws.y;
+            }
+            long long t4[4];
+            unpack5x4_q(wc0, t4);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t bc = (i < 4 ? wc.x : wc.y) >> (8 * (i & 3));
-              const uint32_t bs = (i < 4 ? ws.x : ws.y) >> (8 * (i & 3));
-              qc[i] = qc[i] * 256 + (long long)(int8_t)bc;
-              qs[i] = qs[i] * 256 + (long long)(int8_t)bs;
+            for (int i = 0; i < 4; ++i) qc[i] = t4[i];
+            unpack5x4_q(wc1, t4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qc[4 + i] = t4[i];
+            unpack5x4_q(ws0, t4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qs[i] = t4[i];
+            unpack5x4_q(ws1, t4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qs[4 + i] = t4[i];
+          } else {
+#pragma unroll
+            for (int d = 0; d < KS; ++d) {
+              const uint2 wc = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane);
+              const uint2 ws = *reinterpret_cast<const uint2*>(dp + (long long)d * dplane + J);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t bc = (i < 4 ? wc.x : wc.y) >> (8 * (i & 3));
+                const uint32_t bs = (i < 4 ? ws.x : ws.y) >> (8 * (i & 3));
+                qc[i] = qc[i] * 256 + (long long)(int8_t)bc;
+                qs[i] = qs[i] * 256 + (long long)(int8_t)bs;
+              }
             }
           }
         }
@@ -731,11 +769,26 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           sacc += pc * phc + ps * phs;
         }
       }
-      // column sums over this warp's 32 rows: features f0 .. f0+7
+      // column sums over this warp's 32 rows (features f0 .. f0+7) as a reduce-scatter: every step halves the
+      // values a lane carries (9 additions and 9 shuffles per lane instead of 40 for eight butterflies); lanes
+      // 4 k .. 4 k + 3 end up with the sum of feature f0 + k.  Fixed order: results repeat bit for bit.
+      {
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        double a4[4], a2[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const double cs = warp_sum(zb[i]);
-        if (lane == 0) shcol[warp - umma::EPI_WARP0][h16 * 8 + i] = cs;
+        for (int k = 0; k < 4; ++k) {
+          const double keep = b4 ? zb[4 + k] : zb[k], give = b4 ? zb[k] : zb[4 + k];
+          a4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const double keep = b3 ? a4[2 + k] : a4[k], give = b3 ? a4[k] : a4[2 + k];
+          a2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+        }
+        double cs = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
+        cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+        cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+        if ((lane & 3) == 0) shcol[warp - umma::EPI_WARP0][h16 * 8 + (lane >> 2)] = cs;
       }
     }
     sacc = warp_sum(sacc);

@@ -34,7 +34,7 @@ __global__ void k_mma_stream(int steps, int random_data, long long* out /*[2 per
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  if (warp == 1 && lane == 0) {
+  if (warp == 1 && elect_one()) {
     const uint32_t sa = smem_u32(base), sb = sa + G::A_BYTES;
     constexpr int MAXCNT = G::MAXCNT;
     const long long t0 = clock64();

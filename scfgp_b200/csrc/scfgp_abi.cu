@@ -381,7 +381,7 @@ int scfgp_select_rows(scfgp_handle* h, const long long* idx, long long n, long l
   }
   for (long long i = 0; i < n; ++i)
     if (idx[i] < 0 || idx[i] >= h->fullN) { h->err = "select_rows: row index out of range"; return SCFGP_ERR_ARG; }
-  if (n > h->sel_cap) {
+  if (n > h->sel_cap || h->selX == nullptr) {
     CK(cudaStreamSynchronize(h->stream));
     for (void* p : {(void*)h->selX, (void*)h->sely, (void*)h->selidx}) if (p) cudaFree(p);
     h->selX = h->sely = nullptr; h->selidx = nullptr; h->sel_cap = 0;

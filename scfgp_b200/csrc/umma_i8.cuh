@@ -49,7 +49,7 @@ constexpr int EPI_THREADS = 256;
 constexpr int MAX_REGS = 96;  // per thread: 320 x 96 leaves more than half of the register file to co-resident kernels
 // two-phase epilogue (KS <= 5): a thread parks its TNW / 2 recombined accumulators as int64 (up to 96 registers at
 // TNW = 96) so that tensor memory goes back to the MMA warp before the fused epilogue math starts
-constexpr int MAX_REGS_2PHASE = 184;
+constexpr int MAX_REGS_2PHASE = 168;  // 10 warps: one scheduler partition (16 K registers) hosts 3 of them -> at most 170 per thread
 
 // TNW: tile columns per class.  64: four B digits per instruction (N = 256), every digit count; 96: two B digits
 // per instruction (N = 192), 20 % fewer operand bytes per digit product, at most 5 digits (480 class columns).
@@ -99,6 +99,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// one lane of a converged warp (elect.sync): the compiler knows the guarded region runs on a single thread and
+// keeps descriptors / addresses in uniform registers without uniformisation loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // all tcgen05.mma issued so far by this thread arrive (once) on the mbarrier when they retire
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
@@ -231,6 +245,9 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
 //   5 epilogue: acc_full -> accumulators released   6 epilogue: release -> end of the tile's epilogue
 //   7 producer waiting for free stages
 __device__ unsigned long long* g_tile_timing = nullptr;
+// (A-operand collector hints -- fill ... lastuse on the instructions that share an A digit slice -- were measured
+// as a run-time knob in round 2: no gain (profiles/r2_mma_issue_and_epilogue.txt), and the extra branch in the
+// single-thread issue loop cost 12 % on the Gram kernel.  They remain as the compile-time option UMMA_COLLECTOR.)
 constexpr int TT_SLOTS = 8;
 __device__ __forceinline__ void tt_add(unsigned long long* tt, int slot, long long v) {
   if (tt) atomicAdd(tt + (size_t)blockIdx.x * TT_SLOTS + slot, (unsigned long long)v);
@@ -323,7 +340,7 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
   const int nkb = (t.c_end - t.c_begin + KB - 1) / KB;
   unsigned long long* const tt = g_tile_timing;
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       long long w_empty = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int it = it0 + kb;
@@ -350,7 +367,7 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
       tt_add(tt, 7, w_empty);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const long long t_begin = tt ? clock64() : 0;
       long long w_full = 0;
       if (seq > 0) {
@@ -368,6 +385,10 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         tc_fence_after();
         const uint32_t sa = smem_u32(p.stages + (size_t)st * G::STAGE_BYTES);
         const uint32_t sb = sa + G::A_BYTES;
+        // descriptors of the stage's first A / B digit block; every instruction adds a compile-time offset to
+        // the 14-bit start-address field (16-byte units; the sum is a valid shared-memory address, no carry out)
+        const uint64_t adesc0 = TR ? smem_desc_mn(sa, 0, 8 * TM, 2 /*SWIZZLE_128B*/) : smem_desc_sw64(sa);
+        const uint64_t bdesc0 = TR ? smem_desc_mn(sb, TNW * KB, 8 * TNW, 4 /*SWIZZLE_64B*/) : smem_desc_sw64(sb);
 #if UMMA_A_TMEM
         // A digits staged into tensor memory behind the class accumulators (double-buffered per stage)
         const uint32_t abuf = tmem_base + (uint32_t)(TNW * KS + (it & 1) * (KS * 16));
@@ -399,14 +420,11 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
 #pragma unroll
           for (int i = 0; i < KS; ++i) {
             // one digit block is TM x KB = KB x TM bytes in either layout
-            const uint64_t adesc = TR ? smem_desc_mn(sa + i * (TM * KB) + ks * 32 * TM, 0, 8 * TM, 2 /*SWIZZLE_128B*/)
-                                      : smem_desc_sw64(sa + i * (TM * KB) + ks * 32);
+            const uint64_t adesc = adesc0 + (uint64_t)((i * (TM * KB) + ks * 32 * (TR ? TM : 1)) >> 4);
 #pragma unroll
             for (int j0 = 0; j0 < KS - i; j0 += MAXCNT) {
               const int cnt = (KS - i - j0) < MAXCNT ? (KS - i - j0) : MAXCNT;
-              const uint64_t bdesc =
-                  TR ? smem_desc_mn(sb + j0 * (TNW * KB) + ks * 32 * TNW, TNW * KB, 8 * TNW, 4 /*SWIZZLE_64B*/)
-                     : smem_desc_sw64(sb + j0 * (TNW * KB) + ks * 32);
+              const uint64_t bdesc = bdesc0 + (uint64_t)((j0 * (TNW * KB) + ks * 32 * (TR ? TNW : 1)) >> 4);
               const uint32_t acc = (kb == 0 && ks == 0 && i == 0) ? 0u : 1u;
 #if UMMA_PROBE_MODE != 1
 #if UMMA_A_TMEM
@@ -416,8 +434,8 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
               else
 #endif
 #if UMMA_COLLECTOR
-              if (KS - i > 4) {   // two instructions share this A slice
-                if (j0 == 0)
+              if (KS - i > MAXCNT) {   // several instructions share this A slice
+                if (j0 + MAXCNT < KS - i)            // not the last one: (re)fill the collector
                   mma_i8_coll<1>(tmem_base + (uint32_t)(TNW * (i + j0)), adesc, bdesc,
                                  TR ? idesc_i8_mn(TNW * cnt) : idesc_i8(TNW * cnt), acc);
                 else
