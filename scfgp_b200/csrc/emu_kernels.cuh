@@ -821,6 +821,226 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   umma::pipe_teardown<KS, TNW>(p, tmem_base);
 }
 
+// ------------------------------------------------------------------------------------
+// backward tile, two-phase epilogue (KS <= 5; the default).  Same mathematics and outputs as k_backward_i8; the
+// epilogue is organised around what bounds it once the MMA stream runs at full rate: global-memory latency under
+// the TMA traffic.  Per tile the epilogue warps
+//   1. stage the tile's column vectors (cscale * sc, pbar, alpha of the TNW permuted columns) in shared memory and
+//      start the loads of the first group's Phi digits -- all while the MMAs of the tile are still running,
+//   2. drain: park the exactly recombined accumulators (int64) and hand tensor memory back to the MMA warp,
+//   3. run the fused math per group of 16 columns with the next group's Phi digits already in flight.
+// ------------------------------------------------------------------------------------
+struct PhiWords5 { uint32_t c0[5], c1[5], s0[5], s1[5]; };   // digit planes of 8 cos + 8 sin features of one row
+
+template <int KS, int TNW>
+__global__ void __maxnreg__(umma::MAX_REGS_2PHASE)
+k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapC, int seg1_stages, int row0, const int8_t* __restrict__ dphi,
+                 long long dpitch, long long dplane, double recon, int rows, int J,
+                 int depth2, int ntiles, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
+                 long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
+                 const double* __restrict__ pbar, const double* __restrict__ alpha, double* __restrict__ Zbar,
+                 long long ldz, double* __restrict__ slots, double* __restrict__ dphi_part, long long ldpart) {
+  static_assert(KS <= 5, "two-phase epilogue: exact int64 recombination");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ double sh[8];
+  __shared__ double shcol[8][TNW / 4];   // per epilogue warp: column sums of its TNW / 4 features
+  __shared__ double colv[3][TNW];        // per permuted tile column: cscale * sc, pbar, alpha
+  umma::Pipe p = umma::pipe_init<KS, TNW>(smem_raw);
+  const uint32_t tmem_base = *p.tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool front = warp < umma::EPI_WARP0;
+  constexpr int FPT = TNW / 2;             // features per tile (cos/sin column pairs)
+  constexpr int NG = TNW / 32;             // groups of 16 columns (8 features) per thread
+  const int nfb = (J + FPT - 1) / FPT;
+  const double sc = sA * umma::PROD_SCALE;
+  int it0 = 0, seq = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
+    umma::Tile t;
+    t.m0 = (tile / nfb) * TM;     // row-block major: consecutive tiles share the A operand in L2
+    t.n0 = (tile % nfb) * TNW;
+    t.c_begin = 0;
+    t.c_end = depth2;
+    t.mapA1 = &mapA1;
+    t.seg1_stages = seg1_stages;
+    t.seg1_row_off = row0;
+    if (front) {
+      umma::run_mainloop<KS, false, TNW>(p, tmem_base, &mapA, &mapC, t, it0, seq);
+      it0 += umma::tile_stages(t);
+      continue;
+    }
+    unsigned long long* const tt = (threadIdx.x == umma::EPI_WARP0 * 32) ? umma::g_tile_timing : nullptr;
+    const long long tt0 = tt ? clock64() : 0;
+    // ---- 1. while the tile's MMAs run: row scalars, column vectors, first Phi digits
+    const int quarter = warp & 3, half = (warp - umma::EPI_WARP0) >> 2;
+    const int r = t.m0 + quarter * 32 + lane;
+    const int col0 = half * (TNW / 2);
+    const bool rvalid = r < rows;
+    const double yn = rvalid ? y[r] : 0.0, gm = rvalid ? gmu[r] : 0.0;
+    const double* prow = Phi + (long long)(rvalid ? r : 0) * ldp;
+    const int8_t* drow = dphi ? dphi + (long long)(row0 + (rvalid ? r : 0)) * dpitch : nullptr;
+    auto load_words = [&](int g, PhiWords5& w) {
+      const int f0 = (t.n0 + col0 + 16 * g) >> 1;
+      const bool ok = rvalid && f0 < J;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        uint2 wc = make_uint2(0x80808080u, 0x80808080u), ws = wc;   // (planes 1..4 of q = 0; plane 0 fixed below)
+        if (d == 0) wc = ws = make_uint2(0u, 0u);
+        if (ok && d < KS) {
+          wc = *reinterpret_cast<const uint2*>(drow + (long long)d * dplane + f0);
+          ws = *reinterpret_cast<const uint2*>(drow + (long long)d * dplane + J + f0);
+        }
+        w.c0[d] = wc.x; w.c1[d] = wc.y; w.s0[d] = ws.x; w.s1[d] = ws.y;
+      }
+    };
+    // the next group's digit words are pulled into L1 while the current group is processed (no registers held)
+    auto prefetch_words = [&](int g) {
+      const int f0 = (t.n0 + col0 + 16 * g) >> 1;
+      if (rvalid && f0 < J) {
+#pragma unroll
+        for (int d = 0; d < KS; ++d) {
+          asm volatile("prefetch.global.L1 [%0];\n" ::"l"(drow + (long long)d * dplane + f0));
+          asm volatile("prefetch.global.L1 [%0];\n" ::"l"(drow + (long long)d * dplane + J + f0));
+        }
+      }
+    };
+    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");   // everyone is done with the previous tile
+    for (int c = threadIdx.x - umma::EPI_WARP0 * 32; c < 3 * TNW; c += umma::EPI_THREADS) {
+      const int which = c / TNW, cc = c - which * TNW;
+      const int pj = t.n0 + cc, f = pj >> 1, hf = pj & 1;
+      double v = 0.0;
+      if (f < J) v = which == 0 ? cscale[pj] * sc : (which == 1 ? pbar[hf * J + f] : alpha[hf * J + f]);
+      colv[which][cc] = v;
+    }
+    if (dphi != nullptr) prefetch_words(0);
+    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");   // column vectors visible
+    // ---- 2. drain
+    const umma::EpiPos e = umma::epilogue_wait<TNW>(p, tmem_base, seq & 1);
+    const long long tt1 = tt ? clock64() : 0;
+    long long parked[NG][16];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) umma::epilogue_drain16<KS, TNW>(e, col0 + 16 * g, parked[g]);
+    umma::epilogue_release(p);
+    const long long tt2 = tt ? clock64() : 0;
+    // ---- 3. fused math on the parked values
+    double sacc = 0;
+    PhiWords5 wcur;
+    if (dphi != nullptr) load_words(0, wcur);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int pcol = col0 + 16 * g;                     // permuted tile column of this group's first value
+      const int f0 = (t.n0 + pcol) >> 1;
+      if (dphi != nullptr && g + 1 < NG) prefetch_words(g + 1);      // in flight during this group's math
+      double zb[8];
+#pragma unroll
+      for (int hq = 0; hq < 2; ++hq) {                    // four features at a time (keeps the live set small)
+        double phc4[4], phs4[4];
+        if (dphi != nullptr) {
+          if constexpr (KS == 5) {
+            long long q4[4];
+            unpack5x4_q(hq ? wcur.c1 : wcur.c0, q4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) phc4[i] = (double)q4[i] * recon;
+            unpack5x4_q(hq ? wcur.s1 : wcur.s0, q4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) phs4[i] = (double)q4[i] * recon;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              long long qc = 0, qs = 0;
+#pragma unroll
+              for (int d = 0; d < KS; ++d) {
+                qc = qc * 256 + (long long)(int8_t)((hq ? wcur.c1[d] : wcur.c0[d]) >> (8 * i));
+                qs = qs * 256 + (long long)(int8_t)((hq ? wcur.s1[d] : wcur.s0[d]) >> (8 * i));
+              }
+              phc4[i] = (double)qc * recon; phs4[i] = (double)qs * recon;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = rvalid && f0 + 4 * hq + i < J;
+            phc4[i] = ok ? prow[f0 + 4 * hq + i] : 0.0;
+            phs4[i] = ok ? prow[J + f0 + 4 * hq + i] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int i = 4 * hq + i4;
+          const int f = f0 + i, cc = pcol + 2 * i;
+          zb[i] = 0.0;
+          if (rvalid && f < J) {
+            const double pc = umma::drained_value<KS>(parked[g][2 * i]) * colv[0][cc] + yn * colv[1][cc] + gm * colv[2][cc];
+            const double ps = umma::drained_value<KS>(parked[g][2 * i + 1]) * colv[0][cc + 1] + yn * colv[1][cc + 1] +
+                              gm * colv[2][cc + 1];
+            zb[i] = -pc * phs4[i4] + ps * phc4[i4];
+            sacc += pc * phc4[i4] + ps * phs4[i4];
+          }
+        }
+      }
+      if (rvalid) {                                       // 8 neighbouring features of one row: 16-byte stores
+        double* zrow = Zbar + (long long)r * ldz + f0;
+        if (f0 + 7 < J && (ldz & 1) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) *reinterpret_cast<double2*>(zrow + i) = make_double2(zb[i], zb[i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (f0 + i < J) zrow[i] = zb[i];
+        }
+      }
+      // column sums over this warp's 32 rows as a reduce-scatter (9 additions and 9 shuffles per lane); lanes
+      // 4 k .. 4 k + 3 end up with the sum of feature f0 + k.  Fixed order: results repeat bit for bit.
+      {
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        double a4[4], a2[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double keep = b4 ? zb[4 + k] : zb[k], give = b4 ? zb[k] : zb[4 + k];
+          a4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const double keep = b3 ? a4[2 + k] : a4[k], give = b3 ? a4[k] : a4[2 + k];
+          a2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+        }
+        double cs = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
+        cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+        cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+        if ((lane & 3) == 0) shcol[warp - umma::EPI_WARP0][g * 8 + (lane >> 2)] = cs;
+      }
+      if (dphi != nullptr && g + 1 < NG) load_words(g + 1, wcur);
+    }
+    sacc = warp_sum(sacc);
+    if (lane == 0) sh[warp - umma::EPI_WARP0] = sacc;
+    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");
+    if (warp == umma::EPI_WARP0) {
+      if (lane == 0) {
+        double sum = 0;
+        for (int w = 0; w < 8; ++w) sum += sh[w];
+        slots[tile] += sum;
+      }
+      // warps w and w+4 hold column halves 0 / 1; their 4 lane quarters are the 4 row groups
+      for (int fi = lane; fi < FPT; fi += 32) {           // features of the tile: half * (FPT / 2) + k
+        const int hh = fi / (FPT / 2), k = fi % (FPT / 2);
+        const int f = (t.n0 >> 1) + fi;
+        if (f < J) {
+          double cs = 0;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) cs += shcol[hh * 4 + qd][k];   // the 4 row quarters, fixed order
+          dphi_part[(long long)(tile / nfb) * ldpart + f] += cs;
+        }
+      }
+    }
+    if (tt) {
+      umma::tt_add(tt, 4, tt1 - tt0);
+      umma::tt_add(tt, 5, tt2 - tt1);
+      umma::tt_add(tt, 6, clock64() - tt2);
+    }
+  }
+  umma::pipe_teardown<KS, TNW>(p, tmem_base);
+}
+
 // generic C[m][n] = sum_c A[m,c] B[n,c] with per-row scales on both sides (self-test hook)
 template <int KS>
 __global__ void __maxnreg__(umma::MAX_REGS)

@@ -151,14 +151,30 @@ int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache
   // the epilogue rebuilds Phi from the cached digits (8-byte loads: needs J % 8 == 0), else reads the slab
   const bool phi_from_digits = use_cache && h->J % 8 == 0;
   const double recon = h->s2 * std::ldexp(1.0, -(8 * std::max(h->cache_ks, 1) - 1));
+  const int grid = std::min(ntiles, h->num_sms);
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
-  EMU_TILE_LAUNCH(k_backward_i8, std::min(ntiles, h->num_sms), c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA,
-                  h->mapCB, use_cache ? (int)(h->Kp / umma::KB) : 0, use_cache ? (int)r0 : 0,
-                  phi_from_digits ? h->phi_cache : nullptr, h->Kc, h->cache_rows * h->Kc, recon, rows, h->J,
-                  (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0, h->pbar,
-                  h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K);
+#define BWD_ARGS                                                                                                     \
+  c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA, h->mapCB, use_cache ? (int)(h->Kp / umma::KB) : 0,              \
+      use_cache ? (int)r0 : 0, phi_from_digits ? h->phi_cache : nullptr, h->Kc, h->cache_rows * h->Kc, recon, rows,  \
+      h->J, (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0, h->pbar,          \
+      h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K
+  if (h->two_phase && h->ks2 <= 5) {
+    if (h->tnw == 96) {
+      if (h->ks2 != 5) { h->err = "wide tiles are built for 5 digits"; return SCFGP_ERR_ARG; }
+      emu::k_backward_i8_2p<5, 96><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(BWD_ARGS);
+    } else if (h->ks2 == 4) {
+      emu::k_backward_i8_2p<4, 64><<<grid, umma::THREADS, umma::Geo<4>::SMEM, c.sg>>>(BWD_ARGS);
+    } else {
+      emu::k_backward_i8_2p<5, 64><<<grid, umma::THREADS, umma::Geo<5>::SMEM, c.sg>>>(BWD_ARGS);
+    }
+  } else if (h->tnw == 96) {
+    emu::k_backward_i8<5, 96, false><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(BWD_ARGS);
+  } else {
+    EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS, 64, false><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(BWD_ARGS));
+  }
+#undef BWD_ARGS
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
   return gemm_leave(h, c);

@@ -259,9 +259,9 @@ int set_emu_attrs(scfgp_handle* h) {
   CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 64, false>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   if constexpr (KS <= 5) {
     CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8_2p<KS, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 64, true>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 64, true>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8_2p<KS, 64>), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
   CK(cudaFuncSetAttribute(emu::k_gemm_i8_dbg<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int mx = (int)cudaSharedmemCarveoutMaxShared;
@@ -272,9 +272,9 @@ int set_emu_attrs(scfgp_handle* h) {
   if constexpr (KS == 5) {   // wide (96-column) tiles of the two K-major products
     const int smw = (int)umma::Geo<KS, 96>::SMEM;
     CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
-    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8_2p<KS, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
     CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, true>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
-    CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96, true>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+    CK(cudaFuncSetAttribute((emu::k_backward_i8_2p<KS, 96>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));
     CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
     CK(cudaFuncSetAttribute((emu::k_backward_i8<KS, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smw));
     CK(cudaFuncSetAttribute((emu::k_tgemm_i8<KS, 96, false>), cudaFuncAttributePreferredSharedMemoryCarveout, mx));

@@ -571,21 +571,42 @@ __device__ __forceinline__ void tmem_ld16_landed(uint32_t (&r)[16], bool wait) {
 template <int KS, int TNW = TN>
 __device__ __forceinline__ void epilogue_drain16(const EpiPos& e, int col, long long (&s)[16]) {
   static_assert(KS <= 5, "exact int64 recombination needs 8 (KS - 1) + 31 < 63");
-  uint32_t r[KS][16];
+  // two batches of classes (3 + the rest): at most 48 transient registers on top of the parked values
+  constexpr int B0 = KS < 3 ? KS : 3;
+  {
+    uint32_t r[B0][16];
 #pragma unroll
-  for (int q = 0; q < KS; ++q) tmem_ld16_issue(e.lane_base + (uint32_t)(q * TNW + col), r[q]);
+    for (int q = 0; q < B0; ++q) tmem_ld16_issue(e.lane_base + (uint32_t)(q * TNW + col), r[q]);
 #pragma unroll
-  for (int q = 0; q < KS; ++q) tmem_ld16_landed(r[q], q == 0);
+    for (int q = 0; q < B0; ++q) tmem_ld16_landed(r[q], q == 0);
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    long long a = (long long)(int)r[KS - 1][c];
+    for (int c = 0; c < 16; ++c) {
+      long long a = 0;
 #pragma unroll
-    for (int q = KS - 2; q >= 0; --q) {
-      const int sh = DIGIT_BITS * (KS - 1 - q);
-      if (sh < 31) a += (long long)(int)r[q][c] * (long long)(1 << sh);   // mul.wide.s32 + add
-      else a += (long long)(int)r[q][c] << sh;
+      for (int q = 0; q < B0; ++q) {
+        const int sh = DIGIT_BITS * (KS - 1 - q);
+        if (sh < 31) a += (long long)(int)r[q][c] * (long long)(1 << sh);   // mul.wide.s32 + add
+        else a += (long long)(int)r[q][c] << sh;
+      }
+      s[c] = a;
     }
-    s[c] = a;
+  }
+  if constexpr (KS > B0) {
+    uint32_t r[KS - B0][16];
+#pragma unroll
+    for (int q = B0; q < KS; ++q) tmem_ld16_issue(e.lane_base + (uint32_t)(q * TNW + col), r[q - B0]);
+#pragma unroll
+    for (int q = B0; q < KS; ++q) tmem_ld16_landed(r[q - B0], q == B0);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      long long a = s[c];
+#pragma unroll
+      for (int q = B0; q < KS; ++q) {
+        const int sh = DIGIT_BITS * (KS - 1 - q);
+        a += (long long)(int)r[q - B0][c] * (long long)(1 << sh);
+      }
+      s[c] = a;
+    }
   }
 }
 // phase 2: the parked integer as a float64 (one rounding; exact below 2^53)
