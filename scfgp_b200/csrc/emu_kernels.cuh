@@ -822,13 +822,17 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------
-// backward tile, two-phase epilogue (KS <= 5; the default).  Same mathematics and outputs as k_backward_i8; the
-// epilogue is organised around what bounds it once the MMA stream runs at full rate: global-memory latency under
-// the TMA traffic.  Per tile the epilogue warps
-//   1. stage the tile's column vectors (cscale * sc, pbar, alpha of the TNW permuted columns) in shared memory and
-//      start the loads of the first group's Phi digits -- all while the MMAs of the tile are still running,
-//   2. drain: park the exactly recombined accumulators (int64) and hand tensor memory back to the MMA warp,
-//   3. run the fused math per group of 16 columns with the next group's Phi digits already in flight.
+// backward tile, two-phase epilogue (KS <= 5; the default).  Same Zbar as k_backward_i8.  What bounds this epilogue
+// is the FP64 pipe: while the tcgen05.mma stream of the next tile runs, every DMUL / DFMA / DADD of the epilogue
+// warps waits for the pipe for ~300 cycles ("math pipe throttle" is half of all stall samples,
+// profiles/r2_ncu_backward_stalls.txt), so the kernel is built around the FP64 instruction count:
+//   * the accumulators are recombined exactly in int64 on the integer pipes and parked, tensor memory goes back
+//     to the MMA warp at once (phase 1);
+//   * all scales are folded into three per-column vectors staged in shared memory (cscale sA 2^-14 2^-32 recon,
+//     pbar recon, alpha recon): Phibar costs one DMUL + two DFMA per value, Zbar one DMUL + one DFMA per feature
+//     on the integer-valued Phi digits;
+//   * the reductions left the kernel: sbar = sum <Phibar, Phi> is a pair of K x K traces in the dense backward
+//     phase (k_sbar_rows), dphi = colsum(Zbar) a side kernel over the Zbar slab (k_colsum).
 // ------------------------------------------------------------------------------------
 struct PhiWords5 { uint32_t c0[5], c1[5], s0[5], s1[5]; };   // digit planes of 8 cos + 8 sin features of one row
 
@@ -840,12 +844,10 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                  int depth2, int ntiles, const double* __restrict__ cscale, double sA, const double* __restrict__ Phi,
                  long long ldp, const double* __restrict__ y, const double* __restrict__ gmu,
                  const double* __restrict__ pbar, const double* __restrict__ alpha, double* __restrict__ Zbar,
-                 long long ldz, double* __restrict__ slots, double* __restrict__ dphi_part, long long ldpart) {
+                 long long ldz) {
   static_assert(KS <= 5, "two-phase epilogue: exact int64 recombination");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ double sh[8];
-  __shared__ double shcol[8][TNW / 4];   // per epilogue warp: column sums of its TNW / 4 features
-  __shared__ double colv[3][TNW];        // per permuted tile column: cscale * sc, pbar, alpha
+  __shared__ double colv[3][TNW];        // per permuted tile column: cscale * sc * 2^-8(KS-1) * rs, pbar * rs, alpha * rs
   umma::Pipe p = umma::pipe_init<KS, TNW>(smem_raw);
   const uint32_t tmem_base = *p.tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -853,7 +855,10 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr int FPT = TNW / 2;             // features per tile (cos/sin column pairs)
   constexpr int NG = TNW / 32;             // groups of 16 columns (8 features) per thread
   const int nfb = (J + FPT - 1) / FPT;
-  const double sc = sA * umma::PROD_SCALE;
+  // Phi enters Zbar as (integer digits value q) * recon when it comes from the digit cache, as the float64 value
+  // itself otherwise: rs is the factor that is folded into the column vectors
+  const double rs = dphi != nullptr ? recon : 1.0;
+  const double sc = sA * umma::PROD_SCALE * __longlong_as_double((long long)(1023 - umma::DIGIT_BITS * (KS - 1)) << 52) * rs;
   int it0 = 0, seq = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
     umma::Tile t;
@@ -871,7 +876,7 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     unsigned long long* const tt = (threadIdx.x == umma::EPI_WARP0 * 32) ? umma::g_tile_timing : nullptr;
     const long long tt0 = tt ? clock64() : 0;
-    // ---- 1. while the tile's MMAs run: row scalars, column vectors, first Phi digits
+    // ---- 1. while the tile's MMAs run: row scalars, column vectors, first Phi digits towards L1
     const int quarter = warp & 3, half = (warp - umma::EPI_WARP0) >> 2;
     const int r = t.m0 + quarter * 32 + lane;
     const int col0 = half * (TNW / 2);
@@ -909,7 +914,7 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int which = c / TNW, cc = c - which * TNW;
       const int pj = t.n0 + cc, f = pj >> 1, hf = pj & 1;
       double v = 0.0;
-      if (f < J) v = which == 0 ? cscale[pj] * sc : (which == 1 ? pbar[hf * J + f] : alpha[hf * J + f]);
+      if (f < J) v = which == 0 ? cscale[pj] * sc : (which == 1 ? pbar[hf * J + f] : alpha[hf * J + f]) * rs;
       colv[which][cc] = v;
     }
     if (dphi != nullptr) prefetch_words(0);
@@ -922,8 +927,7 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int g = 0; g < NG; ++g) umma::epilogue_drain16<KS, TNW>(e, col0 + 16 * g, parked[g]);
     umma::epilogue_release(p);
     const long long tt2 = tt ? clock64() : 0;
-    // ---- 3. fused math on the parked values
-    double sacc = 0;
+    // ---- 3. Zbar from the parked values
     PhiWords5 wcur;
     if (dphi != nullptr) load_words(0, wcur);
 #pragma unroll
@@ -934,16 +938,16 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       double zb[8];
 #pragma unroll
       for (int hq = 0; hq < 2; ++hq) {                    // four features at a time (keeps the live set small)
-        double phc4[4], phs4[4];
+        double phc4[4], phs4[4];                          // Phi / rs of the row's features
         if (dphi != nullptr) {
           if constexpr (KS == 5) {
             long long q4[4];
             unpack5x4_q(hq ? wcur.c1 : wcur.c0, q4);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) phc4[i] = (double)q4[i] * recon;
+            for (int i = 0; i < 4; ++i) phc4[i] = (double)q4[i];
             unpack5x4_q(hq ? wcur.s1 : wcur.s0, q4);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) phs4[i] = (double)q4[i] * recon;
+            for (int i = 0; i < 4; ++i) phs4[i] = (double)q4[i];
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -953,7 +957,7 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 qc = qc * 256 + (long long)(int8_t)((hq ? wcur.c1[d] : wcur.c0[d]) >> (8 * i));
                 qs = qs * 256 + (long long)(int8_t)((hq ? wcur.s1[d] : wcur.s0[d]) >> (8 * i));
               }
-              phc4[i] = (double)qc * recon; phs4[i] = (double)qs * recon;
+              phc4[i] = (double)qc; phs4[i] = (double)qs;
             }
           }
         } else {
@@ -967,18 +971,14 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const int i = 4 * hq + i4;
-          const int f = f0 + i, cc = pcol + 2 * i;
-          zb[i] = 0.0;
-          if (rvalid && f < J) {
-            const double pc = umma::drained_value<KS>(parked[g][2 * i]) * colv[0][cc] + yn * colv[1][cc] + gm * colv[2][cc];
-            const double ps = umma::drained_value<KS>(parked[g][2 * i + 1]) * colv[0][cc + 1] + yn * colv[1][cc + 1] +
-                              gm * colv[2][cc + 1];
-            zb[i] = -pc * phs4[i4] + ps * phc4[i4];
-            sacc += pc * phc4[i4] + ps * phs4[i4];
-          }
+          const int cc = pcol + 2 * i;
+          // Phibar * rs of the cos and sin columns (exact int64 -> float64: one rounding)
+          const double pc = fma(gm, colv[2][cc], fma(yn, colv[1][cc], (double)parked[g][2 * i] * colv[0][cc]));
+          const double ps = fma(gm, colv[2][cc + 1], fma(yn, colv[1][cc + 1], (double)parked[g][2 * i + 1] * colv[0][cc + 1]));
+          zb[i] = fma(ps, phc4[i4], -(pc * phs4[i4]));
         }
       }
-      if (rvalid) {                                       // 8 neighbouring features of one row: 16-byte stores
+      if (rvalid && f0 < J) {                             // 8 neighbouring features of one row: 16-byte stores
         double* zrow = Zbar + (long long)r * ldz + f0;
         if (f0 + 7 < J && (ldz & 1) == 0) {
 #pragma unroll
@@ -989,48 +989,7 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (f0 + i < J) zrow[i] = zb[i];
         }
       }
-      // column sums over this warp's 32 rows as a reduce-scatter (9 additions and 9 shuffles per lane); lanes
-      // 4 k .. 4 k + 3 end up with the sum of feature f0 + k.  Fixed order: results repeat bit for bit.
-      {
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-        double a4[4], a2[2];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double keep = b4 ? zb[4 + k] : zb[k], give = b4 ? zb[k] : zb[4 + k];
-          a4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const double keep = b3 ? a4[2 + k] : a4[k], give = b3 ? a4[k] : a4[2 + k];
-          a2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
-        }
-        double cs = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
-        cs += __shfl_xor_sync(0xffffffffu, cs, 2);
-        cs += __shfl_xor_sync(0xffffffffu, cs, 1);
-        if ((lane & 3) == 0) shcol[warp - umma::EPI_WARP0][g * 8 + (lane >> 2)] = cs;
-      }
       if (dphi != nullptr && g + 1 < NG) load_words(g + 1, wcur);
-    }
-    sacc = warp_sum(sacc);
-    if (lane == 0) sh[warp - umma::EPI_WARP0] = sacc;
-    asm volatile("bar.sync 1, %0;\n" ::"n"(umma::EPI_THREADS) : "memory");
-    if (warp == umma::EPI_WARP0) {
-      if (lane == 0) {
-        double sum = 0;
-        for (int w = 0; w < 8; ++w) sum += sh[w];
-        slots[tile] += sum;
-      }
-      // warps w and w+4 hold column halves 0 / 1; their 4 lane quarters are the 4 row groups
-      for (int fi = lane; fi < FPT; fi += 32) {           // features of the tile: half * (FPT / 2) + k
-        const int hh = fi / (FPT / 2), k = fi % (FPT / 2);
-        const int f = (t.n0 >> 1) + fi;
-        if (f < J) {
-          double cs = 0;
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) cs += shcol[hh * 4 + qd][k];   // the 4 row quarters, fixed order
-          dphi_part[(long long)(tile / nfb) * ldpart + f] += cs;
-        }
-      }
     }
     if (tt) {
       umma::tt_add(tt, 4, tt1 - tt0);

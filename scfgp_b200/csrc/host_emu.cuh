@@ -146,6 +146,11 @@ int emu_tgemm(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
   return gemm_leave(h, c);
 }
 
+// the lean two-phase backward kernel (k_backward_i8_2p): up to 5 digits, unless SCFGP_EPILOGUE=1
+bool emu_two_phase_backward(const scfgp_handle* h) {
+  return h->prec == SCFGP_PREC_EMU_I8 && h->two_phase && h->ks2 <= 5 && (h->tnw != 96 || h->ks2 == 5);
+}
+
 int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
   const int ntiles = cdiv(h->J, h->tnw / 2) * cdiv(rows, umma::TM);
   // the epilogue rebuilds Phi from the cached digits (8-byte loads: needs J % 8 == 0), else reads the slab
@@ -155,29 +160,41 @@ int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_BACKWARD, c.sg);
-#define BWD_ARGS                                                                                                     \
+#define BWD_ARGS_2P                                                                                                  \
   c.mapRowsA, use_cache ? h->mapCacheK : c.mapRowsA, h->mapCB, use_cache ? (int)(h->Kp / umma::KB) : 0,              \
       use_cache ? (int)r0 : 0, phi_from_digits ? h->phi_cache : nullptr, h->Kc, h->cache_rows * h->Kc, recon, rows,  \
       h->J, (int)(h->Kp + h->K), ntiles, h->cscale, h->s2, c.Phi, h->ldk, h->dy + r0, h->gmu + r0, h->pbar,          \
-      h->alpha, c.Zbar, h->ldj, c.slots, c.colpart, (long long)h->K
-  if (h->two_phase && h->ks2 <= 5) {
+      h->alpha, c.Zbar, h->ldj
+#define BWD_ARGS BWD_ARGS_2P, c.slots, c.colpart, (long long)h->K
+  const bool two_phase = emu_two_phase_backward(h);
+  if (two_phase) {
     if (h->tnw == 96) {
       if (h->ks2 != 5) { h->err = "wide tiles are built for 5 digits"; return SCFGP_ERR_ARG; }
-      emu::k_backward_i8_2p<5, 96><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(BWD_ARGS);
+      emu::k_backward_i8_2p<5, 96><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(BWD_ARGS_2P);
     } else if (h->ks2 == 4) {
-      emu::k_backward_i8_2p<4, 64><<<grid, umma::THREADS, umma::Geo<4>::SMEM, c.sg>>>(BWD_ARGS);
+      emu::k_backward_i8_2p<4, 64><<<grid, umma::THREADS, umma::Geo<4>::SMEM, c.sg>>>(BWD_ARGS_2P);
     } else {
-      emu::k_backward_i8_2p<5, 64><<<grid, umma::THREADS, umma::Geo<5>::SMEM, c.sg>>>(BWD_ARGS);
+      emu::k_backward_i8_2p<5, 64><<<grid, umma::THREADS, umma::Geo<5>::SMEM, c.sg>>>(BWD_ARGS_2P);
     }
   } else if (h->tnw == 96) {
     emu::k_backward_i8<5, 96, false><<<grid, umma::THREADS, umma::Geo<5, 96>::SMEM, c.sg>>>(BWD_ARGS);
   } else {
     EMU_KS_SWITCH(h->ks2, emu::k_backward_i8<KS, 64, false><<<grid, umma::THREADS, umma::Geo<KS>::SMEM, c.sg>>>(BWD_ARGS));
   }
+#undef BWD_ARGS_2P
 #undef BWD_ARGS
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
-  return gemm_leave(h, c);
+  if ((rc = gemm_leave(h, c))) return rc;
+  if (two_phase) {
+    // the two-phase kernel leaves the reductions to others: dphi = colsum(Zbar) here (the slab is L2-warm),
+    // sbar = sum <Phibar, Phi> as two K x K traces in the dense backward phase (k_sbar_rows)
+    trace_begin(h, "colsum", c.st);
+    k_colsum<<<dim3(cdiv(h->J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, h->J, nullptr, c.colpart, h->K);
+    trace_end(h, c.st);
+    CKL();
+  }
+  return SCFGP_OK;
 }
 
 // (re)allocate the digit cache for the current data set if it is wanted and fits; otherwise run without

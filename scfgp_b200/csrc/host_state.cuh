@@ -134,6 +134,7 @@ struct scfgp_handle {
   double a = 0, b = 0, c = 0, sig2n = 0, sigf = 0, tau = 0, s = 0;
   int want_grad = 0;
   bool have_factors = false;
+  bool sbar_from_traces = false;   // this evaluation's d nlml / d b comes from k_sbar_rows (scal[5])
 
   std::string err;
   long long pivot = -1;

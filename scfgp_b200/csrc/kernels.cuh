@@ -682,4 +682,35 @@ __global__ void k_abar(const double* __restrict__ Bm, const double* __restrict__
   if (threadIdx.x == 0) pbar[i] = ti - 2.0 * ai / sig2n;
 }
 
+// sbar = sum <Phibar, Phi> (A.5) without touching the rows again:
+//   Phibar = Phi (2 Abar) + (2 gv) . (Phi B) + y pbarT + gmu alphaT
+//   => sum_n <Phibar_n, Phi_n> = tr(2 Abar G) + tr(2 B H) + pbarT p + alphaT q
+// with G = PhiT Phi, H = PhiT diag(gv) Phi, p = PhiT y, q = PhiT gmu of passes 1 and 2 (all-reduced already).
+// G and H hold (at least) their lower triangles; A2 = 2 Abar and B2 = 2 B are symmetric.
+//   part[i] = row i of the two traces (+ the two dot-product terms), summed by k_reduce_slots
+__global__ void k_sbar_rows(const double* __restrict__ A2, const double* __restrict__ B2,
+                            const double* __restrict__ G, const double* __restrict__ H, long long ld, int K,
+                            const double* __restrict__ pbar, const double* __restrict__ p,
+                            const double* __restrict__ alpha, const double* __restrict__ q,
+                            double* __restrict__ part) {
+  const int i = blockIdx.x;
+  if (i >= K) return;
+  double v = 0;
+  for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+    const long long o = (long long)i * ld + j;
+    const double w = j == i ? 1.0 : 2.0;
+    v = fma(w * A2[o], G[o], v);
+    v = fma(w * B2[o], H[o], v);
+  }
+  __shared__ double sh[32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+    part[i] = t + pbar[i] * p[i] + alpha[i] * q[i];
+  }
+}
+
 }  // namespace scfgp

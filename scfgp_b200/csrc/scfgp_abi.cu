@@ -650,6 +650,15 @@ int scfgp_eval_backward(scfgp_handle* h) {
   CKL();
   k_reduce_slots<<<1, 256, 0, h->stream>>>(h->trslots, K, 1, 1, h->scal + 3);
   CKL();
+  h->sbar_from_traces = emu_two_phase_backward(h);
+  if (h->sbar_from_traces) {
+    // sbar = sum <Phibar, Phi> = tr(2 Abar G) + tr(2 B H) + pbarT p + alphaT q  (the pass-3 kernel no longer sums it)
+    k_sbar_rows<<<K, 128, 0, h->stream>>>(h->A2, h->B2, h->red1, H, h->ldk, K, h->pbar, h->red1 + KK, h->alpha, q,
+                                         h->trslots2);
+    CKL();
+    k_reduce_slots<<<1, 256, 0, h->stream>>>(h->trslots2, K, 1, 1, h->scal + 5);
+    CKL();
+  }
   if (h->prec == SCFGP_PREC_EMU_I8 && (rc = emu_prepare_c(h))) return rc;
   return SCFGP_OK;
 }
@@ -754,9 +763,9 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
   CK(cudaSetDevice(h->device));
   const int K = h->K, J = h->J, D = h->D, S = h->S, M = h->M;
   const size_t KK = (size_t)K * h->ldk;
-  double sc[8] = {0};       // logdetL, beta.beta, p.alpha, tr(Abar)
+  double sc[8] = {0};       // logdetL, beta.beta, p.alpha, tr(Abar), -, sbar (two-phase emulated backward)
   double r1[1], r2[2];
-  CK(cudaMemcpyAsync(sc, h->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(sc, h->scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(r1, h->red1 + KK + K, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(r2, h->red2 + KK + K, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   std::vector<double> g3;
@@ -801,7 +810,8 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
   if (grad) {
     const double* dW = g3.data();
     const double* dphi = dW + (size_t)D * h->ldj;
-    const double sbar_s = dphi[h->ldj];  // = sum(Phibar * Phi) = d nlml / d b
+    // = sum(Phibar * Phi) = d nlml / d b: summed by the pass-3 kernels, or from the two traces (k_sbar_rows)
+    const double sbar_s = h->sbar_from_traces ? sc[5] : dphi[h->ldj];
     const double d_a = 2 * h->sig2n * (trA - (yy - pa) / (h->sig2n * h->sig2n)) + 2 * (Ng - M);
     const double d_b = sbar_s;
     const double d_c = gtau / (1 + std::exp(-h->c));
