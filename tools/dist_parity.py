@@ -61,8 +61,21 @@ def facade_fit_presharded(shard):
             np.asarray(mu), np.asarray(sd), m.N)
 
 
+def facade_fit_minibatch():
+    """nbatches > 1 under torch.distributed (row f5): rank 0's permutation is broadcast, every rank gathers the
+    rows of the batch that live in its shard on the device (scfgp_select_rows), the partial sums are all-reduced."""
+    rng = np.random.default_rng(8)
+    X = rng.lognormal(size=(2400, 6))
+    y = (np.sin(X.sum(1) / 3) + 0.1 * rng.standard_normal(2400))[:, None]
+    np.random.seed(31)                                # same seed everywhere: the single-GPU rerun draws the same batches
+    m = SCFGP(rank=3, feature_size=40, fftype="phase", msg=False, device=lr)
+    m.fit(X, y, None, None, max_iter=12, nbatches=3, batchsize=200)
+    return np.array(m.evals["COST"][1]), m.params.copy()
+
+
 fit_sharded = facade_fit()
 fit_pre = facade_fit_presharded(True)
+fit_mb = facade_fit_minibatch()
 dist.barrier()
 if rank == 0:
     # now evaluate the same problems on one GPU with no process group in play
@@ -88,5 +101,10 @@ if rank == 0:
                       "scaler_mu_abs": float(np.abs(m0 - m1).max()),
                       "cost_traj_rel": float(np.abs(c0 - c1).max() / np.abs(c1).max()),
                       "mu_abs": float(np.abs(mu0 - mu1).max()), "sd_abs": float(np.abs(sd0 - sd1).max())}), flush=True)
+    c1, p1 = facade_fit_minibatch()
+    c0, p0 = fit_mb
+    print(json.dumps({"facade_fit_minibatch": "SCFGP.fit(nbatches=3, batchsize=200), 2400 rows over the ranks", "world": world,
+                      "cost_traj_rel": float(np.abs(c0 - c1).max() / np.abs(c1).max()),
+                      "params_abs": float(np.abs(p0 - p1).max())}), flush=True)
 else:
     dist.destroy_process_group()
