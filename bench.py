@@ -107,16 +107,20 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # synthetic data on the device (torch used for data generation only)
 # ---------------------------------------------------------------------------------------
-def make_device_problem(n_local, D, S, M, seed, device, dist=None):
+def make_device_problem(n_local, D, S, M, seed, device, dist=None, lf_scale=None):
     import torch
     from scfgp_b200 import synth
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     X = torch.rand((n_local, D), dtype=torch.float64, device=device, generator=g)
     rng = np.random.default_rng(0)          # teacher and evaluation point are shared by all ranks
-    teacher = synth.draw_params(D, S, M, rng, lf_scale=0.3)
+    # The spread of Z = x.W grows like sqrt(D): the frequency scale shrinks with it (0.3 at the D = 64 of cfg4),
+    # otherwise wide tables (cfg5: D = 256) give random-phase features -- A ~ c I and nothing to learn.
+    if lf_scale is None:
+        lf_scale = 0.3 * (64.0 / D) ** 0.5 if D > 64 else 0.3
+    teacher = synth.draw_params(D, S, M, rng, lf_scale=lf_scale)
     w = torch.as_tensor(rng.standard_normal(2 * (S + M)), device=device)
-    params0 = synth.draw_params(D, S, M, rng, lf_scale=0.3)
+    params0 = synth.draw_params(D, S, M, rng, lf_scale=lf_scale)
     t = 3
     l_F = teacher[t:t + D * S].reshape(D, S); t += D * S
     r_F = teacher[t:t + M * S].reshape(M, S); t += M * S

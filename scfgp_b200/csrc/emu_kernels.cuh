@@ -139,6 +139,12 @@ __global__ void k_rowscale(const double* __restrict__ M1, long long ld1, const d
   }
 }
 
+// out[i] = in[i] * f
+__global__ void k_scale_vector(const double* __restrict__ in, int n, double f, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * f;
+}
+
 // power-of-two bound of |v[0..n)|: out[0] = scale, out[1] = 1/scale; running maximum of the
 // scale in gmax (bit pattern of a positive double orders like an integer)
 __global__ void k_absmax_pow2(const double* __restrict__ v, int n, double* __restrict__ out,
@@ -589,16 +595,21 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 #pragma unroll
       for (int h16 = 0; h16 < TNW / 32; ++h16) umma::epilogue_drain16<KS, TNW>(e, e.col0 + 16 * h16, parked[h16]);
       umma::epilogue_release(p);
+      // (FP64 instructions wait ~300 cycles each while the next tile's MMAs run -- profiles/r2_ncu_backward_stalls.txt --
+      //  so every scale is folded into one factor per column: one DMUL + one DFMA per value)
+      // TWO_PHASE: `liscale` holds liscale[j] * sA * 2^-14 * 2^-8(KS-1) (host: emu_prepare_li, k_scale_vector)
 #pragma unroll
       for (int h16 = 0; h16 < TNW / 32; ++h16) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int j = t.n0 + e.col0 + 16 * h16 + c;
-          const double tv = j <= K ? umma::drained_value<KS>(parked[h16][c]) * liscale[j] : 0.0;
-          if (j == K) { if (r < rows) mu[r] = tv * sc; }
+          const double tv = j <= K ? (double)parked[h16][c] * liscale[j] : 0.0;   // = T[n][j] (mu for j == K)
+          if (j == K) { if (r < rows) mu[r] = tv; }
           else sq = fma(tv, tv, sq);
         }
       }
+      if (r < rows) vpart[(long long)(2 * nb + (e.col0 ? 1 : 0)) * ldv + r] = sq;
+      continue;
     } else {
 #pragma unroll 1
       for (int h16 = 0; h16 < TNW / 32; ++h16) {

@@ -200,7 +200,7 @@ void free_emu_static(scfgp_handle* h) {
     if (*p) cudaFree(*p);
     *p = nullptr;
   }
-  for (double** p : {&h->liscale, &h->liinv, &h->cscale, &h->cinv, &h->sigg}) {
+  for (double** p : {&h->liscale, &h->liscale_w, &h->liinv, &h->cscale, &h->cinv, &h->sigg}) {
     if (*p) cudaFree(*p);
     *p = nullptr;
   }
@@ -221,7 +221,7 @@ int alloc_emu_static(scfgp_handle* h) {
   int rc;
   if ((rc = dalloc(h, &h->digLi, (size_t)ks * (K + 1) * Kp))) return rc;   // rows 0..K-1: Li, row K: alpha
   if ((rc = dalloc(h, &h->digC, (size_t)ks * K * 2 * Kp))) return rc;
-  for (double** p : {&h->liscale, &h->liinv, &h->cscale, &h->cinv})
+  for (double** p : {&h->liscale, &h->liscale_w, &h->liinv, &h->cscale, &h->cinv})
     if ((rc = dalloc(h, p, K + 1))) return rc;
   if ((rc = dalloc(h, &h->sigg, 2))) return rc;
   if ((rc = dalloc(h, &h->gvmax, 1))) return rc;

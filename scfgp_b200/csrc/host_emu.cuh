@@ -139,8 +139,11 @@ int emu_tgemm(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache) {
   int rc;
   if ((rc = gemm_enter(h, c))) return rc;
   prof_begin(h, SCFGP_FAM_TGEMM, c.sg);
+  // (two-phase epilogue: the column scales come pre-multiplied by every constant factor, see emu_prepare_li)
+  const bool tg2 = h->two_phase && h->ks2 <= 5;
   EMU_TILE_LAUNCH(k_tgemm_i8, std::min(ntiles, h->num_sms), use_cache ? h->mapCacheK : c.mapRowsA, h->mapLiB,
-                  use_cache ? (int)r0 : 0, rows, h->K, ntiles, h->liscale, h->s2, c.vpart, h->R, c.mu);
+                  use_cache ? (int)r0 : 0, rows, h->K, ntiles, tg2 ? h->liscale_w : h->liscale, h->s2, c.vpart, h->R,
+                  c.mu);
   prof_end(h, SCFGP_FAM_TGEMM, c.sg);
   CKL();
   return gemm_leave(h, c);
@@ -247,6 +250,17 @@ int ensure_phi_cache(scfgp_handle* h) {
   return SCFGP_OK;
 }
 
+// liscale[j] * sA * 2^-14 * 2^-8(ks2-1): the one factor the two-phase Phi.LiT epilogue multiplies by.  sA = s2 is
+// the digit scale of Phi, a function of the hyper-parameter b: refreshed whenever the parameters are unpacked
+// after the factors were set (scfgp_set_factors followed by scfgp_predict_device).
+int emu_refresh_liscale_w(scfgp_handle* h) {
+  const int K = h->K;
+  emu::k_scale_vector<<<cdiv(K + 1, 256), 256, 0, h->stream>>>(
+      h->liscale, K + 1, h->s2 * umma::PROD_SCALE * std::ldexp(1.0, -umma::DIGIT_BITS * (h->ks2 - 1)), h->liscale_w);
+  CKL();
+  return SCFGP_OK;
+}
+
 // digits of Li with per-row power-of-two scales (B operand of Phi.LiT)
 int emu_prepare_li(scfgp_handle* h) {
   const int K = h->K;
@@ -260,8 +274,10 @@ int emu_prepare_li(scfgp_handle* h) {
   // row K = alpha (its own power-of-two scale): the product's column K is mu = Phi.alpha
   emu::k_rowscale<<<1, 128, 0, h->stream>>>(h->alpha, K, nullptr, 0, nullptr, 1, K, 0, h->liscale + K, h->liinv + K);
   CKL();
-  return emu_digits_rows(h, h->stream, h->alpha, K, 1, K, nullptr, h->liinv + K, 1.0, nullptr, 0,
-                         h->digLi + (long long)K * h->Kp, h->Kp, plane, 0);
+  if ((rc = emu_digits_rows(h, h->stream, h->alpha, K, 1, K, nullptr, h->liinv + K, 1.0, nullptr, 0,
+                            h->digLi + (long long)K * h->Kp, h->Kp, plane, 0)))
+    return rc;
+  return emu_refresh_liscale_w(h);
 }
 
 // digits of Cmat = [2 Abar | 2 sigma B] (rows permuted cos/sin-interleaved, per-row scales);

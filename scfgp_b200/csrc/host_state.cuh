@@ -102,6 +102,7 @@ struct scfgp_handle {
   double s2 = 1.0;             // power of two >= s: scale of the Phi digits
   int8_t *digLi = nullptr;     // [KS][K][Kp]
   int8_t *digC = nullptr;      // [KS][K][2 Kp]   rows permuted (cos/sin interleaved): [2Abar | 2 sigma B]
+  double *liscale_w = nullptr;  // liscale * (every constant factor of the Phi.LiT epilogue)
   double *liscale = nullptr, *liinv = nullptr, *cscale = nullptr, *cinv = nullptr, *sigg = nullptr;
   unsigned long long* gvmax = nullptr;
   CUtensorMap mapLiB, mapCB;

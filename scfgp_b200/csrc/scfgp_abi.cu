@@ -998,6 +998,7 @@ int scfgp_predict_device(scfgp_handle* h, const double* params, const double* dX
   CK(cudaSetDevice(h->device));
   int rc;
   if ((rc = unpack_and_upload(h, params))) return rc;
+  if (h->prec == SCFGP_PREC_EMU_I8 && (rc = emu_refresh_liscale_w(h))) return rc;   // (s2 depends on the parameters)
   const int K = h->K;
   const int nkb = h->vparts;
   const int xvec = (((uintptr_t)dXs % 16) == 0 && h->D % 2 == 0) ? 2 : 1;

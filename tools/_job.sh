@@ -1,4 +1,4 @@
-python -m pytest tests/test_gpu_reference_source.py -x -q -s 2>&1 | grep -v "^$" | tail -12
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_parity.py > gpurun_out/r2_dist_parity_2gpu_fp64.txt 2>&1; tail -8 gpurun_out/r2_dist_parity_2gpu_fp64.txt
-SCFGP_PRECISION=emu5 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dist_parity.py > gpurun_out/r2_dist_parity_2gpu_emu5.txt 2>&1; tail -8 gpurun_out/r2_dist_parity_2gpu_emu5.txt
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 4 --warmup 3 > gpurun_out/r2_bench_2gpu.json 2> gpurun_out/r2_bench_2gpu.err; tail -c 400 gpurun_out/r2_bench_2gpu.err; head -c 600 gpurun_out/r2_bench_2gpu.json
+python -m pytest tests/test_gpu_emu.py tests/test_gpu_parity.py tests/test_gpu_guard.py tests/test_gpu_reference_graph.py tests/test_gpu_reference_source.py tests/test_gpu_scaler.py -x -q 2>&1 | tail -4
+python tools/scaler_objective_check.py 2>&1 | tail -8
+python bench.py --steps 4 --warmup 3 --no-fp64-compare --no-cpu-baseline > gpurun_out/r2_bench_v5.json 2> gpurun_out/r2_bench_v5.err; tail -c 300 gpurun_out/r2_bench_v5.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2_bench_v5.json').read().strip().splitlines()[-1]); print(round(d['value']), round(d['ms_per_step'],1), d['roofline']['pass_ms_last'], d['e2e']['value'])"
