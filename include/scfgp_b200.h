@@ -191,8 +191,8 @@ long long scfgp_phi_cache_bytes(const scfgp_handle* h);
  * Gram on a sample of its rows (the same rows through the FP64 DMMA Gram and through the digit Gram) and pushes
  * it through the first-order perturbation of the results with the factors just computed:
  *   est_cost  = estimated absolute error of `cost`      (threshold cost_tol,  default 1e-7)
- *   est_alpha = estimated max error of alpha / max(1, |alpha|_inf)   (threshold alpha_tol, default 1e-6)
- * (north_star's tolerances are 1e-6 relative on the cost and 1e-5 on alpha; the defaults keep a factor 10).
+ *   est_alpha = estimated max error of alpha / max(1, |alpha|_inf)   (threshold alpha_tol, default 1e-7)
+ * (north_star's tolerances are 1e-6 relative on the cost and 1e-5 on alpha; the gradient error is up to ~100 x the estimated alpha error at K = 2080 -- profiles/r2_envelope_*.txt -- hence 1e-7).
  * scfgp_eval escalates on its own when an estimate exceeds its threshold: 5 -> 6 digits -> FP64, restarting the
  * evaluation, and the handle stays at the higher precision (scfgp_get_precision2 tells).  With the phase API the
  * caller reads the estimates after scfgp_eval_factor (scfgp_guard_last), combines them over the ranks (max) and

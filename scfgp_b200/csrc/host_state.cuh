@@ -148,7 +148,7 @@ struct scfgp_handle {
   double *pre_alpha = nullptr, *pre_Li = nullptr;   // host destinations already being filled
   // a-posteriori guard of the emulated path (host_guard.cuh)
   int guard_on = 1;
-  double guard_cost_tol = 1e-7, guard_alpha_tol = 1e-6;
+  double guard_cost_tol = 1e-7, guard_alpha_tol = 1e-7;
   long long guard_sample = 0;
   double guard_est_cost = 0, guard_est_alpha = 0, guard_dg_fro = 0;
   int guard_escalations = 0;      // since the handle was created

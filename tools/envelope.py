@@ -61,7 +61,7 @@ def run_point(engs, X, y, h, D, S, M):
             rec[prec] = errors(res, ref, D, S, M)
             g = eng.guard_info()
             rec[prec].update(est_cost=g["est_cost"], est_alpha=g["est_alpha"],
-                             guard_fires=bool(g["est_cost"] > 1e-7 or g["est_alpha"] > 1e-6))
+                             guard_fires=bool(g["est_cost"] > 1e-7 or g["est_alpha"] > 1e-7))
     return rec
 
 
