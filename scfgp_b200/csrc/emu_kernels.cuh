@@ -11,6 +11,10 @@
 #include "umma_i8.cuh"
 #include "kernels.cuh"
 
+#ifndef UMMA_B_KEEP
+#define UMMA_B_KEEP true   // L2 evict_last hint on the replicated B operand of Phi.LiT and the backward product
+#endif
+
 namespace scfgp {
 namespace emu {
 
@@ -396,63 +400,88 @@ k_features_digits5(const double* __restrict__ X, long long ldx, int rows, int D,
   const int wm0 = wmi * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
   const double mq = digit_mult<5>() * inv_s2;        // value -> 2^39 / s2 units
   const bool odd = t & 1;
+  // phases first: |z| decides (per warp) between the straight-line sincos and the library one (kernels.cuh)
+  bool big = false;
 #pragma unroll
   for (int j = 0; j < Cfg::NI; ++j) {
-    const int fl = wn0 + 8 * j + 2 * t;              // tile-local feature of acc[.][j][0] (even)
-    const int f = n0 + fl;
-    const bool ok0 = f < J, ok1 = f + 1 < J;
-    const double ph0 = ok0 ? phi[f] : 0.0, ph1 = ok1 ? phi[f + 1] : 0.0;
-    double pc0 = 0, pc1 = 0, ps0 = 0, ps1 = 0;       // column sums over this thread's rows
+    const int f = n0 + wn0 + 8 * j + 2 * t;
+    const double ph0 = f < J ? phi[f] : 0.0, ph1 = f + 1 < J ? phi[f + 1] : 0.0;
 #pragma unroll
     for (int i = 0; i < Cfg::MI; ++i) {
-      const int r = m0 + wm0 + 8 * i + g;
-      const bool rv = r < rows;
-      double sn0 = 0.0, cs0 = 0.0, sn1 = 0.0, cs1 = 0.0;
-      if (rv && ok0) { sincos(acc[i][j][0] + ph0, &sn0, &cs0); cs0 *= s; sn0 *= s; }
-      if (rv && ok1) { sincos(acc[i][j][1] + ph1, &sn1, &cs1); cs1 *= s; sn1 *= s; }
-      if (wsum != nullptr && rv) {
-        const double w = wsum[r];
-        pc0 = fma(w, cs0, pc0); pc1 = fma(w, cs1, pc1); ps0 = fma(w, sn0, ps0); ps1 = fma(w, sn1, ps1);
-      }
-      // q' fields of this thread's cos pair and sin pair; lane pairs (t, t ^ 1) hold 4 neighbouring features:
-      // the even lane assembles the cos word, the odd lane the sin word
-      uint32_t hi[4], lo[4], chi[2], clo[2], shi[2], slo[2];
-      quant5(cs0 * mq, chi[0], clo[0]); quant5(cs1 * mq, chi[1], clo[1]);
-      quant5(sn0 * mq, shi[0], slo[0]); quant5(sn1 * mq, shi[1], slo[1]);
-      // send what the partner assembles, keep what this lane assembles
-      const uint32_t give_lo0 = odd ? clo[0] : slo[0], give_lo1 = odd ? clo[1] : slo[1];
-      const uint32_t give_hi = odd ? ((chi[0] & 0xffu) | ((chi[1] & 0xffu) << 8)) : ((shi[0] & 0xffu) | ((shi[1] & 0xffu) << 8));
-      const uint32_t got_lo0 = __shfl_xor_sync(0xffffffffu, give_lo0, 1);
-      const uint32_t got_lo1 = __shfl_xor_sync(0xffffffffu, give_lo1, 1);
-      const uint32_t got_hi = __shfl_xor_sync(0xffffffffu, give_hi, 1);
-      const uint32_t* klo = odd ? slo : clo;
-      const uint32_t* khi = odd ? shi : chi;
-      if (!odd) { lo[0] = klo[0]; lo[1] = klo[1]; hi[0] = khi[0]; hi[1] = khi[1];
-                  lo[2] = got_lo0; lo[3] = got_lo1; hi[2] = got_hi & 0xffu; hi[3] = (got_hi >> 8) & 0xffu; }
-      else      { lo[2] = klo[0]; lo[3] = klo[1]; hi[2] = khi[0]; hi[3] = khi[1];
-                  lo[0] = got_lo0; lo[1] = got_lo1; hi[0] = got_hi & 0xffu; hi[1] = (got_hi >> 8) & 0xffu; }
-      uint32_t w5[5];
-      pack5x4(hi, lo, w5);
-      const int f4 = f & ~3;                          // first of the 4 features of this lane pair
-      if (f4 < J) {                                   // (J % 4 == 0: the word is entirely inside or outside)
-        int8_t* o = dst + (long long)r * pitch + (odd ? J + f4 : f4);
-#pragma unroll
-        for (int d = 0; d < 5; ++d) *reinterpret_cast<uint32_t*>(o + (long long)d * plane) = w5[d];
-      }
-    }
-    if (wsum != nullptr) {
-      // reduce over the 8 row groups g of the warp (lanes with equal t), then over the warps of this column block
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        pc0 += __shfl_xor_sync(0xffffffffu, pc0, o); pc1 += __shfl_xor_sync(0xffffffffu, pc1, o);
-        ps0 += __shfl_xor_sync(0xffffffffu, ps0, o); ps1 += __shfl_xor_sync(0xffffffffu, ps1, o);
-      }
-      if (g == 0) {
-        double* cs = colsum + (size_t)wmi * 2 * Cfg::BN;
-        cs[fl] = pc0; cs[fl + 1] = pc1; cs[Cfg::BN + fl] = ps0; cs[Cfg::BN + fl + 1] = ps1;
-      }
+      acc[i][j][0] += ph0;
+      acc[i][j][1] += ph1;
+      big |= !(fabs(acc[i][j][0]) <= kFastTrigMax) | !(fabs(acc[i][j][1]) <= kFastTrigMax);
     }
   }
+  big = __any_sync(0xffffffffu, big);
+  // the weights of the column sums (p = PhiT.y) of this thread's rows
+  double wrow[Cfg::MI];
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i) {
+    const int r = m0 + wm0 + 8 * i + g;
+    wrow[i] = (wsum != nullptr && r < rows) ? wsum[r] : 0.0;
+  }
+  auto epilogue = [&](auto slow_tag) {
+    constexpr bool SLOW = decltype(slow_tag)::value;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) {
+      const int fl = wn0 + 8 * j + 2 * t;              // tile-local feature of acc[.][j][0] (even)
+      const int f = n0 + fl;
+      const bool ok0 = f < J, ok1 = f + 1 < J;
+      double pc0 = 0, pc1 = 0, ps0 = 0, ps1 = 0;       // column sums over this thread's rows
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i) {
+        const int r = m0 + wm0 + 8 * i + g;
+        const bool rv = r < rows;
+        double sn0, cs0, sn1, cs1;
+        sincos_sel<SLOW>(acc[i][j][0], sn0, cs0);
+        sincos_sel<SLOW>(acc[i][j][1], sn1, cs1);
+        const double s0 = (rv && ok0) ? s : 0.0, s1 = (rv && ok1) ? s : 0.0;   // rows / features outside: zero digits
+        cs0 *= s0; sn0 *= s0; cs1 *= s1; sn1 *= s1;
+        pc0 = fma(wrow[i], cs0, pc0); pc1 = fma(wrow[i], cs1, pc1);
+        ps0 = fma(wrow[i], sn0, ps0); ps1 = fma(wrow[i], sn1, ps1);
+        // q' fields of this thread's cos pair and sin pair; lane pairs (t, t ^ 1) hold 4 neighbouring features:
+        // the even lane assembles the cos word, the odd lane the sin word
+        uint32_t hi[4], lo[4], chi[2], clo[2], shi[2], slo[2];
+        quant5(cs0 * mq, chi[0], clo[0]); quant5(cs1 * mq, chi[1], clo[1]);
+        quant5(sn0 * mq, shi[0], slo[0]); quant5(sn1 * mq, shi[1], slo[1]);
+        // send what the partner assembles, keep what this lane assembles
+        const uint32_t give_lo0 = odd ? clo[0] : slo[0], give_lo1 = odd ? clo[1] : slo[1];
+        const uint32_t give_hi = odd ? ((chi[0] & 0xffu) | ((chi[1] & 0xffu) << 8)) : ((shi[0] & 0xffu) | ((shi[1] & 0xffu) << 8));
+        const uint32_t got_lo0 = __shfl_xor_sync(0xffffffffu, give_lo0, 1);
+        const uint32_t got_lo1 = __shfl_xor_sync(0xffffffffu, give_lo1, 1);
+        const uint32_t got_hi = __shfl_xor_sync(0xffffffffu, give_hi, 1);
+        const uint32_t* klo = odd ? slo : clo;
+        const uint32_t* khi = odd ? shi : chi;
+        if (!odd) { lo[0] = klo[0]; lo[1] = klo[1]; hi[0] = khi[0]; hi[1] = khi[1];
+                    lo[2] = got_lo0; lo[3] = got_lo1; hi[2] = got_hi & 0xffu; hi[3] = (got_hi >> 8) & 0xffu; }
+        else      { lo[2] = klo[0]; lo[3] = klo[1]; hi[2] = khi[0]; hi[3] = khi[1];
+                    lo[0] = got_lo0; lo[1] = got_lo1; hi[0] = got_hi & 0xffu; hi[1] = (got_hi >> 8) & 0xffu; }
+        uint32_t w5[5];
+        pack5x4(hi, lo, w5);
+        const int f4 = f & ~3;                          // first of the 4 features of this lane pair
+        if (f4 < J) {                                   // (J % 4 == 0: the word is entirely inside or outside)
+          int8_t* o = dst + (long long)r * pitch + (odd ? J + f4 : f4);
+#pragma unroll
+          for (int d = 0; d < 5; ++d) *reinterpret_cast<uint32_t*>(o + (long long)d * plane) = w5[d];
+        }
+      }
+      if (wsum != nullptr) {
+        // reduce over the 8 row groups g of the warp (lanes with equal t), then over the warps of this column block
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          pc0 += __shfl_xor_sync(0xffffffffu, pc0, o); pc1 += __shfl_xor_sync(0xffffffffu, pc1, o);
+          ps0 += __shfl_xor_sync(0xffffffffu, ps0, o); ps1 += __shfl_xor_sync(0xffffffffu, ps1, o);
+        }
+        if (g == 0) {
+          double* cs = colsum + (size_t)wmi * 2 * Cfg::BN;
+          cs[fl] = pc0; cs[fl + 1] = pc1; cs[Cfg::BN + fl] = ps0; cs[Cfg::BN + fl + 1] = ps1;
+        }
+      }
+    }
+  };
+  if (big) epilogue(std::true_type{});
+  else epilogue(std::false_type{});
   if (wsum != nullptr) {
     __syncthreads();
     if (threadIdx.x < 2 * Cfg::BN) {
@@ -581,7 +610,7 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     t.c_begin = 0;
     t.c_end = min(K, t.n0 + TNW);  // Li is lower triangular
     if (front) {
-      umma::run_mainloop<KS, false, TNW>(p, tmem_base, &mapA, &mapLi, t, it0, seq);
+      umma::run_mainloop<KS, false, TNW, UMMA_B_KEEP>(p, tmem_base, &mapA, &mapLi, t, it0, seq);
       it0 += umma::tile_stages(t);
       continue;
     }
@@ -668,7 +697,7 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     t.seg1_stages = seg1_stages;
     t.seg1_row_off = row0;
     if (front) {
-      umma::run_mainloop<KS, false, TNW>(p, tmem_base, &mapA, &mapC, t, it0, seq);
+      umma::run_mainloop<KS, false, TNW, UMMA_B_KEEP>(p, tmem_base, &mapA, &mapC, t, it0, seq);
       it0 += umma::tile_stages(t);
       continue;
     }
@@ -843,7 +872,7 @@ k_backward_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 //     pbar recon, alpha recon): Phibar costs one DMUL + two DFMA per value, Zbar one DMUL + one DFMA per feature
 //     on the integer-valued Phi digits;
 //   * the reductions left the kernel: sbar = sum <Phibar, Phi> is a pair of K x K traces in the dense backward
-//     phase (k_sbar_rows), dphi = colsum(Zbar) a side kernel over the Zbar slab (k_colsum).
+//     phase (k_sbar_rows), dphi = colsum(Zbar) is summed by the dW contraction from its operand fragments (k_dw_splitk).
 // ------------------------------------------------------------------------------------
 struct PhiWords5 { uint32_t c0[5], c1[5], s0[5], s1[5]; };   // digit planes of 8 cos + 8 sin features of one row
 
@@ -881,7 +910,7 @@ k_backward_i8_2p(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     t.seg1_stages = seg1_stages;
     t.seg1_row_off = row0;
     if (front) {
-      umma::run_mainloop<KS, false, TNW>(p, tmem_base, &mapA, &mapC, t, it0, seq);
+      umma::run_mainloop<KS, false, TNW, UMMA_B_KEEP>(p, tmem_base, &mapA, &mapC, t, it0, seq);
       it0 += umma::tile_stages(t);
       continue;
     }

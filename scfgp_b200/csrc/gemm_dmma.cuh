@@ -119,11 +119,14 @@ struct SmemSize {
 };
 
 // acc[i][j][e] = C[wm0 + 8i + g][wn0 + 8j + 2t + e],  g = lane>>2, t = lane&3
-template <class Cfg, bool AK, bool BKM, int AVEC, int BVEC, class AMap, class BMap>
+// BSUM: bsum[j] += the B fragment values this thread feeds to the DMMAs, i.e. after the loop
+//   bsum[j] = sum over k = t (mod 4) of B(wn0 + 8j + g, k): the sum over the four lanes t of a group g is the
+//   column sum of the B operand over the whole reduction range (dphi = colsum(Zbar) inside the dW contraction)
+template <class Cfg, bool AK, bool BKM, int AVEC, int BVEC, bool BSUM = false, class AMap, class BMap>
 __device__ __forceinline__ void gemm_mainloop(double (&acc)[Cfg::MI][Cfg::NI][2],
                                               const double* __restrict__ A, long long lda, const AMap& amap,
                                               const double* __restrict__ B, long long ldb, const BMap& bmap,
-                                              int depth, double* smem) {
+                                              int depth, double* smem, double* bsum = nullptr) {
   constexpr int BKT = Cfg::BKT;
   using LA = TileLayout<Cfg::BM, AK, BKT>;
   using LB = TileLayout<Cfg::BN, BKM, BKT>;
@@ -167,6 +170,10 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[Cfg::MI][Cfg::NI][2]
       for (int i = 0; i < Cfg::MI; ++i) a[i] = As[LA::idx(wm0 + 8 * i + g, kk * 4 + t)];
 #pragma unroll
       for (int j = 0; j < Cfg::NI; ++j) b[j] = Bs[LB::idx(wn0 + 8 * j + g, kk * 4 + t)];
+      if constexpr (BSUM) {
+#pragma unroll
+        for (int j = 0; j < Cfg::NI; ++j) bsum[j] += b[j];
+      }
 #pragma unroll
       for (int i = 0; i < Cfg::MI; ++i)
 #pragma unroll

@@ -188,16 +188,9 @@ int emu_backward(scfgp_handle* h, Ctx& c, int rows, long long r0, bool use_cache
 #undef BWD_ARGS
   prof_end(h, SCFGP_FAM_BACKWARD, c.sg);
   CKL();
-  if ((rc = gemm_leave(h, c))) return rc;
-  if (two_phase) {
-    // the two-phase kernel leaves the reductions to others: dphi = colsum(Zbar) here (the slab is L2-warm),
-    // sbar = sum <Phibar, Phi> as two K x K traces in the dense backward phase (k_sbar_rows)
-    trace_begin(h, "colsum", c.st);
-    k_colsum<<<dim3(cdiv(h->J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, h->J, nullptr, c.colpart, h->K);
-    trace_end(h, c.st);
-    CKL();
-  }
-  return SCFGP_OK;
+  // (the two-phase kernel leaves the reductions to others: dphi = colsum(Zbar) to the dW contraction that reads the
+  // slab next (k_dw_splitk), sbar = sum <Phibar, Phi> to two K x K traces in the dense backward phase, k_sbar_rows)
+  return gemm_leave(h, c);
 }
 
 // (re)allocate the digit cache for the current data set if it is wanted and fits; otherwise run without

@@ -9,7 +9,7 @@ constexpr int kColSplit = 64;  // row splits of the column-sum kernels (parallel
 constexpr int kSeedBlocks = 296;
 constexpr int kGramSplit = 1;  // row splits of one chunk's Gram tiles in the emulated mode (work items = tiles x splits)
 constexpr int kWideTile = 96;  // default tile width of Phi.LiT / backward in the emulated mode with 5 digits (64 otherwise)
-constexpr int kDwSplit = 16;   // row splits of the dW = XT.Zbar contraction (partial buffers per chunk stream)
+constexpr int kDwSplit = 32;   // row splits of the dW = XT.Zbar contraction (partial buffers per chunk stream)
 
 struct ItemList {
   int4* d = nullptr;

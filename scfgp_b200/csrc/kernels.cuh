@@ -1,6 +1,8 @@
 // Kernels of the SCFGP marginal-likelihood hot path (sm_100a, FP64 DMMA).
 // Math: SURVEY.md Appendix A, restating SCFGP/SCFGP.py:92-148 of the reference.
 #pragma once
+#include <type_traits>
+
 #include "gemm_dmma.cuh"
 
 namespace scfgp {
@@ -21,6 +23,49 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ------------------------------------------------------------------------------------
+// sin and cos for the feature map (SCFGP.py:98-102).  Straight-line code for |z| <= kFastTrigMax: k = rint(z 2/pi)
+// by the 1.5 * 2^52 magic add, two FMA steps of Cody-Waite reduction on a two-part pi/2 (|k| < 2^20, so k * lo(pi/2)
+// is far below the rounding of the first step), the fdlibm kernel polynomials on [-pi/4, pi/4] and the quadrant
+// fix-up by selects.  Measured against long-double libm over |z| <= 1e6: max |error| 1.74e-16 for both (< 1 ulp of
+// 1; tools/sincos_check.c).  No branch, no call: the compiler interleaves the independent evaluations of an
+// unrolled epilogue (the library sincos carries a slow-path branch per call that serialises them).  Larger
+// arguments take the library function through one out-of-line copy.
+// ------------------------------------------------------------------------------------
+constexpr double kFastTrigMax = 1.0e6;
+__device__ __forceinline__ void sincos_fast(double z, double& sn, double& cs) {
+  const double kd = fma(z, 0.63661977236758138, 6755399441055744.0);
+  const int q = __double2loint(kd);
+  const double k = kd - 6755399441055744.0;
+  double r = fma(-k, 1.5707963267948966, z);
+  r = fma(-k, 6.123233995736766e-17, r);
+  const double w = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, w, -2.50507602534068634195e-08);
+  ps = fma(ps, w, 2.75573137070700676789e-06);
+  ps = fma(ps, w, -1.98412698298579493134e-04);
+  ps = fma(ps, w, 8.33333333332248946124e-03);
+  ps = fma(ps, w, -1.66666666666666324348e-01);
+  const double s = fma(r * w, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, w, 2.08757232129817482790e-09);
+  pc = fma(pc, w, -2.75573143513906633035e-07);
+  pc = fma(pc, w, 2.48015872894767294178e-05);
+  pc = fma(pc, w, -1.38888888888741095749e-03);
+  pc = fma(pc, w, 4.16666666666666019037e-02);
+  const double c = fma(w * w, pc, fma(-0.5, w, 1.0));
+  // quadrant q mod 4: (s, c), (c, -s), (-s, -c), (-c, s); the sign flips are integer operations on the high word
+  const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+  sn = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
+  cs = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
+}
+__device__ __noinline__ void sincos_lib(double z, double* sn, double* cs) { sincos(z, sn, cs); }
+template <bool SLOW>
+__device__ __forceinline__ void sincos_sel(double z, double& sn, double& cs) {
+  if constexpr (SLOW) sincos_lib(z, &sn, &cs);
+  else sincos_fast(z, sn, cs);
 }
 
 // ------------------------------------------------------------------------------------
@@ -77,10 +122,12 @@ k_gemm(const double* __restrict__ A, long long lda, int a_rows,
 //   items: (d block of 64, j block of 128)
 // ------------------------------------------------------------------------------------
 template <int AVEC>
-__global__ void __launch_bounds__(CfgDw::NT, 1)
+__global__ void __launch_bounds__(CfgDw::NT, 2)
 k_dw_splitk(const double* __restrict__ X, long long ldx, int D, const double* __restrict__ Z, long long ldz, int J,
             int rows, int split_len, double* __restrict__ part, long long ldc, long long part_stride,
-            const int4* __restrict__ items) {
+            const int4* __restrict__ items, double* __restrict__ colpart, long long ldcol) {
+  // colpart (optional): colpart[split][j] += sum over the split's rows of Zbar[r, j]  (dphi = colsum(Zbar), A.5) --
+  // the B fragments the DMMAs consume anyway are summed on the way (CTAs of the first d block only)
   using Cfg = CfgDw;
   extern __shared__ __align__(16) double smem[];
   const int4 it = items[blockIdx.x];
@@ -90,9 +137,12 @@ k_dw_splitk(const double* __restrict__ X, long long ldx, int D, const double* __
   if (depth <= 0) return;
   double acc[Cfg::MI][Cfg::NI][2];
   zero_acc<Cfg>(acc);
+  double bsum[Cfg::NI];
+#pragma unroll
+  for (int j = 0; j < Cfg::NI; ++j) bsum[j] = 0.0;
   IdentMap am{m0, D}, bm{n0, J};
-  gemm_mainloop<Cfg, false, false, AVEC, 2>(acc, X + (long long)k0 * ldx, ldx, am, Z + (long long)k0 * ldz, ldz, bm,
-                                            depth, smem);
+  gemm_mainloop<Cfg, false, false, AVEC, 2, true>(acc, X + (long long)k0 * ldx, ldx, am, Z + (long long)k0 * ldz, ldz,
+                                                  bm, depth, smem, bsum);
   double* C = part + (long long)blockIdx.y * part_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -108,6 +158,16 @@ k_dw_splitk(const double* __restrict__ X, long long ldx, int D, const double* __
         const int c = n0 + wn0 + 8 * j + 2 * t + e;
         if (c < J) C[(long long)r * ldc + c] += acc[i][j][e];
       }
+  }
+  if (colpart != nullptr && it.x == 0 && wm0 == 0) {
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) {
+      double v = bsum[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      const int c = n0 + wn0 + 8 * j + g;
+      if (t == 0 && c < J) colpart[(long long)blockIdx.y * ldcol + c] += v;
+    }
   }
 }
 
@@ -140,35 +200,54 @@ k_features(const double* __restrict__ X, long long ldx, int rows, int D,
   const bool vec_c = (ldp & 1) == 0 && (reinterpret_cast<uintptr_t>(Phi) & 15) == 0 &&
                      (Psi == nullptr || (reinterpret_cast<uintptr_t>(Psi) & 15) == 0);
   const bool vec_s = vec_c && (J & 1) == 0;
+  // phases first: |z| decides (per warp) between the straight-line sincos and the library one
+  double ph[Cfg::NI][2];
+  bool big = false;
 #pragma unroll
   for (int j = 0; j < Cfg::NI; ++j) {
     const int f = n0 + wn0 + 8 * j + 2 * t;   // even
-    if (f >= J) continue;
-    const bool two = f + 1 < J;
-    const double ph0 = phi[f], ph1 = two ? phi[f + 1] : 0.0;
+    ph[j][0] = f < J ? phi[f] : 0.0;
+    ph[j][1] = f + 1 < J ? phi[f + 1] : 0.0;
 #pragma unroll
     for (int i = 0; i < Cfg::MI; ++i) {
-      const int r = m0 + wm0 + 8 * i + g;
-      if (r >= rows) continue;
-      double sn0, cs0, sn1 = 0.0, cs1 = 0.0;
-      sincos(acc[i][j][0] + ph0, &sn0, &cs0);
-      if (two) sincos(acc[i][j][1] + ph1, &sn1, &cs1);
-      cs0 *= s; sn0 *= s; cs1 *= s; sn1 *= s;
-      double* row = Phi + (long long)r * ldp;
-      if (two && vec_c) *reinterpret_cast<double2*>(row + f) = make_double2(cs0, cs1);
-      else { row[f] = cs0; if (two) row[f + 1] = cs1; }
-      if (two && vec_s) *reinterpret_cast<double2*>(row + J + f) = make_double2(sn0, sn1);
-      else { row[J + f] = sn0; if (two) row[J + f + 1] = sn1; }
-      if (Psi != nullptr) {
-        const double w = rowscale[r];
-        double* prow = Psi + (long long)r * ldp;
-        if (two && vec_c) *reinterpret_cast<double2*>(prow + f) = make_double2(w * cs0, w * cs1);
-        else { prow[f] = w * cs0; if (two) prow[f + 1] = w * cs1; }
-        if (two && vec_s) *reinterpret_cast<double2*>(prow + J + f) = make_double2(w * sn0, w * sn1);
-        else { prow[J + f] = w * sn0; if (two) prow[J + f + 1] = w * sn1; }
-      }
+      acc[i][j][0] += ph[j][0];
+      acc[i][j][1] += ph[j][1];
+      big |= !(fabs(acc[i][j][0]) <= kFastTrigMax) | !(fabs(acc[i][j][1]) <= kFastTrigMax);
     }
   }
+  big = __any_sync(0xffffffffu, big);
+  auto epilogue = [&](auto slow_tag) {
+    constexpr bool SLOW = decltype(slow_tag)::value;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) {
+      const int f = n0 + wn0 + 8 * j + 2 * t;   // even
+      const bool one = f < J, two = f + 1 < J;
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i) {
+        const int r = m0 + wm0 + 8 * i + g;
+        double sn0, cs0, sn1, cs1;
+        sincos_sel<SLOW>(acc[i][j][0], sn0, cs0);
+        sincos_sel<SLOW>(acc[i][j][1], sn1, cs1);
+        if (r >= rows || !one) continue;
+        cs0 *= s; sn0 *= s; cs1 *= s; sn1 *= s;
+        double* row = Phi + (long long)r * ldp;
+        if (two && vec_c) *reinterpret_cast<double2*>(row + f) = make_double2(cs0, cs1);
+        else { row[f] = cs0; if (two) row[f + 1] = cs1; }
+        if (two && vec_s) *reinterpret_cast<double2*>(row + J + f) = make_double2(sn0, sn1);
+        else { row[J + f] = sn0; if (two) row[J + f + 1] = sn1; }
+        if (Psi != nullptr) {
+          const double w = rowscale[r];
+          double* prow = Psi + (long long)r * ldp;
+          if (two && vec_c) *reinterpret_cast<double2*>(prow + f) = make_double2(w * cs0, w * cs1);
+          else { prow[f] = w * cs0; if (two) prow[f + 1] = w * cs1; }
+          if (two && vec_s) *reinterpret_cast<double2*>(prow + J + f) = make_double2(w * sn0, w * sn1);
+          else { prow[J + f] = w * sn0; if (two) prow[J + f + 1] = w * sn1; }
+        }
+      }
+    }
+  };
+  if (big) epilogue(std::true_type{});
+  else epilogue(std::false_type{});
 }
 
 // ------------------------------------------------------------------------------------

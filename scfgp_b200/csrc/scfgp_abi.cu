@@ -110,6 +110,10 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   if (device < 0 || device >= ndev) { h->err = "no such CUDA device"; return SCFGP_ERR_CUDA; }
   CK(cudaSetDevice(device));
   CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  if (const char* e = getenv("SCFGP_B_KEEP")) {   // A/B knob: L2 evict_last hint on the replicated B operands
+    const int v = atoi(e) != 0;
+    CK(cudaMemcpyToSymbol(umma::g_b_keep, &v, sizeof(v)));
+  }
   int rc;
   if ((rc = set_kernel_attrs(h))) return rc;
   const size_t K = h->K, KK = K * h->ldk;
@@ -724,24 +728,20 @@ int scfgp_eval_pass3(scfgp_handle* h) {
       prof_end(h, SCFGP_FAM_BACKWARD, c.st);
       CKL();
     }
-    // dW partials += XcT . Zbar, the row reduction split over kDwSplit CTAs per tile
+    // dW partials += XcT . Zbar, the row reduction split over kDwSplit CTAs per tile; dphi = colsum(Zbar) is summed
+    // from the same operand fragments (except after the one-phase emulated backward kernel, which sums it itself)
     {
       const int split_len = cdiv(cdiv(rows, kDwSplit), 16) * 16;
       const dim3 grid(h->dw.count, kDwSplit);
       const size_t dsm = SmemSize<CfgDw, false, false>::BYTES;
+      double* colp = (emu_on && !emu_two_phase_backward(h)) ? nullptr : c.colpart;
       trace_begin(h, "dw", c.st);
       if (h->xvec == 2)
         k_dw_splitk<2><<<grid, CfgDw::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
-                                                         (long long)DJ, h->dw.d);
+                                                         (long long)DJ, h->dw.d, colp, (long long)K);
       else
         k_dw_splitk<1><<<grid, CfgDw::NT, dsm, c.st>>>(Xc, D, D, c.Zbar, h->ldj, J, rows, split_len, c.dW, h->ldj,
-                                                         (long long)DJ, h->dw.d);
-      trace_end(h, c.st);
-      CKL();
-    }
-    if (!emu_on) {   // (the emulated backward kernel leaves dphi = colsum(Zbar) in c.colpart itself)
-      trace_begin(h, "colsum", c.st);
-      k_colsum<<<dim3(cdiv(J, 256), kColSplit), 256, 0, c.st>>>(c.Zbar, h->ldj, rows, J, nullptr, c.colpart, K);
+                                                         (long long)DJ, h->dw.d, colp, (long long)K);
       trace_end(h, c.st);
       CKL();
     }

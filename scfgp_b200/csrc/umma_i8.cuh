@@ -88,6 +88,22 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// the same load with an L2 eviction-priority hint (createpolicy): the replicated B operand of the streaming products
+// ([2Abar | 2 sigma B], [Li; alpha]: 44 MB / 22 MB at K = 2080) is re-read by every tile and should outlive the
+// streaming A operand and the result slab in L2
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_slot)),
                "r"(ncols)
@@ -245,6 +261,8 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
 //   5 epilogue: acc_full -> accumulators released   6 epilogue: release -> end of the tile's epilogue
 //   7 producer waiting for free stages
 __device__ unsigned long long* g_tile_timing = nullptr;
+// L2 evict_last hint on the replicated B operand (run_mainloop<.., B_KEEP = true>); SCFGP_B_KEEP=0 switches it off
+__device__ int g_b_keep = 1;
 // (A-operand collector hints -- fill ... lastuse on the instructions that share an A digit slice -- were measured
 // as a run-time knob in round 2: no gain (profiles/r2_mma_issue_and_epilogue.txt), and the extra branch in the
 // single-thread issue loop cost 12 % on the Gram kernel.  They remain as the compile-time option UMMA_COLLECTOR.)
@@ -330,7 +348,8 @@ __device__ __forceinline__ int tile_stages(const Tile& t) { return (t.c_end - t.
 // TR = false: K-major operands (tensor maps (contraction, row, digit), tile rows m0 / n0);
 // TR = true : MN-major operands (tensor maps (M-or-N index, contraction row, digit)): m0 / n0 are
 //             coordinates of dimension 0, the contraction range [c_begin, c_end) of dimension 1.
-template <int KS, bool TR = false, int TNW = TN>
+// B_KEEP: the B operand's loads carry the L2 evict_last hint (K-major operands only)
+template <int KS, bool TR = false, int TNW = TN, bool B_KEEP = false>
 __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, const CUtensorMap* mapA,
                                              const CUtensorMap* mapB, const Tile& t, int it0, int seq = 0) {
   using G = Geo<KS, TNW>;
@@ -342,6 +361,8 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
   if (warp == 0) {
     if (elect_one()) {
       long long w_empty = 0;
+      uint64_t pol_b = 0;
+      if constexpr (B_KEEP) pol_b = g_b_keep ? l2_policy_evict_last() : 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int it = it0 + kb;
         const int st = it % G::STAGES;
@@ -361,7 +382,8 @@ __device__ __forceinline__ void run_mainloop(const Pipe& p, uint32_t tmem_base, 
         } else {
           if (kb < t.seg1_stages) tma_load_3d(sa, t.mapA1, c, t.m0 + t.seg1_row_off, 0, &p.full[st]);
           else tma_load_3d(sa, mapA, c, t.m0, 0, &p.full[st]);
-          tma_load_3d(sa + G::A_BYTES, mapB, c + t.c_off_b, t.n0, 0, &p.full[st]);
+          if (B_KEEP && pol_b != 0) tma_load_3d_hint(sa + G::A_BYTES, mapB, c + t.c_off_b, t.n0, 0, &p.full[st], pol_b);
+          else tma_load_3d(sa + G::A_BYTES, mapB, c + t.c_off_b, t.n0, 0, &p.full[st]);
         }
       }
       tt_add(tt, 7, w_empty);

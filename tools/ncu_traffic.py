@@ -26,6 +26,7 @@ for r in rd[hdr + 2:]:
         continue
     kname = r[col["Kernel Name"]]
     short = re.sub(r"\(.*", "", kname).replace("scfgp::emu::", "").replace("scfgp::", "")
+    short = re.sub(r"^void\s+", "", short).replace("emu::", "")
     vals = {}
     for w in WANT:
         if w in col:
@@ -70,7 +71,8 @@ for short, recs in seen.items():
     key = short
     if m:
         args = [a.strip() for a in m.group(2).split(",")]
-        key = f"{m.group(1)}<{','.join(args[:2])}>" if m.group(1) in ("k_backward_i8", "k_tgemm_i8") else f"{m.group(1)}<{','.join(args)}>"
+        base_name = m.group(1).replace("k_backward_i8_2p", "k_backward_i8")   # the two-phase variant of the same product
+        key = f"{base_name}<{','.join(args[:2])}>" if base_name in ("k_backward_i8", "k_tgemm_i8") else f"{base_name}<{','.join(args)}>"
     r = recs[-1]
     tj[key] = dict(r, rows=rows, source=os.path.relpath(base + "_summary.txt", ROOT))
 if "k_backward_i8<5,96>" in tj:
