@@ -76,6 +76,12 @@ __device__ __forceinline__ void quant5(double v, uint32_t& hi, uint32_t& lo) {
   lo = (uint32_t)__double2loint(d);
   hi = (uint32_t)__double2hiint(d);  // only its low byte is used
 }
+// the same without the clamp, for values that are inside +-2^38 by construction (the feature map: |Phi| <= s <= s2 / 2)
+__device__ __forceinline__ void quant5_inrange(double v, uint32_t& hi, uint32_t& lo) {
+  const double d = v + (6755399441055744.0 + 2155905152.0);
+  lo = (uint32_t)__double2loint(d);
+  hi = (uint32_t)__double2hiint(d);
+}
 // four q' -> the five plane words (byte e of a word = element e): a 4 x 4 byte transpose with byte permutes
 __device__ __forceinline__ void pack5x4(const uint32_t (&hi)[4], const uint32_t (&lo)[4], uint32_t (&w)[5]) {
   const uint32_t a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[0], lo[1], 0x7362);
@@ -370,127 +376,258 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
 }
 
 // ------------------------------------------------------------------------------------
+// The same for the default case (5 digits, source = the digit cache, one output): one thread = one row x 16
+// neighbouring columns -- a 16-byte load per source plane, a 16-byte store per output plane (80 bytes in flight per
+// row instead of 20), byte-permute unpacking / packing, the range clamp applied once per row to the row factor
+// (|x m1| <= 2^38 holds for every value that comes out of valid digits) instead of once per value.
+//   out  : digit s of x * ginv * clamp(rowmul[r] * *gptr, +-1)  -> dst[s][r][c ..]      (x = recon * cached q)
+//   cpart: cpart[blockIdx.y][c] += sum over the block's 128 rows of wsum[r] * x[r][c]   (optional; q = PhiT.gmu)
+// grid = (ceil(ceil16(cols) / 128), ceil(rows / 128)); 256 threads = 8 column groups x 32 row lanes.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dplane, double recon, int rows, int cols,
+                double ginv, const double* __restrict__ rowmul, const double* __restrict__ gptr,
+                int8_t* __restrict__ dst, long long pitch, long long plane, const double* __restrict__ wsum,
+                double* __restrict__ cpart, long long ldpart) {
+  __shared__ double csum[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = (blockIdx.x * 8 + cg) * 16;
+  const int cpad = (cols + 15) / 16 * 16;
+  const int r0 = blockIdx.y * 128;
+  const double m1 = digit_mult<5>() * ginv;
+  const double gs = gptr ? *gptr : 1.0;
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  if (c < cpad) {
+#pragma unroll 2
+    for (int it = 0; it < 4; ++it) {
+      const int r = r0 + ty + 32 * it;
+      const bool rv = r < rows;
+      uint4 w[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) w[d] = make_uint4(0u, 0u, 0u, 0u);   // zero digits
+      if (rv) {
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+          w[d] = *reinterpret_cast<const uint4*>(dsrc + (long long)d * dplane + (long long)r * dpitch + c);
+      }
+      double mm = m1;
+      double wr = 0.0;
+      if (rv) {
+        if (rowmul) mm = m1 * fmin(fmax(rowmul[r] * gs, -1.0), 1.0);
+        else mm = m1 * fmin(fmax(gs, -1.0), 1.0);
+        if (wsum) wr = wsum[r];
+      }
+      uint4 o[5];
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        uint32_t wi[5], hi[4], lo[4], wo[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) wi[d] = g4 == 0 ? w[d].x : (g4 == 1 ? w[d].y : (g4 == 2 ? w[d].z : w[d].w));
+        double q[4];
+        unpack5x4(wi, q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double x = (c + 4 * g4 + e < cols) ? q[e] * recon : 0.0;
+          acc[4 * g4 + e] = fma(wr, x, acc[4 * g4 + e]);
+          quant5_inrange(x * mm, hi[e], lo[e]);
+        }
+        pack5x4(hi, lo, wo);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+          if (g4 == 0) o[d].x = wo[d];
+          else if (g4 == 1) o[d].y = wo[d];
+          else if (g4 == 2) o[d].z = wo[d];
+          else o[d].w = wo[d];
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 5; ++d)
+        *reinterpret_cast<uint4*>(dst + (long long)d * plane + (long long)r * pitch + c) = o[d];
+    }
+  }
+  if (wsum) {
+    // the warp's 4 row lanes (lane bits 3, 4) as a reduce-scatter, then the 8 warps through shared memory (fixed order)
+    const bool b4 = lane & 16, b3 = lane & 8;
+    double a8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      a8[k] = (b4 ? acc[8 + k] : acc[k]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[k] : acc[8 + k], 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double v = (b3 ? a8[4 + k] : a8[k]) + __shfl_xor_sync(0xffffffffu, b3 ? a8[k] : a8[4 + k], 8);
+      csum[warp][cg * 16 + (b4 ? 8 : 0) + (b3 ? 4 : 0) + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int cc = blockIdx.x * 128 + threadIdx.x;
+      if (cc < cols) {
+        double v = 0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) v += csum[wv][threadIdx.x];
+        cpart[(long long)blockIdx.y * ldpart + cc] += v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Pass 1, emulated mode: feature map with the digit extraction fused into its epilogue.
 //   Z = X.W + phi (DMMA, as k_features), Phi = s [cos Z | sin Z]                     SCFGP.py:98-102
-//   out: dst[d][r][f], dst[d][r][J + f] = digit d of Phi / s2 (5 digits), rows [rows, ceil128(rows)) zero;
-//        cpart[row block][col] += sum_r wsum[r] Phi[r][col]   (p = PhiT.y, from the float64 values)
+//   out: dst[d][r][f], dst[d][r][J + f] = digit d of Phi / s2 (5 digits), rows [rows, 64 gridrows) zero;
+//        cpart[row block of 64][col] += sum_r wsum[r] Phi[r][col]   (p = PhiT.y, from the float64 values)
 // Neither the float64 Phi slab nor a second pass over it exists on this path.  Needs J % 4 == 0 (aligned
 // 4-feature words in both halves); the host falls back to k_features + k_digits_slab otherwise.
-//   grid = rowblocks(128) * featblocks(64), as k_features
+// Tile = 64 rows x 64 features.  The DMMA accumulator layout (a thread holds feature pairs of rows 8 apart) is
+// the wrong shape for the output (a digit-plane word is 4 neighbouring features of one row), so Z goes through
+// shared memory once (16-byte chunks, XOR-swizzled: both the fragment stores and the row reads are conflict
+// free) and every thread then owns ONE row x 16 neighbouring features: 16 straight-line sincos, the byte-permute
+// digit packing of the digit kernel, and one 16-byte store per digit plane and half (full 32-byte sectors,
+// 20 stores per thread instead of 80 four-byte ones), with a short non-unrolled code body.
+//   grid = rowblocks(64) * featblocks(64)
 // ------------------------------------------------------------------------------------
+using CfgFeatD = TileCfg<64, 64, 32, 16, 2, 8>;   // 8 warps (2 x 4), 16 accumulators / thread
+constexpr int FEATD_MAIN_BYTES = (int)SmemSize<CfgFeatD, true, true>::BYTES;
+constexpr int FEATD_EPI_BYTES = (64 * 64 + 8 * 128) * (int)sizeof(double);   // Z tile + per-warp column sums
+constexpr int FEATD_SMEM = FEATD_MAIN_BYTES > FEATD_EPI_BYTES ? FEATD_MAIN_BYTES : FEATD_EPI_BYTES;
+
 template <int XVEC>
-__global__ void __launch_bounds__(CfgFeat::NT, 2)
+__global__ void __launch_bounds__(CfgFeatD::NT, 2)
 k_features_digits5(const double* __restrict__ X, long long ldx, int rows, int D, const double* __restrict__ Wt,
                    long long ldw, const double* __restrict__ phi, int J, double s, double inv_s2,
                    int8_t* __restrict__ dst, long long pitch, long long plane, const double* __restrict__ wsum,
                    double* __restrict__ cpart, long long ldpart, int nfb) {
-  using Cfg = CfgFeat;
+  using Cfg = CfgFeatD;
   extern __shared__ __align__(16) double smem[];
   const int rb = blockIdx.x / nfb, fb = blockIdx.x % nfb;
   const int m0 = rb * Cfg::BM, n0 = fb * Cfg::BN;
-  double acc[Cfg::MI][Cfg::NI][2];
-  zero_acc<Cfg>(acc);
-  IdentMap am{m0, rows}, bm{n0, J};
-  gemm_mainloop<Cfg, true, true, XVEC, 2>(acc, X, ldx, am, Wt, ldw, bm, D, smem);
-  __syncthreads();                                   // the stage buffers are free: reused for the column sums
-  double* colsum = smem;                             // [WARPS_M][2][BN]  (cos / sin halves)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int wmi = warp / Cfg::WARPS_N;
-  const int wm0 = wmi * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
-  const double mq = digit_mult<5>() * inv_s2;        // value -> 2^39 / s2 units
-  const bool odd = t & 1;
-  // phases first: |z| decides (per warp) between the straight-line sincos and the library one (kernels.cuh)
-  bool big = false;
+  {
+    double acc[Cfg::MI][Cfg::NI][2];
+    zero_acc<Cfg>(acc);
+    IdentMap am{m0, rows}, bm{n0, J};
+    gemm_mainloop<Cfg, true, true, XVEC, 2>(acc, X, ldx, am, Wt, ldw, bm, D, smem);   // ends with a CTA barrier
+    // Z + phase -> shared memory: chunk c (features 2c, 2c+1) of row rl lies at chunk (c & ~7) | ((c & 7) ^ swz),
+    // swz = (c >> 3) | ((rl & 1) << 2)
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wni = warp % Cfg::WARPS_N;
 #pragma unroll
-  for (int j = 0; j < Cfg::NI; ++j) {
-    const int f = n0 + wn0 + 8 * j + 2 * t;
-    const double ph0 = f < J ? phi[f] : 0.0, ph1 = f + 1 < J ? phi[f + 1] : 0.0;
+    for (int j = 0; j < Cfg::NI; ++j) {
+      const int f = n0 + wni * Cfg::WN + 8 * j + 2 * t;
+      const double ph0 = f < J ? phi[f] : 0.0, ph1 = f + 1 < J ? phi[f + 1] : 0.0;
 #pragma unroll
-    for (int i = 0; i < Cfg::MI; ++i) {
-      acc[i][j][0] += ph0;
-      acc[i][j][1] += ph1;
-      big |= !(fabs(acc[i][j][0]) <= kFastTrigMax) | !(fabs(acc[i][j][1]) <= kFastTrigMax);
+      for (int i = 0; i < Cfg::MI; ++i) {
+        const int rl = wm0 + 8 * i + g;
+        const int pc = 8 * wni + ((4 * j + t) ^ (wni | ((rl & 1) << 2)));
+        *reinterpret_cast<double2*>(smem + rl * Cfg::BN + 2 * pc) = make_double2(acc[i][j][0] + ph0, acc[i][j][1] + ph1);
+      }
     }
   }
-  big = __any_sync(0xffffffffu, big);
-  // the weights of the column sums (p = PhiT.y) of this thread's rows
-  double wrow[Cfg::MI];
+  __syncthreads();
+  // this thread's item: row il of the tile, features 16 gq .. 16 gq + 15
+  const int il = threadIdx.x >> 2, gq = threadIdx.x & 3;
+  double z[16];
 #pragma unroll
-  for (int i = 0; i < Cfg::MI; ++i) {
-    const int r = m0 + wm0 + 8 * i + g;
-    wrow[i] = (wsum != nullptr && r < rows) ? wsum[r] : 0.0;
+  for (int k = 0; k < 8; ++k) {
+    const int pc = 8 * gq + (k ^ (gq | ((il & 1) << 2)));
+    const double2 v = *reinterpret_cast<const double2*>(smem + il * Cfg::BN + 2 * pc);
+    z[2 * k] = v.x; z[2 * k + 1] = v.y;
   }
+  bool big = false;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) big |= !(fabs(z[e]) <= kFastTrigMax);
+  big = __any_sync(0xffffffffu, big);
+  const int r = m0 + il;
+  const bool rv = r < rows;
+  const int f16 = n0 + 16 * gq;                        // first feature of the item
+  const double wr = (wsum != nullptr && rv) ? wsum[r] : 0.0;
+  const double mq = digit_mult<5>() * inv_s2;          // value -> 2^39 / s2 units
+  double* wpart = smem + Cfg::BM * Cfg::BN + warp * 128;   // this warp's column sums: [cos 64 | sin 64]
+  uint32_t cw[5][4], sw[5][4];                         // digit-plane words: [plane][4-feature group]
   auto epilogue = [&](auto slow_tag) {
     constexpr bool SLOW = decltype(slow_tag)::value;
 #pragma unroll
-    for (int j = 0; j < Cfg::NI; ++j) {
-      const int fl = wn0 + 8 * j + 2 * t;              // tile-local feature of acc[.][j][0] (even)
-      const int f = n0 + fl;
-      const bool ok0 = f < J, ok1 = f + 1 < J;
-      double pc0 = 0, pc1 = 0, ps0 = 0, ps1 = 0;       // column sums over this thread's rows
+    for (int q4 = 0; q4 < 4; ++q4) {
+      double cs[4], sn[4];
+      uint32_t hi[4], lo[4], w5[5];
 #pragma unroll
-      for (int i = 0; i < Cfg::MI; ++i) {
-        const int r = m0 + wm0 + 8 * i + g;
-        const bool rv = r < rows;
-        double sn0, cs0, sn1, cs1;
-        sincos_sel<SLOW>(acc[i][j][0], sn0, cs0);
-        sincos_sel<SLOW>(acc[i][j][1], sn1, cs1);
-        const double s0 = (rv && ok0) ? s : 0.0, s1 = (rv && ok1) ? s : 0.0;   // rows / features outside: zero digits
-        cs0 *= s0; sn0 *= s0; cs1 *= s1; sn1 *= s1;
-        pc0 = fma(wrow[i], cs0, pc0); pc1 = fma(wrow[i], cs1, pc1);
-        ps0 = fma(wrow[i], sn0, ps0); ps1 = fma(wrow[i], sn1, ps1);
-        // q' fields of this thread's cos pair and sin pair; lane pairs (t, t ^ 1) hold 4 neighbouring features:
-        // the even lane assembles the cos word, the odd lane the sin word
-        uint32_t hi[4], lo[4], chi[2], clo[2], shi[2], slo[2];
-        quant5(cs0 * mq, chi[0], clo[0]); quant5(cs1 * mq, chi[1], clo[1]);
-        quant5(sn0 * mq, shi[0], slo[0]); quant5(sn1 * mq, shi[1], slo[1]);
-        // send what the partner assembles, keep what this lane assembles
-        const uint32_t give_lo0 = odd ? clo[0] : slo[0], give_lo1 = odd ? clo[1] : slo[1];
-        const uint32_t give_hi = odd ? ((chi[0] & 0xffu) | ((chi[1] & 0xffu) << 8)) : ((shi[0] & 0xffu) | ((shi[1] & 0xffu) << 8));
-        const uint32_t got_lo0 = __shfl_xor_sync(0xffffffffu, give_lo0, 1);
-        const uint32_t got_lo1 = __shfl_xor_sync(0xffffffffu, give_lo1, 1);
-        const uint32_t got_hi = __shfl_xor_sync(0xffffffffu, give_hi, 1);
-        const uint32_t* klo = odd ? slo : clo;
-        const uint32_t* khi = odd ? shi : chi;
-        if (!odd) { lo[0] = klo[0]; lo[1] = klo[1]; hi[0] = khi[0]; hi[1] = khi[1];
-                    lo[2] = got_lo0; lo[3] = got_lo1; hi[2] = got_hi & 0xffu; hi[3] = (got_hi >> 8) & 0xffu; }
-        else      { lo[2] = klo[0]; lo[3] = klo[1]; hi[2] = khi[0]; hi[3] = khi[1];
-                    lo[0] = got_lo0; lo[1] = got_lo1; hi[0] = got_hi & 0xffu; hi[1] = (got_hi >> 8) & 0xffu; }
-        uint32_t w5[5];
-        pack5x4(hi, lo, w5);
-        const int f4 = f & ~3;                          // first of the 4 features of this lane pair
-        if (f4 < J) {                                   // (J % 4 == 0: the word is entirely inside or outside)
-          int8_t* o = dst + (long long)r * pitch + (odd ? J + f4 : f4);
+      const double se = (rv && f16 + 4 * q4 < J) ? s : 0.0;   // rows / features outside: zero digits (J % 4 == 0)
 #pragma unroll
-          for (int d = 0; d < 5; ++d) *reinterpret_cast<uint32_t*>(o + (long long)d * plane) = w5[d];
-        }
+      for (int e = 0; e < 4; ++e) {
+        sincos_sel<SLOW>(z[4 * q4 + e], sn[e], cs[e]);
+        cs[e] *= se; sn[e] *= se;
       }
-      if (wsum != nullptr) {
-        // reduce over the 8 row groups g of the warp (lanes with equal t), then over the warps of this column block
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          pc0 += __shfl_xor_sync(0xffffffffu, pc0, o); pc1 += __shfl_xor_sync(0xffffffffu, pc1, o);
-          ps0 += __shfl_xor_sync(0xffffffffu, ps0, o); ps1 += __shfl_xor_sync(0xffffffffu, ps1, o);
+      for (int e = 0; e < 4; ++e) quant5_inrange(cs[e] * mq, hi[e], lo[e]);
+      pack5x4(hi, lo, w5);
+#pragma unroll
+      for (int d = 0; d < 5; ++d) cw[d][q4] = w5[d];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) quant5_inrange(sn[e] * mq, hi[e], lo[e]);
+      pack5x4(hi, lo, w5);
+#pragma unroll
+      for (int d = 0; d < 5; ++d) sw[d][q4] = w5[d];
+      if (wsum != nullptr) {
+        // column sums over the warp's 8 rows (lanes with equal gq) as a reduce-scatter: every step halves the
+        // values a lane carries; the lane with bits (b4, b3, b2) ends up with value 4 b4 + 2 b3 + b2 of
+        // [cos 0..3 | sin 0..3].  Fixed order: results repeat bit for bit.
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        double a4[4], a2[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double vc = wr * cs[k], vs = wr * sn[k];
+          a4[k] = (b4 ? vs : vc) + __shfl_xor_sync(0xffffffffu, b4 ? vc : vs, 16);
         }
-        if (g == 0) {
-          double* cs = colsum + (size_t)wmi * 2 * Cfg::BN;
-          cs[fl] = pc0; cs[fl + 1] = pc1; cs[Cfg::BN + fl] = ps0; cs[Cfg::BN + fl + 1] = ps1;
-        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          a2[k] = (b3 ? a4[2 + k] : a4[k]) + __shfl_xor_sync(0xffffffffu, b3 ? a4[k] : a4[2 + k], 8);
+        const double a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
+        wpart[(b4 ? 64 : 0) + 16 * gq + 4 * q4 + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = a1;
       }
     }
   };
   if (big) epilogue(std::true_type{});
   else epilogue(std::false_type{});
+  // digit planes: 16 neighbouring features = 16 bytes per plane and half
+  if (f16 < J) {
+    int8_t* oc = dst + (long long)r * pitch + f16;
+    int8_t* os = oc + J;
+    const bool full = f16 + 16 <= J;
+    if (full && ((reinterpret_cast<uintptr_t>(oc) | (uintptr_t)plane) & 15) == 0) {
+#pragma unroll
+      for (int d = 0; d < 5; ++d)
+        *reinterpret_cast<uint4*>(oc + (long long)d * plane) = make_uint4(cw[d][0], cw[d][1], cw[d][2], cw[d][3]);
+    } else {
+#pragma unroll
+      for (int d = 0; d < 5; ++d)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          if (f16 + 4 * q4 < J) *reinterpret_cast<uint32_t*>(oc + (long long)d * plane + 4 * q4) = cw[d][q4];
+    }
+    if (full && ((reinterpret_cast<uintptr_t>(os) | (uintptr_t)plane) & 15) == 0) {
+#pragma unroll
+      for (int d = 0; d < 5; ++d)
+        *reinterpret_cast<uint4*>(os + (long long)d * plane) = make_uint4(sw[d][0], sw[d][1], sw[d][2], sw[d][3]);
+    } else {
+#pragma unroll
+      for (int d = 0; d < 5; ++d)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          if (f16 + 4 * q4 < J) *reinterpret_cast<uint32_t*>(os + (long long)d * plane + 4 * q4) = sw[d][q4];
+    }
+  }
   if (wsum != nullptr) {
     __syncthreads();
     if (threadIdx.x < 2 * Cfg::BN) {
       const int half = threadIdx.x / Cfg::BN, fl = threadIdx.x % Cfg::BN;
       const int f = n0 + fl;
       if (f < J) {
+        const double* wp = smem + Cfg::BM * Cfg::BN + threadIdx.x;
         double v = 0;
 #pragma unroll
-        for (int w = 0; w < Cfg::WARPS_M; ++w) v += colsum[(size_t)w * 2 * Cfg::BN + half * Cfg::BN + fl];   // fixed order
+        for (int w = 0; w < Cfg::NWARPS; ++w) v += wp[w * 128];   // the 8 row groups of the tile, fixed order
         cpart[(long long)rb * ldpart + half * J + f] += v;
       }
     }

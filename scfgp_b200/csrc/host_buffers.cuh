@@ -157,7 +157,7 @@ int alloc_chunk_buffers(scfgp_handle* h) {
   if (const char* e = getenv("SCFGP_GRAM_SPLIT")) h->gsplit = emu_on ? std::max(1, std::min(16, atoi(e))) : 1;
   if ((rc = dalloc(h, &h->acc_all, KK * h->ns * h->gsplit))) return rc;
   if ((rc = dalloc(h, &h->dW_all, DJ * kDwSplit * h->ns))) return rc;
-  h->csplit = std::max(kColSplit, R / 128);
+  h->csplit = std::max(kColSplit, R / 64);   // one partial row per 64-row tile of the fused feature kernel
   if ((rc = dalloc(h, &h->colpart_all, (size_t)h->csplit * K * h->ns))) return rc;
   if ((rc = dalloc(h, &h->slots_all, (size_t)h->slot_stride * h->ns))) return rc;
   for (int i = 0; i < h->ns; ++i) {

@@ -31,7 +31,15 @@ int emu_digits_slab(scfgp_handle* h, Ctx& c, int nd, bool from_cache, long long 
   const dim3 grid(cdiv((K + 15) / 16 * 16, 256), cdiv(rows, 128));
   const double recon = h->s2 * std::ldexp(1.0, -(8 * h->cache_ks - 1));
   trace_begin(h, from_cache ? "digits(cache)" : "digits(slab)", c.st);
-  if (from_cache) {
+  // the default case (5 digits from a 5-digit cache, one output, 16-byte aligned planes) has its own kernel
+  const bool fast5 = from_cache && nd == 5 && h->cache_ks == 5 && dst1 && !dst2 && !write_slab && h->Kc % 16 == 0 &&
+                     pitch % 16 == 0 && plane % 16 == 0 && (reinterpret_cast<uintptr_t>(dst1) & 15) == 0;
+  if (fast5) {
+    const dim3 g5(cdiv((K + 15) / 16 * 16, 128), cdiv(rows, 128));
+    emu::k_digits_cache5<<<g5, 256, 0, c.st>>>(h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon, rows, K,
+                                               1.0 / h->s2, rowmul1, gptr1, dst1, pitch, plane, wsum, cpart,
+                                               (long long)K);
+  } else if (from_cache) {
     EMU_KS_SWITCH(nd, emu::k_digits_slab<KS, true><<<grid, 256, 0, c.st>>>(
                           nullptr, 0, h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon, rows, K,
                           1.0 / h->s2, rowmul1, gptr1, dst1, rowmul2, gptr2, dst2, pitch, plane, wsum, cpart,
@@ -51,19 +59,19 @@ int emu_digits_slab(scfgp_handle* h, Ctx& c, int nd, bool from_cache, long long 
 bool fused_features_ok(const scfgp_handle* h) { return h->fuse_features && h->ks == 5 && h->J % 4 == 0; }
 int run_features_digits(scfgp_handle* h, Ctx& c, const double* Xc, int xvec, int rows, int8_t* dst, long long pitch,
                         long long plane, const double* wsum, double* cpart) {
-  const int nfb = cdiv(h->J, 64);
-  const int nrb = cdiv(rows, 128);
-  const size_t smem = SmemSize<CfgFeat, true, true>::BYTES;
+  const int nfb = cdiv(h->J, emu::CfgFeatD::BN);
+  // 64-row tiles over the chunk's rows rounded up to 128: the pad rows are written as zero digits
+  const int nrb = cdiv(rows, 128) * (128 / emu::CfgFeatD::BM);
   prof_begin(h, SCFGP_FAM_FEATURES, c.st);
   trace_begin(h, "features+digits", c.st);
   if (xvec == 2)
-    emu::k_features_digits5<2><<<nrb * nfb, CfgFeat::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
-                                                                      h->s, 1.0 / h->s2, dst, pitch, plane, wsum, cpart,
-                                                                      (long long)h->K, nfb);
+    emu::k_features_digits5<2><<<nrb * nfb, emu::CfgFeatD::NT, emu::FEATD_SMEM, c.st>>>(
+        Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J, h->s, 1.0 / h->s2, dst, pitch, plane, wsum, cpart,
+        (long long)h->K, nfb);
   else
-    emu::k_features_digits5<1><<<nrb * nfb, CfgFeat::NT, smem, c.st>>>(Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J,
-                                                                      h->s, 1.0 / h->s2, dst, pitch, plane, wsum, cpart,
-                                                                      (long long)h->K, nfb);
+    emu::k_features_digits5<1><<<nrb * nfb, emu::CfgFeatD::NT, emu::FEATD_SMEM, c.st>>>(
+        Xc, h->D, rows, h->D, h->Wt, h->ldw, h->phi, h->J, h->s, 1.0 / h->s2, dst, pitch, plane, wsum, cpart,
+        (long long)h->K, nfb);
   trace_end(h, c.st);
   prof_end(h, SCFGP_FAM_FEATURES, c.st);
   CKL();

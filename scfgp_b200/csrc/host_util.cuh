@@ -220,10 +220,8 @@ int set_kernel_attrs(scfgp_handle* h) {
                           (int)SmemSize<CfgBig, true, true>::BYTES));
   CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SmemSize<CfgBig, true, true>::BYTES));
-  CK(cudaFuncSetAttribute(emu::k_features_digits5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SmemSize<CfgFeat, true, true>::BYTES));
-  CK(cudaFuncSetAttribute(emu::k_features_digits5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SmemSize<CfgFeat, true, true>::BYTES));
+  CK(cudaFuncSetAttribute(emu::k_features_digits5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, emu::FEATD_SMEM));
+  CK(cudaFuncSetAttribute(emu::k_features_digits5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, emu::FEATD_SMEM));
   CK(cudaFuncSetAttribute(emu::k_features_digits5<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(emu::k_features_digits5<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
