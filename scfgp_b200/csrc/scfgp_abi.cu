@@ -646,9 +646,12 @@ int scfgp_eval_backward(scfgp_handle* h) {
   if ((rc = launch_gemm<CfgBig, true, true, 2, 2>(h, h->Bm, h->ldk, K, H, h->ldk, K, h->BH, h->ldk, 1.0, 0.0,
                                                   h->fullK, K)))
     return rc;
+  // (BHB is symmetric: lower tiles + mirror, as for B itself)
   if ((rc = launch_gemm<CfgBig, true, true, 2, 2>(h, h->BH, h->ldk, K, h->Bm, h->ldk, K, h->BHB, h->ldk, 1.0,
-                                                  0.0, h->fullK, K)))
+                                                  0.0, h->lowerK, K)))
     return rc;
+  k_symmetrize<<<dim3(cdiv(K, 32), cdiv(K, 32)), dim3(32, 32), 0, h->stream>>>(h->BHB, h->ldk, K);
+  CKL();
   k_abar<<<K, 256, 0, h->stream>>>(h->Bm, h->BHB, h->ldk, K, h->tvec, h->alpha, h->sig2n, h->A2, h->B2,
                                    h->pbar, h->trslots);
   CKL();
@@ -830,18 +833,30 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
     double* g_rf = g_lf + (size_t)D * S;
     double* g_lp = g_rf + (size_t)M * S;
     double* g_p = g_lp + S;
-    for (int d = 0; d < D; ++d)
-      for (int s2 = 0; s2 < S; ++s2) {
-        double acc = Wl[(size_t)d * S + s2];
-        for (int m = 0; m < M; ++m) acc += WF[(size_t)d * M + m] * h->rF[(size_t)m * S + s2];
-        g_lf[(size_t)d * S + s2] = acc / Ng;
+    // (contiguous inner loops over the S latent columns: the same summation order as the textbook triple loops --
+    //  m ascending / d ascending per output entry -- at a fraction of their 3 ms of host time)
+    std::vector<double> accv(S);
+    for (int d = 0; d < D; ++d) {
+      for (int s2 = 0; s2 < S; ++s2) accv[s2] = Wl[(size_t)d * S + s2];
+      const double* wf = &WF[(size_t)d * M];
+      for (int m = 0; m < M; ++m) {
+        const double w = wf[m];
+        const double* rfm = &h->rF[(size_t)m * S];
+        for (int s2 = 0; s2 < S; ++s2) accv[s2] += w * rfm[s2];
       }
-    for (int m = 0; m < M; ++m)
-      for (int s2 = 0; s2 < S; ++s2) {
-        double acc = 0;
-        for (int d = 0; d < D; ++d) acc += WF[(size_t)d * M + m] * h->lF[(size_t)d * S + s2];
-        g_rf[(size_t)m * S + s2] = acc / Ng;
+      for (int s2 = 0; s2 < S; ++s2) g_lf[(size_t)d * S + s2] = accv[s2] / Ng;
+    }
+    for (size_t i = 0; i < (size_t)M * S; ++i) g_rf[i] = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double* wf = &WF[(size_t)d * M];
+      const double* lfd = &h->lF[(size_t)d * S];
+      for (int m = 0; m < M; ++m) {
+        const double w = wf[m];
+        double* gr = g_rf + (size_t)m * S;
+        for (int s2 = 0; s2 < S; ++s2) gr[s2] += w * lfd[s2];
       }
+    }
+    for (size_t i = 0; i < (size_t)M * S; ++i) g_rf[i] /= Ng;
     for (int s2 = 0; s2 < S; ++s2) g_lp[s2] = phase ? dphi[s2] / Ng : 0.0;
     for (int m = 0; m < M; ++m) g_p[m] = phase ? dphi[S + m] / Ng : 0.0;
   }
