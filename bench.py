@@ -357,6 +357,7 @@ def main():
         sec = float(tt[0])
         K = eng.K
         e2e = {"value": N / sec, "unit": "rows/s", "ms_per_step": sec * 1e3,
+               "pass_ms_last": dict(zip(["pass1", "pass2", "pass3", "dense"], [float(v) for v in eng.pass_ms()])),
                "h2d_bytes_per_step": int(n_local * D * 8 + n_local * 8 + eng.P * 8) * world,
                "d2h_bytes_per_step": int(8 * (1 + eng.P + K + K * K)) * world,
                "api": "Engine.set_data(X_host, y_host, overlap=True) + Engine.eval(params) == "

@@ -9,6 +9,9 @@ constexpr int kColSplit = 64;  // row splits of the column-sum kernels (parallel
 constexpr int kSeedBlocks = 296;
 constexpr int kGramSplit = 1;  // row splits of one chunk's Gram tiles in the emulated mode (work items = tiles x splits)
 constexpr int kWideTile = 96;  // default tile width of Phi.LiT / backward in the emulated mode with 5 digits (64 otherwise)
+// rows per chunk of the emulated mode: the reduction depth of the Gram products (exact in int32 up to 18724 rows at
+// 8 digits, 32767 at 5); 16384 halves the Gram tiles' epilogues and pipeline restarts against 8192 (-0.9 % per evaluation)
+constexpr int kEmuChunkRows = 16384;
 constexpr int kDwSplit = 32;   // row splits of the dW = XT.Zbar contraction (partial buffers per chunk stream)
 
 struct ItemList {
@@ -64,7 +67,9 @@ struct scfgp_handle {
   std::vector<cudaEvent_t> up_ev;        // one event per uploaded row block
   long long up_block = 0;                // rows per block
   bool upload_pending = false;
-  int R = 4096;  // rows per chunk (8192 in the emulated mode unless set by the caller)
+  const double *up_X = nullptr, *up_y = nullptr;   // host arrays of a pending upload (scfgp_set_data_host_async)
+  bool up_submitted = false;             // its copies have been queued on the copy stream
+  int R = 4096;  // rows per chunk (kEmuChunkRows in the emulated mode unless set by the caller)
   bool R_user = false;
   int xvec = 2;
   long long ldk = 0;  // leading dimension of K x K matrices and slabs

@@ -10,6 +10,7 @@
 #include <functional>
 #include <atomic>
 
+#include <chrono>
 #include <cuda_runtime.h>
 
 #include "../../include/scfgp_b200.h"
@@ -72,6 +73,41 @@ static int mma_stream_peak(int ctas, int steps, int random_data, double* tops, d
 // =====================================================================================
 extern "C" {
 
+// ---- upload of host training data in row blocks (scfgp_set_data_host_async) ----------------------------------------
+// y first, then X in blocks of a few chunks on the copy stream; one event per block (pass 1 waits per chunk)
+static int submit_upload(scfgp_handle* h) {
+  if (!h->upload_pending || h->up_submitted) return SCFGP_OK;
+  const long long N = h->N;
+  CK(cudaMemcpyAsync(h->owny, h->up_y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->cstream));
+  h->up_block = (long long)h->R * 8;
+  const long long nblk = (N + h->up_block - 1) / h->up_block;
+  while ((long long)h->up_ev.size() < nblk) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->up_ev.push_back(e);
+  }
+  for (long long b = 0; b < nblk; ++b) {
+    const long long r0 = b * h->up_block, rows = std::min(h->up_block, N - r0);
+    CK(cudaMemcpyAsync(h->ownX + r0 * h->D, h->up_X + r0 * h->D, (size_t)rows * h->D * sizeof(double),
+                       cudaMemcpyHostToDevice, h->cstream));
+    CK(cudaEventRecord(h->up_ev[b], h->cstream));
+  }
+  h->up_submitted = true;
+  return SCFGP_OK;
+}
+// wait (on the host) for an upload started by scfgp_set_data_host_async
+static int finish_upload(scfgp_handle* h) {
+  if (h->upload_pending) {
+    int rc;
+    if ((rc = submit_upload(h))) return rc;
+    CK(cudaStreamSynchronize(h->cstream));
+    h->upload_pending = false;
+    h->up_X = h->up_y = nullptr;
+  }
+  return SCFGP_OK;
+}
+
+
 int scfgp_abi_version(void) { return 1; }
 
 int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out) {
@@ -102,7 +138,7 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
         const int d2 = atoi(sl + 1);
         if (d2 >= 4 && d2 <= 8) h->ks2 = d2;
       }
-      h->R = 8192;
+      h->R = kEmuChunkRows;
     }
   }
   int ndev = 0;
@@ -240,8 +276,8 @@ int scfgp_eval_prefetch_factors(scfgp_handle* h, double* alpha, double* Li) {
 int scfgp_set_chunk_rows(scfgp_handle* h, int rows) {
   if (!h || rows < 128 || rows % 128 != 0) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
+  { int rcu = finish_upload(h); if (rcu) return rcu; }
   CK(cudaDeviceSynchronize());
-  h->upload_pending = false;  // (the device-wide sync above completed any upload)
   const int old_R = h->R;
   h->R = rows;
   int rc;
@@ -258,13 +294,13 @@ int scfgp_set_precision2(scfgp_handle* h, int mode, int digits, int digits2) {
   if (digits2 == 0) digits2 = digits;
   if (digits < 4 || digits > 8 || digits2 < 4 || digits2 > 8) { h->err = "digits must be 4..8"; return SCFGP_ERR_ARG; }
   CK(cudaSetDevice(h->device));
+  { int rcu = finish_upload(h); if (rcu) return rcu; }
   CK(cudaDeviceSynchronize());
-  h->upload_pending = false;  // (the device-wide sync above completed any upload)
   const int o_prec = h->prec, o_ks = h->ks, o_ks2 = h->ks2, o_R = h->R;
   h->prec = mode;
   h->ks = digits;
   h->ks2 = digits2;
-  if (!h->R_user) h->R = mode == SCFGP_PREC_EMU_I8 ? 8192 : 4096;
+  if (!h->R_user) h->R = mode == SCFGP_PREC_EMU_I8 ? kEmuChunkRows : 4096;
   int rc;
   if ((rc = emu_check_depths(h))) { h->prec = o_prec; h->ks = o_ks; h->ks2 = o_ks2; h->R = o_R; return rc; }
   h->have_factors = false;
@@ -291,8 +327,8 @@ int scfgp_get_precision2(const scfgp_handle* h, int* mode, int* digits, int* dig
 int scfgp_set_streams(scfgp_handle* h, int n) {
   if (!h || n < 1 || n > kMaxStreams) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
+  { int rcu = finish_upload(h); if (rcu) return rcu; }
   CK(cudaDeviceSynchronize());
-  h->upload_pending = false;  // (the device-wide sync above completed any upload)
   h->ns = n;
   return alloc_chunk_buffers(h);
 }
@@ -305,15 +341,6 @@ static int set_data_common(scfgp_handle* h, long long N, long long n_global) {
   h->have_factors = false;
   h->xvec = (((uintptr_t)h->dX % 16) == 0 && h->D % 2 == 0) ? 2 : 1;
   return ensure_row_arrays(h, N);
-}
-
-// wait (on the host) for an upload started by scfgp_set_data_host_async
-static int finish_upload(scfgp_handle* h) {
-  if (h->upload_pending) {
-    CK(cudaStreamSynchronize(h->cstream));
-    h->upload_pending = false;
-  }
-  return SCFGP_OK;
 }
 
 int scfgp_set_data_host_async(scfgp_handle* h, const double* X, const double* y, long long N, long long n_global) {
@@ -334,21 +361,13 @@ int scfgp_set_data_host_async(scfgp_handle* h, const double* X, const double* y,
     // the previous evaluation may still be reading the buffers
     CK(cudaStreamSynchronize(h->stream));
   }
-  // y first, then X in blocks of a few chunks; one event per block
-  CK(cudaMemcpyAsync(h->owny, y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->cstream));
-  h->up_block = (long long)h->R * 8;
-  const long long nblk = (N + h->up_block - 1) / h->up_block;
-  while ((long long)h->up_ev.size() < nblk) {
-    cudaEvent_t e;
-    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h->up_ev.push_back(e);
-  }
-  for (long long b = 0; b < nblk; ++b) {
-    const long long r0 = b * h->up_block, rows = std::min(h->up_block, N - r0);
-    CK(cudaMemcpyAsync(h->ownX + r0 * h->D, X + r0 * h->D, (size_t)rows * h->D * sizeof(double),
-                       cudaMemcpyHostToDevice, h->cstream));
-    CK(cudaEventRecord(h->up_ev[b], h->cstream));
-  }
+  // The copies are queued by the first pass of the next evaluation (submit_upload), i.e. BEHIND that evaluation's
+  // parameter upload: the host-to-device copy engine serves its queue in order, and 5 GB of row blocks queued here
+  // would hold the (small, pageable) parameter copy -- and the host thread that waits for it before it can launch
+  // pass 1 -- until the whole table has landed (measured: the upload was then fully exposed, +80 ms per step).
+  h->up_X = X;
+  h->up_y = y;
+  h->up_submitted = false;
   h->upload_pending = true;
   h->dX = h->ownX;
   h->dy = h->owny;
@@ -435,6 +454,7 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   double* G = h->red1;
   double* p = h->red1 + KK;
   double* yy = p + K;
+  if ((rc = submit_upload(h))) return rc;   // (queued behind this evaluation's parameter upload)
   if ((rc = fork_streams(h))) return rc;
   for (int i = 0; i < h->ns; ++i) {
     Ctx& c = h->ctx[i];
@@ -486,6 +506,7 @@ int scfgp_eval_pass1(scfgp_handle* h) {
   CKL();
   if ((rc = join_streams(h))) return rc;
   h->upload_pending = false;  // everything queued after this point is ordered behind the whole upload
+  h->up_X = h->up_y = nullptr;
   k_sum_parts<<<cdiv((long long)KK, 256), 256, 0, h->stream>>>(h->acc_all, (long long)KK, h->ns * h->gsplit, (int)KK, G);
   CKL();
   k_sum_parts<<<cdiv(K, 256), 256, 0, h->stream>>>(h->colpart_all, K, h->csplit * h->ns, K, p);
@@ -788,7 +809,9 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
                            (size_t)K * sizeof(double), K, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  const auto t_host0 = std::chrono::steady_clock::now();
   if (h->pre_alpha || h->pre_Li) CK(cudaStreamSynchronize(h->cstream));
+  const auto t_host1 = std::chrono::steady_clock::now();
   h->pre_alpha = h->pre_Li = nullptr;
   prof_collect(h);
   for (int i = 0; i < 3; ++i) {
@@ -860,6 +883,12 @@ int scfgp_eval_finish(scfgp_handle* h, double* cost, double* grad, double* alpha
     for (int s2 = 0; s2 < S; ++s2) g_lp[s2] = phase ? dphi[s2] / Ng : 0.0;
     for (int m = 0; m < M; ++m) g_p[m] = phase ? dphi[S + m] / Ng : 0.0;
   }
+  if (getenv("SCFGP_HOST_TIMING")) {
+    const auto t_host2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[scfgp_b200] finish: wait for the factor copy %.3f ms, host math after the last sync %.3f ms\n",
+            std::chrono::duration<double, std::milli>(t_host1 - t_host0).count(),
+            std::chrono::duration<double, std::milli>(t_host2 - t_host1).count());
+  }
   return SCFGP_OK;
 }
 
@@ -898,8 +927,8 @@ long long scfgp_phi_cache_bytes(const scfgp_handle* h) {
 int scfgp_set_phi_cache(scfgp_handle* h, int on, double max_gb) {
   if (!h) return SCFGP_ERR_ARG;
   CK(cudaSetDevice(h->device));
+  { int rcu = finish_upload(h); if (rcu) return rcu; }
   CK(cudaDeviceSynchronize());
-  h->upload_pending = false;
   h->want_cache = on != 0;
   if (max_gb > 0) h->cache_max_gb = max_gb;
   free_phi_cache(h);   // re-decided by the next evaluation

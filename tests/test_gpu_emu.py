@@ -90,7 +90,7 @@ def test_digit_gemm_zero_rows_and_columns():
     ("abalone cfg3", (3133, 10, 5, 50)),
     ("co2 cfg3", (2225, 1, 100, 50)),
     ("ragged: odd D, odd J, N not a tile multiple", (777, 7, 3, 30)),
-    ("more than one 8192-row chunk", (9000, 8, 4, 100)),
+    ("more than one 16384-row chunk", (17000, 8, 4, 100)),
     ("tiny", (5, 2, 2, 2)),
 ])
 def test_eval_matches_oracle(name, shape, prec):
