@@ -738,10 +738,18 @@ k_tgemm_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     // Column-block major, deepest reduction first: tile k goes to CTA k mod gridDim, so every round of
     // tiles has (nearly) one depth and the persistent CTAs stay balanced although Li is triangular;
     // the CTAs of a round share the B operand (the same 64 rows of [Li; alpha]).
+    // Row blocks go in super-blocks of 64 (8192 rows): within one, all column blocks are walked before the next
+    // begins, so the A operand being re-read by the column blocks (85 MB of digits) stays L2-resident also with
+    // 16384-row chunks (whole-chunk order: 1.54 GB of DRAM reads per launch, 7.7 x the operand bytes).
     const int nrb = ntiles / nnb;
-    const int nb = nnb - 1 - tile / nrb;
+    constexpr int SBR = 64;
+    const int nsb = (nrb + SBR - 1) / SBR;
+    const int sb = min(tile / (SBR * nnb), nsb - 1);
+    const int rem = tile - sb * (SBR * nnb);
+    const int rbs = sb == nsb - 1 ? nrb - sb * SBR : SBR;   // row blocks of this super-block
+    const int nb = nnb - 1 - rem / rbs;
     umma::Tile t;
-    const int rb0 = (tile % nrb) * TM;   // chunk-local first row of the tile
+    const int rb0 = (sb * SBR + rem % rbs) * TM;   // chunk-local first row of the tile
     t.m0 = row0 + rb0;
     t.n0 = nb * TNW;
     t.c_begin = 0;

@@ -667,12 +667,14 @@ int scfgp_eval_backward(scfgp_handle* h) {
   if ((rc = launch_gemm<CfgBig, true, true, 2, 2>(h, h->Bm, h->ldk, K, H, h->ldk, K, h->BH, h->ldk, 1.0, 0.0,
                                                   h->fullK, K)))
     return rc;
-  // (BHB is symmetric: lower tiles + mirror, as for B itself)
+  // BHB is symmetric in exact arithmetic, but it must be computed WHOLE: the rounding error of (BH).B is delta.B, and
+  // everything downstream sees it through products like tr(delta.B.G) with B.G ~ I.  Mirroring the lower triangle
+  // keeps |delta.B| without that cancellation: at cond(A) ~ 4e7 the a/b/c gradient went from 1e-10 to 1e-4 of the
+  // oracle's and l_F from 2e-9 to 3e-6 (tools/envelope.py, round 2) -- for 0.3 ms saved.  (B = LiT.Li, G and H are
+  // Gram matrices: their two triangles are the same sums in the same order, so mirroring those is exact.)
   if ((rc = launch_gemm<CfgBig, true, true, 2, 2>(h, h->BH, h->ldk, K, h->Bm, h->ldk, K, h->BHB, h->ldk, 1.0,
-                                                  0.0, h->lowerK, K)))
+                                                  0.0, h->fullK, K)))
     return rc;
-  k_symmetrize<<<dim3(cdiv(K, 32), cdiv(K, 32)), dim3(32, 32), 0, h->stream>>>(h->BHB, h->ldk, K);
-  CKL();
   k_abar<<<K, 256, 0, h->stream>>>(h->Bm, h->BHB, h->ldk, K, h->tvec, h->alpha, h->sig2n, h->A2, h->B2,
                                    h->pbar, h->trslots);
   CKL();

@@ -48,7 +48,7 @@ for short, lid, v in lines:
     dw = gb(v.get("dram__bytes_write.sum", 0), v.get("dram__bytes_write.sum#unit"))
     dur = v.get("gpu__time_duration.sum", 0)
     du = v.get("gpu__time_duration.sum#unit")
-    dur_us = dur * {"nsecond": 1e-3, "usecond": 1, "msecond": 1e3, "second": 1e6}.get(du, 1)
+    dur_us = dur * {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1, "us": 1, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}.get(du, 1)
     rec = {"launch_id": lid, "duration_us": dur_us, "dram_read_bytes": dr, "dram_write_bytes": dw,
            "dram_bytes_per_launch": dr + dw,
            "tensor_pipe_active_pct": v.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
