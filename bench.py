@@ -214,6 +214,11 @@ def main():
                     help="skip the one-evaluation comparison run of the FP64 DMMA path (N = 1 GPU only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: row shards proportional to each GPU's measured rows/s instead of equal shards "
+                         "(sharding.weighted_bounds).  Off by default: on the pool's 8-GPU boxes the per-evaluation "
+                         "speed of a power-capped GPU jitters by about as much (+-3 %%) as the GPUs differ, and the "
+                         "gain was 0.3 %% (profiles/r2_bench_N10M_8gpu_emu5_balanced.json)")
     args = ap.parse_args()
 
     D, S, M = WORKLOAD["D"], WORKLOAD["S"], WORKLOAD["M"]
@@ -245,7 +250,7 @@ def main():
 
     # ---------------------------------------------------------------- our arm
     import torch
-    from scfgp_b200 import Engine, shard_bounds, _lib
+    from scfgp_b200 import Engine, shard_bounds, weighted_bounds, _lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     dist = None
@@ -258,7 +263,11 @@ def main():
     lo, hi = shard_bounds(N, rank, world)
     n_local = hi - lo
 
-    Xd, yd, params0 = make_device_problem(n_local, D, S, M, seed=1000 + rank, device=device, dist=dist)
+    # (N > 1: 15 % more rows than the equal share are generated per rank, so that the shards can be re-cut in
+    #  proportion to the ranks' measured speeds without regenerating anything; the evaluation only sees n_local rows)
+    n_gen = n_local if world == 1 or (not args.balance) else int(n_local * 1.15) // 128 * 128 + 128
+    Xfull, yfull, params0 = make_device_problem(n_gen, D, S, M, seed=1000 + rank, device=device, dist=dist)
+    Xd, yd = Xfull[:n_local], yfull[:n_local]
     eng = Engine(D, S, M, device=local_rank, chunk_rows=args.chunk_rows or None, precision=args.precision,
                  pinned_results=True)   # results land in page-locked host buffers owned by the engine
     eng.set_data_device(Xd, yd, n_global=N)
@@ -282,6 +291,51 @@ def main():
 
     for _ in range(args.warmup):
         eng.eval(params0)
+    # ---- N > 1: row shards in proportion to each GPU's own speed.  The B200s of a node run this workload at their
+    #      1 kW power cap and settle at clocks that differ by a few per cent; every all-reduce of an evaluation waits
+    #      for the slowest rank.  One more untimed evaluation measures each rank's device time in the three streaming
+    #      passes (CUDA events inside the passes: waiting for other ranks is not in them), the shards are re-cut with
+    #      sharding.weighted_bounds and the synthetic rows regenerated.  Total rows and total work are unchanged.
+    shards = None
+    if dist is not None:
+        eq_rows = [shard_bounds(N, r, world)[1] - shard_bounds(N, r, world)[0] for r in range(world)]
+        shards = {"policy": "equal", "rows": eq_rows}
+
+        def rank_speeds():
+            eng.eval(params0)                      # (settle at the new shard sizes)
+            eng.eval(params0)
+            p1, p2, p3, _ = eng.pass_ms()
+            mine = torch.tensor([n_local / max(p1 + p2 + p3, 1e-6)], dtype=torch.float64, device=device)
+            allsp = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allsp, mine)
+            return [float(t[0]) for t in allsp]
+
+        speeds = rank_speeds()
+        shards["rank_rows_per_ms_equal_shards"] = speeds
+        if args.balance:
+            # a fast rank that idles at the all-reduces boosts higher than it sustains under full load, so the
+            # measurement is repeated at the re-cut shard sizes (up to 3 rounds)
+            shards["policy"] = "proportional to each rank's measured rows/ms (sharding.weighted_bounds, granule 128, <= 3 rounds)"
+            for _round in range(3):
+                lo2, hi2 = weighted_bounds(N, rank, speeds, granule=128)
+                n_new = hi2 - lo2
+                # [largest relative move, 1 if some rank would need more rows than it generated]
+                moved = torch.tensor([abs(n_new - n_local) / max(n_local, 1), float(n_new > n_gen)],
+                                     dtype=torch.float64, device=device)
+                dist.all_reduce(moved, op=dist.ReduceOp.MAX)
+                if float(moved[0]) < 2e-3 or float(moved[1]) > 0:
+                    break
+                n_local = n_new
+                Xd, yd = Xfull[:n_local], yfull[:n_local]
+                eng.set_data_device(Xd, yd, n_global=N)
+                speeds = rank_speeds()
+            cnt = torch.tensor([float(n_local)], dtype=torch.float64, device=device)
+            allc = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(allc, cnt)
+            shards["rows"] = [int(t[0]) for t in allc]
+            shards["rank_rows_per_ms_final_shards"] = speeds
+            N_eff = sum(shards["rows"])
+            assert N_eff == N or world == 1, (N_eff, N)
     # ---- timed region: K evaluations, inputs resident in HBM
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -305,6 +359,11 @@ def main():
     eng.set_profiling(_lib.FAM_NONE)
     t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=device)
     if dist is not None:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        if shards is not None:
+            shards["rank_ms_per_step"] = [float(x[0]) / args.steps for x in allt]   # (each includes its waits for the others)
+            config["parallelism"] += "; shards " + shards["policy"]
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total = float(tmax[0]); launches = int(tsum[1])
@@ -358,7 +417,7 @@ def main():
         K = eng.K
         e2e = {"value": N / sec, "unit": "rows/s", "ms_per_step": sec * 1e3,
                "pass_ms_last": dict(zip(["pass1", "pass2", "pass3", "dense"], [float(v) for v in eng.pass_ms()])),
-               "h2d_bytes_per_step": int(n_local * D * 8 + n_local * 8 + eng.P * 8) * world,
+               "h2d_bytes_per_step": int(N * D * 8 + N * 8 + eng.P * 8 * world),
                "d2h_bytes_per_step": int(8 * (1 + eng.P + K + K * K)) * world,
                "api": "Engine.set_data(X_host, y_host, overlap=True) + Engine.eval(params) == "
                       "scfgp_set_data_host_async + scfgp_eval (pinned host X/y uploaded in row blocks inside the "
@@ -522,7 +581,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 emulated on int8 tensor cores (s8 x s8 -> s32 digit products)" if emulated else "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "roofline": roofline, "phi_cache": phi_cache, "guard": eng.guard_info(),
+            "gpu_launches": launches, "roofline": roofline, "phi_cache": phi_cache, "shards": shards, "guard": eng.guard_info(),
             "fp64_dmma_path": fp64_compare,
             "cpu_baseline": cpu_baseline,
             "cost": cost, "grad_norm": float(np.linalg.norm(grad))}

@@ -7,7 +7,7 @@ from .scaler import Scaler  # noqa: F401
 from .gpu_scaler import GpuScaler  # noqa: F401
 from .optimizer import Optimizer  # noqa: F401
 from .engine import Engine, ScfgpError  # noqa: F401
-from .sharding import shard_bounds, run_eval_phases, predict_sharded  # noqa: F401
+from .sharding import shard_bounds, weighted_bounds, run_eval_phases, predict_sharded  # noqa: F401
 
-__all__ = ["SCFGP", "Scaler", "GpuScaler", "Optimizer", "Engine", "ScfgpError", "CompiledFuncs", "shard_bounds",
+__all__ = ["SCFGP", "Scaler", "GpuScaler", "Optimizer", "Engine", "ScfgpError", "CompiledFuncs", "shard_bounds", "weighted_bounds",
            "run_eval_phases", "predict_sharded"]

@@ -21,7 +21,7 @@ from . import _lib
 from .engine import Engine
 from .optimizer import Optimizer as OPT
 from .scaler import Scaler
-from .sharding import shard_bounds
+from .sharding import shard_bounds, weighted_bounds
 
 _PHASE_NAMES = {None: _lib.FF_PHASE, True: _lib.FF_PHASE, "phase": _lib.FF_PHASE, "ph": _lib.FF_PHASE,
                 False: _lib.FF_NOPHASE, "non-phase": _lib.FF_NOPHASE, "nonphase": _lib.FF_NOPHASE,
@@ -54,7 +54,7 @@ class SCFGP(object):
     def __init__(self, rank=None, feature_size=None, fftype=None, msg=None, *, sparsity=None, nfeats=None,
                  evals=None, X_scaling_method='auto-inv-normal', y_scaling_method='auto-normal',
                  verbose=None, device=None, chunk_rows=None, precision=None, scaler_device='cpu',
-                 presharded=False):
+                 presharded=False, shard_weights=None):
         # G2 spelling: SCFGP(sparsity=20, nfeats=18, ...) (SCFGP.py:33-35);
         # G1 spelling: SCFGP(rank, feature_size, fftype, msg) (README.md:47-50).
         if device is None:             # one process per GPU under torchrun: LOCAL_RANK picks the device
@@ -79,6 +79,9 @@ class SCFGP(object):
         # table that is sharded by rows (too large to replicate); the scalers then combine their statistics
         # over the ranks, which needs the streaming GPU scalers
         self.presharded = bool(presharded)
+        # shard_weights (torch.distributed, replicated table): one positive number per rank, e.g. the GPUs' measured
+        # rows/s -- the row shards are then proportional to them (sharding.weighted_bounds) instead of equal
+        self.shard_weights = None if shard_weights is None else [float(w) for w in shard_weights]
         if self.presharded and scaler_device != 'gpu':
             raise ValueError("presharded=True needs scaler_device='gpu' (the scalers all-reduce their statistics)")
         if scaler_device == 'gpu':
@@ -194,7 +197,7 @@ class SCFGP(object):
             if world > 1 and self.presharded:
                 n = int(getattr(self.X_scaler, "n_total", n))      # rows of all ranks (all-reduced by the scaler)
             elif world > 1:
-                lo, hi = shard_bounds(n, rank, world)
+                lo, hi = self._my_rows(n, rank, world)
                 X, y = X[lo:hi], y[lo:hi]
             if self._is_cuda_tensor(X):
                 self._engine.set_data_device(X, y, n_global=n)   # device-resident training set: zero-copy hand-off
@@ -322,6 +325,14 @@ class SCFGP(object):
             td.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev))
             lo = int(sum(int(c) for c in counts[:rank]))
             return lo, lo + n
+        return self._my_rows(n, rank, world)
+
+    def _my_rows(self, n, rank, world):
+        """[lo, hi) of the rows of a replicated table that this rank holds: equal shares, or ``shard_weights``."""
+        if self.shard_weights is not None:
+            if len(self.shard_weights) != world:
+                raise ValueError(f"shard_weights has {len(self.shard_weights)} entries for {world} ranks")
+            return weighted_bounds(n, rank, self.shard_weights)
         return shard_bounds(n, rank, world)
 
     def _train_iter_rows(self, batch):

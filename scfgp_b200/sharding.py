@@ -19,6 +19,27 @@ def shard_bounds(n_rows: int, rank: int, world: int):
     return lo, hi
 
 
+def weighted_bounds(n_rows: int, rank: int, weights, granule: int = 1):
+    """Contiguous row range [lo, hi) of `rank` when the ranks' shares are proportional to `weights` (one positive
+    number per rank, e.g. each GPU's measured rows/s: power-capped B200s of one node differ by a few per cent in
+    sustained clock, and every all-reduce of an evaluation waits for the slowest rank).  Boundaries are rounded to
+    multiples of `granule` rows (the last rank takes the remainder); equal weights reproduce ``shard_bounds`` up to
+    that rounding.  Deterministic: every rank computes the same table from the same weights."""
+    w = [float(x) for x in weights]
+    world = len(w)
+    if world <= 0 or not (0 <= rank < world) or any(not (x > 0.0) for x in w) or granule <= 0:
+        raise ValueError("bad rank/weights")
+    total = sum(w)
+    cuts = [0]
+    acc = 0.0
+    for r in range(world - 1):
+        acc += w[r]
+        c = int(round(n_rows * acc / total / granule)) * granule
+        cuts.append(min(max(c, cuts[-1]), int(n_rows)))
+    cuts.append(int(n_rows))
+    return cuts[rank], cuts[rank + 1]
+
+
 def run_eval_phases(api, allreduce, want_grad: bool):
     """Sequence: pass1 -> allreduce(RED1) -> factor -> pass2 -> allreduce(RED2)
     [-> backward -> pass3 -> allreduce(RED3)].  `api` exposes pass1/factor/pass2/backward/

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import scfgp_b200
-from scfgp_b200 import Optimizer, Scaler, SCFGP, _lib, shard_bounds
+from scfgp_b200 import Optimizer, Scaler, SCFGP, _lib, shard_bounds, weighted_bounds
 from scfgp_b200 import build as libbuild
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -55,6 +55,21 @@ def test_shard_bounds_cover_rows():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_weighted_bounds_cover_rows_and_follow_the_weights():
+    for n in (0, 5, 1000, 10_000_001):
+        for w in ([1.0], [1.0, 1.0], [1.0, 0.97, 1.02, 1.0], [3.0, 1.0]):
+            for granule in (1, 128):
+                spans = [weighted_bounds(n, r, w, granule) for r in range(len(w))]
+                assert spans[0][0] == 0 and spans[-1][1] == n
+                assert all(spans[i][1] == spans[i + 1][0] and spans[i][0] <= spans[i][1] for i in range(len(w) - 1))
+                for (a, b), wr in zip(spans, w):
+                    assert abs((b - a) - n * wr / sum(w)) <= granule + 1
+    # equal weights: the plain balanced split (up to the rounding of the cut points)
+    assert [weighted_bounds(1000, r, [1, 1, 1, 1]) for r in range(4)] == [shard_bounds(1000, r, 4) for r in range(4)]
+    with pytest.raises(ValueError):
+        weighted_bounds(10, 0, [1.0, 0.0])
 
 
 # ------------------------------------------------------------------ optimiser (Optimizer.py)
