@@ -32,7 +32,7 @@ int emu_digits_slab(scfgp_handle* h, Ctx& c, int nd, bool from_cache, long long 
   const double recon = h->s2 * std::ldexp(1.0, -(8 * h->cache_ks - 1));
   trace_begin(h, from_cache ? "digits(cache)" : "digits(slab)", c.st);
   // the default case (5 digits from a 5-digit cache, one output, 16-byte aligned planes) has its own kernel
-  const bool fast5 = from_cache && nd == 5 && h->cache_ks == 5 && dst1 && !dst2 && !write_slab && h->Kc % 16 == 0 &&
+  const bool fast5 = h->fast_digits && from_cache && nd == 5 && h->cache_ks == 5 && dst1 && !dst2 && !write_slab && h->Kc % 16 == 0 &&
                      pitch % 16 == 0 && plane % 16 == 0 && (reinterpret_cast<uintptr_t>(dst1) & 15) == 0;
   if (fast5) {
     const dim3 g5(cdiv((K + 15) / 16 * 16, 128), cdiv(rows, 128));

@@ -124,6 +124,7 @@ struct scfgp_handle {
   int gram_count = 0;
   int vparts = 0;              // partial rows of vpart per chunk
   int fuse_features = 1;       // pass 1 (5 digits, J % 4 == 0): digits straight from the feature kernel; SCFGP_FUSED_FEATURES=0: two kernels
+  int fast_digits = 1;         // 16-byte-wide digit kernel for the cached 5-digit path; SCFGP_DIGIT_KERNEL=generic: k_digits_slab
   int two_phase = 1;           // two-phase epilogue of Phi.LiT / backward (up to 5 digits); SCFGP_EPILOGUE=1: one-phase
   int tnw = 64;                // tile width of the K-major digit products (Phi.LiT, backward): 64, or 96 (5 digits)
   int gsplit = 1;              // partial Gram accumulators per chunk stream (kGramSplit in the emulated mode)

@@ -128,6 +128,7 @@ int scfgp_create(int D, int S, int M, int fftype, int device, scfgp_handle** out
   if (const char* e = getenv("SCFGP_PHI_CACHE_LOG")) h->cache_log = atoi(e);
   if (const char* e = getenv("SCFGP_EPILOGUE")) h->two_phase = atoi(e) != 1;
   if (const char* e = getenv("SCFGP_FUSED_FEATURES")) h->fuse_features = atoi(e) != 0;
+  if (const char* e = getenv("SCFGP_DIGIT_KERNEL")) h->fast_digits = strcmp(e, "generic") != 0;
   if (const char* e = getenv("SCFGP_PRECISION")) {
     if (!strncmp(e, "emu", 3)) {
       h->prec = SCFGP_PREC_EMU_I8;

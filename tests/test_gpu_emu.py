@@ -404,6 +404,41 @@ def test_tile_widths_agree(monkeypatch, shape):
     assert abs(a[0] - c0) <= 1e-7 * abs(c0) and rel(a[1], g0) <= 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2500, 8, 4, 124), (20000, 8, 4, 100), (1500, 64, 16, 1024), (700, 5, 3, 33)])
+@pytest.mark.parametrize("knob,alt", [("SCFGP_FUSED_FEATURES", "0"), ("SCFGP_EPILOGUE", "1"), ("SCFGP_DIGIT_KERNEL", "generic")])
+def test_kernel_variants_agree(monkeypatch, shape, knob, alt):
+    """Every fast kernel of the 5-digit path has a plainer sibling behind an environment knob; they must compute the same
+    thing.  SCFGP_FUSED_FEATURES=0: k_features + k_digits_slab instead of the fused feature+digit kernel (the same
+    sincos and the same rounding: bit-identical digits, hence bit-identical Gram and Li; only p = PhiT.y is summed in
+    another order).  SCFGP_EPILOGUE=1: the one-phase Phi.LiT / backward kernels (dphi and sbar summed in the kernel
+    instead of by the dW contraction / the K x K traces).  SCFGP_DIGIT_KERNEL=generic: k_digits_slab instead of the
+    16-byte-wide digit kernel (bit-identical digits; q = PhiT.gmu summed in another order).
+    Shapes: J = 128 (16-byte plane stores), J = 104 (4-byte words in the sin half), cfg4 geometry, J = 36 (J % 16 != 0)."""
+    N, D, S, M = shape
+    X, y, h = synth.make_problem(N, D, S, M, seed=N + 7)
+    res = {}
+    for val in (None, alt):
+        if val is None:
+            monkeypatch.delenv(knob, raising=False)
+        else:
+            monkeypatch.setenv(knob, val)
+        eng = Engine(D, S, M, precision="emu5")
+        eng.set_data(X, y)
+        res[val] = eng.eval(h)
+        eng.close()
+    a, b = res[None], res[alt]
+    if knob != "SCFGP_FUSED_FEATURES":
+        np.testing.assert_array_equal(a[3], b[3])          # pass 1 untouched: the same Li and alpha
+        np.testing.assert_array_equal(a[2], b[2])
+    else:
+        assert np.abs(a[3] - b[3]).max() == 0.0            # the Gram is bit-identical; alpha sees p's summation order
+        assert np.abs(a[2] - b[2]).max() <= 1e-12 * max(1.0, np.abs(b[2]).max())
+    assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0])
+    # (one-phase: sbar = sum <Phibar, Phi> carries the digit rounding of the backward product, the traces that of the
+    #  Gram products -- they agree to the accuracy of the arithmetic, not to round-off)
+    assert rel(a[1], b[1]) <= (1e-7 if knob == "SCFGP_EPILOGUE" else 1e-9)
+
+
 @pytest.mark.parametrize("prec,amp,gtol", [("emu5", 30.0, 1e-5), ("emu6", 1000.0, 1e-6)])
 def test_outliers_in_y(prec, amp, gtol):
     """Outlier rows stretch the range of the per-row seeds gv (one power-of-two scale per chunk /
