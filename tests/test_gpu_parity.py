@@ -103,6 +103,43 @@ def test_feature_kernel(shape):
     eng.close()
 
 
+@pytest.mark.parametrize("scale", [3.0e4, 1.0e7, 1.0e12])
+def test_feature_kernel_large_arguments(scale):
+    """The feature map's sincos is straight-line code up to |z| = 1e6 and the library function beyond (per warp):
+    arguments on both sides of the switch and far beyond it (Payne-Hanek range) against NumPy.  D = S = 1 makes
+    z = x w + phi one product and one sum, i.e. bit-identical on both sides -- at |z| ~ 1e7 an ulp of z is already 2e-9,
+    so any other geometry would compare summation orders of X.W, not the trigonometric functions."""
+    N, D, S, M = 600, 1, 1, 29
+    X, y, h = synth.make_problem(N, D, S, M, seed=4)
+    Xb = X * scale
+    Xb[::7] = X[::7]                                     # mixed warps: small and large arguments side by side
+    eng = Engine(D, S, M)
+    Phi = eng.features(h, Xb)
+    ref = synth.features_np(h, Xb, S, M)
+    assert np.isfinite(Phi).all()
+    np.testing.assert_allclose(Phi, ref, rtol=0, atol=1e-15 * max(1.0, np.abs(ref).max()))
+    eng.close()
+
+
+def test_emulated_feature_kernel_large_arguments():
+    """The fused feature+digit kernel of the emulated pass 1 takes the same switch: one evaluation on a table with
+    arguments up to ~1e8 against the FP64 path on the same data (the two feature kernels must see the same Phi)."""
+    N, D, S, M = 3000, 8, 4, 100
+    X, y, h = synth.make_problem(N, D, S, M, seed=6)
+    Xb = X.copy()
+    Xb[::5] *= 1.0e8
+    res = {}
+    for prec in ("fp64", "emu5"):
+        eng = Engine(D, S, M, precision=prec)
+        eng.set_data(Xb, y)
+        res[prec] = eng.eval(h)
+        eng.close()
+    a, b = res["emu5"], res["fp64"]
+    assert abs(a[0] - b[0]) <= 1e-7 * abs(b[0])
+    assert np.abs(a[2] - b[2]).max() <= 1e-6 * max(1.0, np.abs(b[2]).max())
+    assert np.linalg.norm(a[1] - b[1]) <= 1e-5 * np.linalg.norm(b[1])
+
+
 # ------------------------------------------------------------------ full evaluations (BASELINE configs)
 @pytest.mark.parametrize("name,shape", [
     ("boston cfg1 (train split)", (400, 13, 5, 50)),
