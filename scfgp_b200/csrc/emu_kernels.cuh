@@ -375,6 +375,9 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
   }
 }
 
+#ifndef DIGITS_CACHE5_MINB
+#define DIGITS_CACHE5_MINB 3
+#endif
 // ------------------------------------------------------------------------------------
 // The same for the default case (5 digits, source = the digit cache, one output): one thread = one row x 16
 // neighbouring columns -- a 16-byte load per source plane, a 16-byte store per output plane (80 bytes in flight per
@@ -384,7 +387,8 @@ k_digits_slab(const double* __restrict__ src, long long ld, const int8_t* __rest
 //   cpart: cpart[blockIdx.y][c] += sum over the block's 128 rows of wsum[r] * x[r][c]   (optional; q = PhiT.gmu)
 // grid = (ceil(ceil16(cols) / 128), ceil(rows / 128)); 256 threads = 8 column groups x 32 row lanes.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <bool WSUM>
+__global__ void __launch_bounds__(256, DIGITS_CACHE5_MINB)
 k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dplane, double recon, int rows, int cols,
                 double ginv, const double* __restrict__ rowmul, const double* __restrict__ gptr,
                 int8_t* __restrict__ dst, long long pitch, long long plane, const double* __restrict__ wsum,
@@ -397,9 +401,9 @@ k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dpl
   const int r0 = blockIdx.y * 128;
   const double m1 = digit_mult<5>() * ginv;
   const double gs = gptr ? *gptr : 1.0;
-  double acc[16];
+  double acc[WSUM ? 16 : 1];      // (WSUM = false: no column sums, 32 registers fewer)
 #pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  for (int e = 0; e < (WSUM ? 16 : 1); ++e) acc[e] = 0.0;
   if (c < cpad) {
 #pragma unroll 2
     for (int it = 0; it < 4; ++it) {
@@ -418,7 +422,7 @@ k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dpl
       if (rv) {
         if (rowmul) mm = m1 * fmin(fmax(rowmul[r] * gs, -1.0), 1.0);
         else mm = m1 * fmin(fmax(gs, -1.0), 1.0);
-        if (wsum) wr = wsum[r];
+        if (WSUM) wr = wsum[r];
       }
       uint4 o[5];
 #pragma unroll
@@ -431,7 +435,7 @@ k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dpl
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const double x = (c + 4 * g4 + e < cols) ? q[e] * recon : 0.0;
-          acc[4 * g4 + e] = fma(wr, x, acc[4 * g4 + e]);
+          if constexpr (WSUM) acc[4 * g4 + e] = fma(wr, x, acc[4 * g4 + e]);
           quant5_inrange(x * mm, hi[e], lo[e]);
         }
         pack5x4(hi, lo, wo);
@@ -448,7 +452,7 @@ k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dpl
         *reinterpret_cast<uint4*>(dst + (long long)d * plane + (long long)r * pitch + c) = o[d];
     }
   }
-  if (wsum) {
+  if constexpr (WSUM) {
     // the warp's 4 row lanes (lane bits 3, 4) as a reduce-scatter, then the 8 warps through shared memory (fixed order)
     const bool b4 = lane & 16, b3 = lane & 8;
     double a8[8];

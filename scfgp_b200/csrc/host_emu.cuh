@@ -36,9 +36,14 @@ int emu_digits_slab(scfgp_handle* h, Ctx& c, int nd, bool from_cache, long long 
                      pitch % 16 == 0 && plane % 16 == 0 && (reinterpret_cast<uintptr_t>(dst1) & 15) == 0;
   if (fast5) {
     const dim3 g5(cdiv((K + 15) / 16 * 16, 128), cdiv(rows, 128));
-    emu::k_digits_cache5<<<g5, 256, 0, c.st>>>(h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon, rows, K,
-                                               1.0 / h->s2, rowmul1, gptr1, dst1, pitch, plane, wsum, cpart,
-                                               (long long)K);
+    if (wsum)
+      emu::k_digits_cache5<true><<<g5, 256, 0, c.st>>>(h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon, rows,
+                                                       K, 1.0 / h->s2, rowmul1, gptr1, dst1, pitch, plane, wsum, cpart,
+                                                       (long long)K);
+    else
+      emu::k_digits_cache5<false><<<g5, 256, 0, c.st>>>(h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon,
+                                                        rows, K, 1.0 / h->s2, rowmul1, gptr1, dst1, pitch, plane, nullptr,
+                                                        nullptr, (long long)K);
   } else if (from_cache) {
     EMU_KS_SWITCH(nd, emu::k_digits_slab<KS, true><<<grid, 256, 0, c.st>>>(
                           nullptr, 0, h->phi_cache + r0 * h->Kc, h->Kc, h->cache_rows * h->Kc, recon, rows, K,
