@@ -492,7 +492,7 @@ k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dpl
 // 20 stores per thread instead of 80 four-byte ones), with a short non-unrolled code body.
 //   grid = rowblocks(64) * featblocks(64)
 // ------------------------------------------------------------------------------------
-using CfgFeatD = TileCfg<64, 64, 32, 16, 2, 8>;   // 8 warps (2 x 4), 16 accumulators / thread
+using CfgFeatD = TileCfg<64, 64, 32, 16, 2, 16>;   // 8 warps (2 x 4), 16 accumulators / thread; 2 stages of depth 16 (41 KB)
 constexpr int FEATD_MAIN_BYTES = (int)SmemSize<CfgFeatD, true, true>::BYTES;
 constexpr int FEATD_EPI_BYTES = (64 * 64 + 8 * 128) * (int)sizeof(double);   // Z tile + per-warp column sums
 constexpr int FEATD_SMEM = FEATD_MAIN_BYTES > FEATD_EPI_BYTES ? FEATD_MAIN_BYTES : FEATD_EPI_BYTES;

@@ -16,7 +16,7 @@ using CfgTall = TileCfg<128, 64, 32, 32, 3>;   // 8 warps, panels
 // enough to share an SM with a resident tcgen05 CTA of the emulated path (186 KB at 5 digits)
 using CfgFeat = TileCfg<128, 64, 32, 32, 2, 8>;   // 8 warps, 2 stages
 using CfgWide = TileCfg<64, 128, 32, 32, 3>;   // 8 warps, small dense NN products
-using CfgDw = TileCfg<64, 128, 32, 32, 2, 8>;  // 8 warps, D x J contraction (dW)
+using CfgDw = TileCfg<64, 128, 32, 32, 3, 16>;  // 8 warps, D x J contraction (dW): 3 stages of depth 16 (77 KB)
 using CfgSq = TileCfg<64, 64, 32, 32, 3>;      // 4 warps, 64 x 64 tiles: block-recursive triangular inverse
 
 __device__ __forceinline__ double warp_sum(double v) {
