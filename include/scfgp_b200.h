@@ -109,11 +109,13 @@ int scfgp_set_data_host(scfgp_handle* h, const double* X, const double* y, long 
                         long long n_global);
 int scfgp_set_data_device(scfgp_handle* h, const double* dX, const double* dy, long long N,
                           long long n_global);
-/* Like scfgp_set_data_host, but returns as soon as the copies are queued: X is uploaded in row
- * blocks on a copy stream and the first pass of the next evaluation starts on each block as it
- * lands, so the transfer hides behind compute (use page-locked host memory; pageable memory
- * works but is staged by the driver).  X and y must stay valid and unchanged until that
- * evaluation's scfgp_eval / scfgp_eval_pass1 has returned. */
+/* Like scfgp_set_data_host, but returns at once: X is uploaded in row blocks on a copy stream and
+ * the first pass of the next evaluation starts on each block as it lands, so the transfer hides
+ * behind compute (use page-locked host memory; pageable memory works but is staged by the driver).
+ * The copies are queued by that evaluation's first pass, behind its parameter upload (the
+ * host-to-device copy engine serves its queue in order), or by the next call that needs the whole
+ * table on the device.  X and y must stay valid and unchanged until that evaluation's scfgp_eval /
+ * scfgp_eval_pass1 has returned. */
 int scfgp_set_data_host_async(scfgp_handle* h, const double* X, const double* y, long long N,
                               long long n_global);
 

@@ -170,9 +170,10 @@ class Engine:
     def set_data(self, X, y, n_global: int | None = None, overlap: bool = False):
         """X (N,D), y (N,) or (N,1) host arrays -> device copies owned by the handle.
 
-        ``overlap=True`` queues the upload in row blocks and returns at once; the first pass of
-        the next ``eval`` consumes the blocks as they land (use pinned host memory).  The arrays
-        are kept alive by the engine and must not be modified until that ``eval`` returns."""
+        ``overlap=True`` returns at once; the upload runs in row blocks during the first pass of the next
+        ``eval``, which consumes the blocks as they land (use pinned host memory; the copies are queued behind
+        that evaluation's parameter upload).  The arrays are kept alive by the engine and must not be modified
+        until that ``eval`` returns."""
         X = _lib.as_f64(X)
         y = _lib.as_f64(np.asarray(y).reshape(-1))
         if X.ndim != 2 or X.shape[1] != self.D or y.shape[0] != X.shape[0]:
