@@ -49,6 +49,12 @@ int build_static_lists(scfgp_handle* h) {
   int rc;
   if ((rc = upload_items(h, lower_tiles(K, 128, 0, -1), &h->lowerK))) return rc;
   {
+    // B = LiT.Li on lower tiles (i, j): rows k < 128 i of Li's column block i are zero, the reduction starts there
+    std::vector<int4> v = lower_tiles(K, 128, 0, -1);
+    for (int4& it : v) it.z = it.x * 128;
+    if ((rc = upload_items(h, v, &h->lowerK_tri))) return rc;
+  }
+  {
     // TMA Gram kernel: full lower tiles first, then the K mod 128 border row block with the
     // operand roles swapped (narrow side = n side) and a transposed store
     std::vector<int4> v;

@@ -132,6 +132,7 @@ struct scfgp_handle {
 
   // work lists
   ItemList lowerK, syrkK, fullK, tgemm, bwd, dw;
+  ItemList lowerK_tri;   // the same tiles with the reduction starting at the tile's row block (B = LiT.Li: Li is lower triangular)
   std::vector<ItemList> potrf_panel, potrf_trail;
   std::vector<ItemList> inv_t, inv_x;   // per level of the block-recursive triangular inverse: T = L21.Li11, Li21 = -Li22.T
   std::vector<int4*> to_free;

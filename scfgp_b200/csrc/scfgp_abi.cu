@@ -544,7 +544,7 @@ int scfgp_eval_factor(scfgp_handle* h) {
   if (h->want_grad) {
     // B = LiT Li = A^-1 (lower tiles; rows r < m0 of Li[:, m-block] are zero), then mirror
     if ((rc = launch_gemm<CfgBig, false, false, 2, 2>(h, h->Li, h->ldk, K, h->Li, h->ldk, K, h->Bm, h->ldk,
-                                                      1.0, 0.0, h->lowerK, K)))
+                                                      1.0, 0.0, h->lowerK_tri, K)))
       return rc;
     k_symmetrize<<<dim3(cdiv(K, 32), cdiv(K, 32)), dim3(32, 32), 0, h->stream>>>(h->Bm, h->ldk, K);
     CKL();
