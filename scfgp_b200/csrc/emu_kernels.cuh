@@ -486,10 +486,10 @@ k_digits_cache5(const int8_t* __restrict__ dsrc, long long dpitch, long long dpl
 // 4-feature words in both halves); the host falls back to k_features + k_digits_slab otherwise.
 // Tile = 64 rows x 64 features.  The DMMA accumulator layout (a thread holds feature pairs of rows 8 apart) is
 // the wrong shape for the output (a digit-plane word is 4 neighbouring features of one row), so Z goes through
-// shared memory once (16-byte chunks, XOR-swizzled: both the fragment stores and the row reads are conflict
-// free) and every thread then owns ONE row x 16 neighbouring features: 16 straight-line sincos, the byte-permute
-// digit packing of the digit kernel, and one 16-byte store per digit plane and half (full 32-byte sectors,
-// 20 stores per thread instead of 80 four-byte ones), with a short non-unrolled code body.
+// shared memory once (16-byte chunks, XOR-swizzled: the fragment stores are conflict free, the row reads 2-way)
+// and every thread then owns ONE row x 2 x 8 neighbouring features: 16 straight-line sincos, the byte-permute
+// digit packing of the digit kernel, and 8-byte stores per digit plane and half (four lanes fill a 32-byte sector;
+// 20 stores per thread instead of 80 four-byte ones), with a short code body and 80 registers (3 CTAs per SM).
 //   grid = rowblocks(64) * featblocks(64)
 // ------------------------------------------------------------------------------------
 using CfgFeatD = TileCfg<64, 64, 32, 16, 2, 16>;   // 8 warps (2 x 4), 16 accumulators / thread; 2 stages of depth 16 (41 KB)
@@ -497,8 +497,11 @@ constexpr int FEATD_MAIN_BYTES = (int)SmemSize<CfgFeatD, true, true>::BYTES;
 constexpr int FEATD_EPI_BYTES = (64 * 64 + 8 * 128) * (int)sizeof(double);   // Z tile + per-warp column sums
 constexpr int FEATD_SMEM = FEATD_MAIN_BYTES > FEATD_EPI_BYTES ? FEATD_MAIN_BYTES : FEATD_EPI_BYTES;
 
+#ifndef FEATD_MINB
+#define FEATD_MINB 3
+#endif
 template <int XVEC>
-__global__ void __launch_bounds__(CfgFeatD::NT, 2)
+__global__ void __launch_bounds__(CfgFeatD::NT, FEATD_MINB)
 k_features_digits5(const double* __restrict__ X, long long ldx, int rows, int D, const double* __restrict__ Wt,
                    long long ldw, const double* __restrict__ phi, int J, double s, double inv_s2,
                    int8_t* __restrict__ dst, long long pitch, long long plane, const double* __restrict__ wsum,
@@ -530,96 +533,99 @@ k_features_digits5(const double* __restrict__ X, long long ldx, int rows, int D,
     }
   }
   __syncthreads();
-  // this thread's item: row il of the tile, features 16 gq .. 16 gq + 15
+  // this thread's items: row il of the tile, features 32 hf + 8 gq .. + 7 for hf = 0, 1 (the live set of one item -- 8
+  // arguments, 2 x 10 plane words -- keeps the kernel at 80 registers: 3 CTAs per SM; the 4 lanes of a row write 32
+  // neighbouring bytes per plane and half: full sectors)
   const int il = threadIdx.x >> 2, gq = threadIdx.x & 3;
-  double z[16];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int pc = 8 * gq + (k ^ (gq | ((il & 1) << 2)));
-    const double2 v = *reinterpret_cast<const double2*>(smem + il * Cfg::BN + 2 * pc);
-    z[2 * k] = v.x; z[2 * k + 1] = v.y;
-  }
-  bool big = false;
-#pragma unroll
-  for (int e = 0; e < 16; ++e) big |= !(fabs(z[e]) <= kFastTrigMax);
-  big = __any_sync(0xffffffffu, big);
   const int r = m0 + il;
   const bool rv = r < rows;
-  const int f16 = n0 + 16 * gq;                        // first feature of the item
   const double wr = (wsum != nullptr && rv) ? wsum[r] : 0.0;
   const double mq = digit_mult<5>() * inv_s2;          // value -> 2^39 / s2 units
   double* wpart = smem + Cfg::BM * Cfg::BN + warp * 128;   // this warp's column sums: [cos 64 | sin 64]
-  uint32_t cw[5][4], sw[5][4];                         // digit-plane words: [plane][4-feature group]
-  auto epilogue = [&](auto slow_tag) {
-    constexpr bool SLOW = decltype(slow_tag)::value;
+#pragma unroll 1
+  for (int hf = 0; hf < 2; ++hf) {
+    double z[8];
 #pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      double cs[4], sn[4];
-      uint32_t hi[4], lo[4], w5[5];
+    for (int k = 0; k < 4; ++k) {
+      const int c = 16 * hf + 4 * gq + k;            // chunk = feature pair; swizzle as written above
+      const int pc = (c & ~7) | ((c & 7) ^ ((c >> 3) | ((il & 1) << 2)));
+      const double2 v = *reinterpret_cast<const double2*>(smem + il * Cfg::BN + 2 * pc);
+      z[2 * k] = v.x; z[2 * k + 1] = v.y;
+    }
+    bool big = false;
 #pragma unroll
-      const double se = (rv && f16 + 4 * q4 < J) ? s : 0.0;   // rows / features outside: zero digits (J % 4 == 0)
+    for (int e = 0; e < 8; ++e) big |= !(fabs(z[e]) <= kFastTrigMax);
+    big = __any_sync(0xffffffffu, big);
+    const int f8 = n0 + 32 * hf + 8 * gq;              // first feature of this half: the 4 lanes of a row cover 32 neighbours
+    uint32_t cw[5][2], sw[5][2];                       // digit-plane words: [plane][4-feature group]
+    auto epilogue = [&](auto slow_tag) {
+      constexpr bool SLOW = decltype(slow_tag)::value;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        sincos_sel<SLOW>(z[4 * q4 + e], sn[e], cs[e]);
-        cs[e] *= se; sn[e] *= se;
-      }
+      for (int q2 = 0; q2 < 2; ++q2) {
+        double cs[4], sn[4];
+        uint32_t hi[4], lo[4], w5[5];
+        const double se = (rv && f8 + 4 * q2 < J) ? s : 0.0;   // rows / features outside: zero digits (J % 4 == 0)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) quant5_inrange(cs[e] * mq, hi[e], lo[e]);
-      pack5x4(hi, lo, w5);
-#pragma unroll
-      for (int d = 0; d < 5; ++d) cw[d][q4] = w5[d];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) quant5_inrange(sn[e] * mq, hi[e], lo[e]);
-      pack5x4(hi, lo, w5);
-#pragma unroll
-      for (int d = 0; d < 5; ++d) sw[d][q4] = w5[d];
-      if (wsum != nullptr) {
-        // column sums over the warp's 8 rows (lanes with equal gq) as a reduce-scatter: every step halves the
-        // values a lane carries; the lane with bits (b4, b3, b2) ends up with value 4 b4 + 2 b3 + b2 of
-        // [cos 0..3 | sin 0..3].  Fixed order: results repeat bit for bit.
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-        double a4[4], a2[2];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double vc = wr * cs[k], vs = wr * sn[k];
-          a4[k] = (b4 ? vs : vc) + __shfl_xor_sync(0xffffffffu, b4 ? vc : vs, 16);
+        for (int e = 0; e < 4; ++e) {
+          sincos_sel<SLOW>(z[4 * q2 + e], sn[e], cs[e]);
+          cs[e] *= se; sn[e] *= se;
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          a2[k] = (b3 ? a4[2 + k] : a4[k]) + __shfl_xor_sync(0xffffffffu, b3 ? a4[k] : a4[2 + k], 8);
-        const double a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
-        wpart[(b4 ? 64 : 0) + 16 * gq + 4 * q4 + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = a1;
+        for (int e = 0; e < 4; ++e) quant5_inrange(cs[e] * mq, hi[e], lo[e]);
+        pack5x4(hi, lo, w5);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) cw[d][q2] = w5[d];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) quant5_inrange(sn[e] * mq, hi[e], lo[e]);
+        pack5x4(hi, lo, w5);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) sw[d][q2] = w5[d];
+        if (wsum != nullptr) {
+          // column sums over the warp's 8 rows (lanes with equal gq) as a reduce-scatter: every step halves the
+          // values a lane carries; the lane with bits (b4, b3, b2) ends up with value 4 b4 + 2 b3 + b2 of
+          // [cos 0..3 | sin 0..3].  Fixed order: results repeat bit for bit.
+          const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+          double a4[4], a2[2];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double vc = wr * cs[k], vs = wr * sn[k];
+            a4[k] = (b4 ? vs : vc) + __shfl_xor_sync(0xffffffffu, b4 ? vc : vs, 16);
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            a2[k] = (b3 ? a4[2 + k] : a4[k]) + __shfl_xor_sync(0xffffffffu, b3 ? a4[k] : a4[2 + k], 8);
+          const double a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
+          wpart[(b4 ? 64 : 0) + 32 * hf + 8 * gq + 4 * q2 + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = a1;
+        }
       }
-    }
-  };
-  if (big) epilogue(std::true_type{});
-  else epilogue(std::false_type{});
-  // digit planes: 16 neighbouring features = 16 bytes per plane and half
-  if (f16 < J) {
-    int8_t* oc = dst + (long long)r * pitch + f16;
-    int8_t* os = oc + J;
-    const bool full = f16 + 16 <= J;
-    if (full && ((reinterpret_cast<uintptr_t>(oc) | (uintptr_t)plane) & 15) == 0) {
+    };
+    if (big) epilogue(std::true_type{});
+    else epilogue(std::false_type{});
+    // digit planes: 8 neighbouring features = 8 bytes per plane and half (four lanes fill a 32-byte sector)
+    if (f8 < J) {
+      int8_t* oc = dst + (long long)r * pitch + f8;
+      int8_t* os = oc + J;
+      const bool full = f8 + 8 <= J;
+      if (full && ((reinterpret_cast<uintptr_t>(oc) | (uintptr_t)plane) & 7) == 0) {
 #pragma unroll
-      for (int d = 0; d < 5; ++d)
-        *reinterpret_cast<uint4*>(oc + (long long)d * plane) = make_uint4(cw[d][0], cw[d][1], cw[d][2], cw[d][3]);
-    } else {
+        for (int d = 0; d < 5; ++d) *reinterpret_cast<uint2*>(oc + (long long)d * plane) = make_uint2(cw[d][0], cw[d][1]);
+      } else {
 #pragma unroll
-      for (int d = 0; d < 5; ++d)
+        for (int d = 0; d < 5; ++d)
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          if (f16 + 4 * q4 < J) *reinterpret_cast<uint32_t*>(oc + (long long)d * plane + 4 * q4) = cw[d][q4];
-    }
-    if (full && ((reinterpret_cast<uintptr_t>(os) | (uintptr_t)plane) & 15) == 0) {
+          for (int q2 = 0; q2 < 2; ++q2)
+            if (f8 + 4 * q2 < J) *reinterpret_cast<uint32_t*>(oc + (long long)d * plane + 4 * q2) = cw[d][q2];
+      }
+      if (full && ((reinterpret_cast<uintptr_t>(os) | (uintptr_t)plane) & 7) == 0) {
 #pragma unroll
-      for (int d = 0; d < 5; ++d)
-        *reinterpret_cast<uint4*>(os + (long long)d * plane) = make_uint4(sw[d][0], sw[d][1], sw[d][2], sw[d][3]);
-    } else {
+        for (int d = 0; d < 5; ++d) *reinterpret_cast<uint2*>(os + (long long)d * plane) = make_uint2(sw[d][0], sw[d][1]);
+      } else {
 #pragma unroll
-      for (int d = 0; d < 5; ++d)
+        for (int d = 0; d < 5; ++d)
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          if (f16 + 4 * q4 < J) *reinterpret_cast<uint32_t*>(os + (long long)d * plane + 4 * q4) = sw[d][q4];
+          for (int q2 = 0; q2 < 2; ++q2)
+            if (f8 + 4 * q2 < J) *reinterpret_cast<uint32_t*>(os + (long long)d * plane + 4 * q2) = sw[d][q2];
+      }
     }
   }
   if (wsum != nullptr) {
