@@ -99,7 +99,16 @@ class _PhaseEngine:
 
     def set_data(self, X, y, n_global=None):
         self.X, self.y, self.n_global = X, np.asarray(y).reshape(-1), n_global
+        self.fullX, self.fully, self.full_global = self.X, self.y, n_global
         self.rows = X.shape[0]
+        self.batch_rows = []
+
+    def select_rows(self, idx=None, n_global=None):      # Engine.select_rows: LOCAL indices of the resident shard
+        if idx is None:
+            self.X, self.y, self.n_global = self.fullX, self.fully, self.full_global
+        else:
+            self.X, self.y, self.n_global = self.fullX[idx], self.fully[idx], n_global
+            self.batch_rows.append(len(idx))
 
     def eval(self, h, want_grad=True, **_):
         from oracle import scfgp_oracle as O
@@ -177,3 +186,62 @@ def test_facade_fit_shards_rows_over_two_ranks(tmp_path):
     np.testing.assert_allclose(z["params"], m.params, atol=1e-9)
     np.testing.assert_allclose(z["mu"], mu, atol=1e-8)
     np.testing.assert_allclose(z["sd"], sd, atol=1e-8)
+
+
+def _minibatch_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from scfgp_b200 import SCFGP
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Xtr, ytr, Xte, yte = _facade_data()
+    np.random.seed(100 + rank)                  # different shuffles per rank: rank 0's permutation must win
+    m = SCFGP(sparsity=3, nfeats=12)
+    m.set_data(Xtr, ytr)
+    m._engine = _PhaseEngine(m.D, m.S, m.M)
+    m.optimize(Xte, yte, None, None, max_iter=4, nbatches=2, batchsize=40)
+    rows = torch.tensor(m._engine.batch_rows)
+    lst = [torch.zeros_like(rows) for _ in range(world)]
+    dist.all_gather(lst, rows)
+    assert torch.equal(sum(lst), torch.full_like(rows, 40))   # every batch is split over the ranks, none lost
+    if rank == 0:
+        np.savez(out, params=m.params, cost=np.array(m.evals["COST"][1]), alpha=m.alpha)
+    dist.destroy_process_group()
+
+
+def test_facade_minibatch_mode_over_two_ranks(tmp_path):
+    """f5 under torch.distributed (SCFGP.py:172-182,226-235): rank 0's permutation is broadcast, every rank
+    gathers the rows of the batch that lie in its shard (local indices), and the all-reduced evaluation of a
+    batch equals the single-process evaluation of the same batch."""
+    from oracle import scfgp_oracle as O
+    from scfgp_b200 import SCFGP
+
+    class OracleEngine:
+        def __init__(self, D, S, M):
+            self.D, self.S, self.M = D, S, M
+
+        def set_data(self, X, y, n_global=None):
+            self.X, self.y = X, np.asarray(y).reshape(-1)
+            self.fullX, self.fully = self.X, self.y
+
+        def select_rows(self, idx=None, n_global=None):
+            self.X, self.y = (self.fullX, self.fully) if idx is None else (self.fullX[idx], self.fully[idx])
+
+        def eval(self, h, want_grad=True, **_):
+            return O.streaming_eval(h, self.X, self.y, self.S, self.M, want_grad=want_grad)
+
+        def predict(self, h, Xs, a, L):
+            return O.literal_predict(h, Xs, a, L, self.S, self.M)
+
+    out = str(tmp_path / "minibatch.npz")
+    mp.spawn(_minibatch_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    Xtr, ytr, Xte, yte = _facade_data()
+    np.random.seed(100)
+    m = SCFGP(sparsity=3, nfeats=12)
+    m.set_data(Xtr, ytr)
+    m._engine = OracleEngine(m.D, m.S, m.M)
+    m.optimize(Xte, yte, None, None, max_iter=4, nbatches=2, batchsize=40)
+    z = np.load(out)
+    np.testing.assert_allclose(z["cost"], np.array(m.evals["COST"][1]), rtol=1e-10)
+    np.testing.assert_allclose(z["params"], m.params, atol=1e-9)
+    np.testing.assert_allclose(z["alpha"], m.alpha, atol=1e-8)
