@@ -130,19 +130,19 @@ def _facade_data():
     return X[:121], y[:121, None], X[121:], y[121:, None]
 
 
-def _facade_worker(rank, world, port, out):
+def _facade_worker(rank, world, port, out, weights=None):
     sys.path.insert(0, ROOT)
-    from scfgp_b200 import SCFGP, shard_bounds
+    from scfgp_b200 import SCFGP, shard_bounds, weighted_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     Xtr, ytr, Xte, yte = _facade_data()
     np.random.seed(100 + rank)                  # different draws per rank: rank 0's must win
-    m = SCFGP(sparsity=3, nfeats=12)
+    m = SCFGP(sparsity=3, nfeats=12, shard_weights=weights)
     m.set_data(Xtr, ytr)
     m._engine = _PhaseEngine(m.D, m.S, m.M)
     m.optimize(Xte, yte, None, None, max_iter=6)
-    lo, hi = shard_bounds(len(Xtr), rank, world)
+    lo, hi = shard_bounds(len(Xtr), rank, world) if weights is None else weighted_bounds(len(Xtr), rank, weights)
     assert m._engine.rows == hi - lo and m._engine.n_global == len(Xtr)
     mu, sd = m.predict(Xte)
     if rank == 0:
@@ -153,9 +153,11 @@ def _facade_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_facade_fit_shards_rows_over_two_ranks(tmp_path):
+@pytest.mark.parametrize("weights", [None, [1.0, 2.5]])
+def test_facade_fit_shards_rows_over_two_ranks(tmp_path, weights):
     """SCFGP.set_data/optimize/predict under torch.distributed: every rank passes the same training set,
-    uploads only its row shard and follows the single-process fit started from rank 0's parameters."""
+    uploads only its row shard (equal shares, or proportional to ``shard_weights``) and follows the
+    single-process fit started from rank 0's parameters."""
     from oracle import scfgp_oracle as O
     from scfgp_b200 import SCFGP
 
@@ -173,7 +175,7 @@ def test_facade_fit_shards_rows_over_two_ranks(tmp_path):
             return O.literal_predict(h, Xs, a, L, self.S, self.M)
 
     out = str(tmp_path / "facade.npz")
-    mp.spawn(_facade_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_facade_worker, args=(2, _free_port(), out, weights), nprocs=2, join=True)
     Xtr, ytr, Xte, yte = _facade_data()
     np.random.seed(100)
     m = SCFGP(sparsity=3, nfeats=12)
